@@ -1,0 +1,176 @@
+/*
+ * vidtok_b200 -- C ABI of the B200-native VidTok causal tokenizer hot path
+ * (encode -> KL/FSQ regularize -> decode).
+ *
+ * The reference (microsoft/VidTok @ d6ad92d) has no FFI / plugin registry: the only indirection on this
+ * path is `instantiate_from_config` (vidtok/modules/util.py:69-86), which builds
+ * vidtok.models.autoencoder[_v1_1].AutoencodingEngine from a YAML `target:` string, and the engine's
+ * encode()/decode()/forward() methods (vidtok/models/autoencoder.py:197-229,
+ * vidtok/models/autoencoder_v1_1.py:230-342).  The entry points below are what a binding for THAT
+ * interface needs: one opaque model handle per (config, device), a parameter manifest that uses the
+ * reference's checkpoint key names, and encode/decode calls that take raw device pointers in the
+ * reference's tensor layout ([B,C,T,H,W], fp32).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions: plain C types only; every function returns 0 on success or a negative vt_status and
+ * records a message retrievable with vt_last_error() (thread-local).  The library never allocates
+ * caller-visible outputs: the caller owns inputs, outputs and the scratch workspace (size queried
+ * first).  All device work is enqueued on the caller's cudaStream_t (passed as void*); calls on one
+ * handle must be serialised by the caller (the reference's modules are not re-entrant either:
+ * chunk caches live on the modules, vidtok/modules/model_3dcausal_v1_1.py:155-157).
+ */
+#ifndef VIDTOK_B200_H
+#define VIDTOK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VT_MAX_LEVELS 8
+
+typedef enum {
+  VT_OK = 0,
+  VT_ERR_INVALID = -1,    /* bad argument / unsupported configuration */
+  VT_ERR_CUDA = -2,       /* CUDA runtime or driver error */
+  VT_ERR_NOT_READY = -3,  /* parameters missing or vt_model_finalize not called */
+  VT_ERR_WORKSPACE = -4,  /* workspace too small */
+  VT_ERR_NO_DEVICE = -5   /* no sm_100 device: there is deliberately no CPU fallback */
+} vt_status;
+
+/* Precision modes.  EXACT: fp32 activations, fp32 FMA accumulation (parity gate: 1e-3 max-abs, FSQ codes
+ * equal).  BF16: bf16 activations/weights on tcgen05 tensor cores with fp32 accumulation (throughput
+ * mode: PSNR within 0.01 dB). */
+#define VT_PREC_EXACT 0
+#define VT_PREC_BF16 1
+
+#define VT_NORM_LAYERNORM 0
+#define VT_NORM_GROUPNORM 1
+#define VT_REG_KL 0
+#define VT_REG_FSQ 1
+#define VT_INTERP_NEAREST 0
+#define VT_INTERP_TRILINEAR 1
+
+/* Mirrors the `encoder_config.params` block of configs/STAR.yaml plus the regularizer choice
+ * (e.g. configs/vidtok_kl_causal_488_4chn.yaml:11-36).  n_* == -1 selects the reference default
+ * (vidtok/modules/model_3dcausal.py:539-540,756-757). */
+typedef struct vt_model_desc {
+  int32_t version;                /* 0 = v1.0 (model_3dcausal.py), 1 = v1.1 (model_3dcausal_v1_1.py) */
+  int32_t ch;
+  int32_t num_levels;             /* len(ch_mult) */
+  int32_t ch_mult[VT_MAX_LEVELS];
+  int32_t num_res_blocks;
+  int32_t in_channels;
+  int32_t out_ch;
+  int32_t z_channels;
+  int32_t double_z;
+  int32_t norm_type;              /* VT_NORM_* */
+  int32_t time_downsample_factor;
+  int32_t n_spatial_ds, spatial_ds[VT_MAX_LEVELS];
+  int32_t n_tempo_ds, tempo_ds[VT_MAX_LEVELS];
+  int32_t n_spatial_us, spatial_us[VT_MAX_LEVELS];
+  int32_t n_tempo_us, tempo_us[VT_MAX_LEVELS];
+  int32_t interpolation_mode;     /* VT_INTERP_* (v1.1 only) */
+  int32_t regularizer;            /* VT_REG_* */
+  int32_t fsq_num_levels;
+  int32_t fsq_levels[VT_MAX_LEVELS];
+  int32_t kl_sample;              /* DiagonalGaussianRegularizer(sample=...) regularizers.py:75 */
+} vt_model_desc;
+
+typedef struct vt_model vt_model;
+
+const char* vt_last_error(void);
+int32_t vt_abi_version(void);
+/* number of kernels launched by this library on this thread since the last call with reset != 0 */
+int64_t vt_launch_count(int32_t reset);
+
+/* ---- model lifetime (replaces AutoencodingEngine.__init__, autoencoder.py:103-144) ---- */
+int32_t vt_model_create(const vt_model_desc* desc, int32_t device, vt_model** out);
+void vt_model_destroy(vt_model* m);
+
+/* Parameter manifest: names are the reference checkpoint keys ("encoder.conv_in.conv.weight", ...;
+ * SURVEY.md section 8b), shapes are the reference's (OIDHW / OIHW / OIW / [C] / [1]). */
+int32_t vt_model_num_params(const vt_model* m);
+int32_t vt_model_param_info(const vt_model* m, int32_t index, char* name, int32_t name_cap, int64_t* shape5,
+                            int32_t* ndim);
+/* Copies one fp32 parameter (host or device pointer, `numel` floats) into the model
+ * (replaces load_state_dict, autoencoder.py:164). */
+int32_t vt_model_load_param(vt_model* m, const char* name, const float* data, int64_t numel, int32_t is_device,
+                            void* stream);
+/* Repacks all parameters for the kernels (K-major bf16 tiles for tcgen05, [K][Cout] fp32 for the FMA
+ * path).  Must be called after the last vt_model_load_param and before encode/decode. */
+int32_t vt_model_finalize(vt_model* m, void* stream);
+
+/* ---- whole-clip path (AutoencodingEngine.encode/decode, autoencoder.py:197-219;
+ *      untiled v1.1: autoencoder_v1_1.py:230-241,286-300) ---- */
+/* Latent geometry for an input of T x H x W: frames (after the encoder's front padding), height, width. */
+int32_t vt_latent_shape(const vt_model* m, int32_t T, int32_t H, int32_t W, int32_t* Tz, int32_t* Hz, int32_t* Wz);
+/* Number of frames decode() returns for Tz latent frames (v1.0 drops tdf-1, model_3dcausal.py:885). */
+int32_t vt_decoded_frames(const vt_model* m, int32_t Tz);
+int64_t vt_workspace_bytes(const vt_model* m, int32_t precision, int32_t B, int32_t T, int32_t H, int32_t W);
+
+/* x: device fp32 [B,in_channels,T,H,W].  noise: device fp32 [B,z,Tz,Hz,Wz] = the reference's
+ * torch.randn(mean.shape) (distributions.py:17), required for KL with kl_sample, else NULL.
+ * Outputs (device, caller-allocated): z fp32 [B,z,Tz,Hz,Wz]; indices int32 [B,Tz,Hz,Wz] (FSQ, may be
+ * NULL); kl_loss 1 float (KL, may be NULL); h_pre fp32 [B,2z|z,Tz,Hz,Wz] encoder output before the
+ * regularizer (may be NULL). */
+int32_t vt_encode(vt_model* m, int32_t precision, const float* x, int32_t B, int32_t T, int32_t H, int32_t W,
+                  const float* noise, float* z, int32_t* indices, float* kl_loss, float* h_pre, void* workspace,
+                  int64_t workspace_bytes, void* stream);
+/* z: device fp32 [B,z,Tz,Hz,Wz], or (from_indices) int32 [B,Tz,Hz,Wz] (autoencoder.py:205-217).
+ * x_out: device fp32 [B,out_ch,vt_decoded_frames(Tz),Hz*s,Wz*s]. */
+int32_t vt_decode(vt_model* m, int32_t precision, const void* z, int32_t from_indices, int32_t B, int32_t Tz,
+                  int32_t Hz, int32_t Wz, float* x_out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- temporal tiling with causal caches (v1.1: tile_encode / tile_decode,
+ *      autoencoder_v1_1.py:244-264,302-331; per-layer caches model_3dcausal_v1_1.py:159-178,216-236,
+ *      289-302,325-343).  One state object per in-flight video. ---- */
+typedef struct vt_chunk_state vt_chunk_state;
+int32_t vt_chunk_state_create(vt_model* m, int32_t precision, int32_t B, int32_t H, int32_t W, int32_t is_decoder,
+                              int32_t use_overlap, vt_chunk_state** out);
+void vt_chunk_state_destroy(vt_chunk_state* s);
+int64_t vt_chunk_workspace_bytes(const vt_chunk_state* s, int32_t T_chunk);
+/* x_chunk: device fp32 [B,C,Tc,H,W] (dense).  Outputs as vt_encode, for this chunk only. */
+int32_t vt_encode_chunk(vt_chunk_state* s, int32_t is_first, const float* x_chunk, int32_t Tc, const float* noise,
+                        float* z, int32_t* indices, float* kl_loss, void* workspace, int64_t workspace_bytes,
+                        void* stream);
+/* z_chunk: device fp32 [B,z,Tzc,Hz,Wz] including the look-ahead frame when overlap applies; x_out receives
+ * all decoded frames of this chunk (the caller trims the look-ahead tail as autoencoder_v1_1.py:327-328). */
+int32_t vt_decode_chunk(vt_chunk_state* s, int32_t is_first, const float* z_chunk, int32_t Tzc, float* x_out,
+                        void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- single operators, exposed for the parity tests (same kernels the model path launches) ---- */
+typedef struct vt_conv_desc {
+  int32_t B, Ti, Hi, Wi, Ci;        /* input, channels-last [B,Ti,Hi,Wi,Ci] */
+  int32_t Co, kt, kh, kw;
+  int32_t st, sh, sw;               /* strides */
+  int32_t pt;                       /* causal front pad in time (zeros) */
+  int32_t ph0, ph1, pw0, pw1;       /* spatial zero pads (top,bottom,left,right) */
+  int32_t ut, uh, uw;               /* nearest-neighbour upsampling of the input folded into the gather */
+  int32_t res_mode;                 /* 0 none, 1 out = conv + res, 2 out = a*res[t/2] + (1-a)*conv, 3 out = a*avgpool3(res) + (1-a)*conv */
+  float alpha;
+} vt_conv_desc;
+/* x/res/out are channels-last activations in the precision's activation type (fp32 or bf16);
+ * w fp32 [Co,Ci,kt,kh,kw]; bias fp32 [Co].  force_simt != 0 runs the FMA kernel even in BF16 mode. */
+int32_t vt_op_conv(int32_t precision, int32_t force_simt, const vt_conv_desc* d, const void* x, const float* w,
+                   const float* bias, const void* res, void* out, void* stream);
+/* y = silu?(norm(x)) over channels-last x [rows, C]; groupnorm variants take frame geometry. */
+int32_t vt_op_layernorm(int32_t precision, const void* x, const float* gamma, const float* beta, void* y,
+                        int64_t rows, int32_t C, int32_t apply_silu, void* stream);
+int32_t vt_op_groupnorm(int32_t precision, const void* x, const float* gamma, const float* beta, void* y,
+                        int64_t frames, int64_t positions_per_frame, int32_t C, int32_t per_position,
+                        int32_t apply_silu, void* workspace, int64_t workspace_bytes, void* stream);
+/* per-frame single-head attention core: q,k,v,o channels-last [frames, tokens, C]; scale = C^-0.5 */
+int32_t vt_op_attention(int32_t precision, const void* q, const void* k, const void* v, void* o, int32_t frames,
+                        int32_t tokens, int32_t C, void* workspace, int64_t workspace_bytes, void* stream);
+int32_t vt_op_fsq(const float* h, int32_t d, const int32_t* levels, int64_t positions_per_batch, int32_t B,
+                  float* codes, int32_t* indices, void* stream);
+int32_t vt_op_fsq_indices_to_codes(const int32_t* indices, int32_t d, const int32_t* levels,
+                                   int64_t positions_per_batch, int32_t B, float* codes, void* stream);
+int32_t vt_op_kl(const float* h, const float* noise, int32_t zc, int64_t positions_per_batch, int32_t B, int32_t sample,
+                 float* z, float* kl_loss, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIDTOK_B200_H */

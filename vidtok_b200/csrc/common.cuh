@@ -1,0 +1,89 @@
+// Shared device/host definitions for the vidtok_b200 kernels.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vt {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- per-thread launch counter (vt_launch_count) -------------------------------------------------
+extern thread_local long long g_launches;
+inline void count_launch(int n = 1) { g_launches += n; }
+
+// ---- element helpers ------------------------------------------------------------------------------
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// load 4 consecutive elements as floats (pointer must be 4-element aligned)
+__device__ __forceinline__ void load4(const float* p, float (&o)[4]) {
+  float4 v = *reinterpret_cast<const float4*>(p);
+  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+__device__ __forceinline__ void load4(const bf16* p, float (&o)[4]) {
+  uint2 v = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&v.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&v.y);
+  o[0] = __low2float(a); o[1] = __high2float(a); o[2] = __low2float(b); o[3] = __high2float(b);
+}
+__device__ __forceinline__ void store4(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store4(bf16* p, const float (&v)[4]) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// accurate variant for the EXACT mode (expf, not the fast intrinsic)
+__device__ __forceinline__ float silu_exact(float x) { return x * (1.0f / (1.0f + expf(-x))); }
+
+// ---- generalized causal convolution geometry --------------------------------------------------------
+// One struct describes every convolution on the path:
+//   CausalConv3d / CausalConv1d (model_3dcausal.py:144-197), per-frame Conv2d of ResnetBlock (:296-306),
+//   Downsample (:223-230, asymmetric zero pad + stride 2), Upsample (:208-212, nearest 2x folded into the
+//   gather), TimeUpsampleResCausal2x (:267-273, nearest 2x in T folded), TimeDownsampleResCausal2x (:247-252),
+//   the encoder's replicate front padding (:685-689) and the decoder's dropped frames (:883-885).
+// Virtual input time axis (length t_rep + ut*Ti): [t_rep copies of frame 0][frames upsampled ut times].
+// Output (to,ho,wo), tap (a,b,c) reads virtual coordinate
+//   tv = (to + to_off)*st + a - pt ; hv = ho*sh + b - ph ; wv = wo*sw + c - pw
+// tv < 0 : zero (t_mode 0), frame 0 (t_mode 1, v1.1 first chunk) or cache frame cacheT+tv (t_mode 2);
+// hv/wv outside [0, uh*Hi) x [0, uw*Wi) : zero.  Source = (max(tv - t_rep,0)/ut, hv/uh, wv/uw).
+struct ConvP {
+  int B, Ti, Hi, Wi, Ci;
+  long long isB, isT, isH, isW, isC;  // input element strides
+  int To, Ho, Wo, Co;
+  long long osB, osT, osH, osW, osC;  // output element strides
+  int to_off;
+  int kt, kh, kw, st, sh, sw;
+  int pt, ph, pw;
+  int ut, uh, uw;
+  int t_rep;
+  int t_mode;
+  const void* cache;                  // [B, cacheT, Hi, Wi, Ci] channels-last, same type as input
+  int cacheT;
+  // epilogue: out = rb * (acc + bias) + ra * R
+  const float* bias;
+  int res_mode;                       // 0 none, 1 same index, 2 R[t/2] (time-upsample mix), 3 avgpool3 over R frames 2t-1..2t+1
+  const void* res;
+  long long rsB, rsT, rsH, rsW;       // residual element strides (channel stride 1)
+  int resT;                           // residual frame count (mode 3 bounds)
+  int res_t_mode;                     // mode 3 front pad: 0 zero (v1.0), 1 replicate frame 0, 2 res_cache (1 frame)
+  const void* res_cache;              // [B,1,H,W,C]
+  float ra, rb;
+};
+
+struct ConvLaunch {  // host-side convenience
+  long long M;       // B*To*Ho*Wo
+  int K;             // kt*kh*kw*Ci
+};
+
+}  // namespace vt
