@@ -477,7 +477,8 @@ class OracleModel:
             log = {"kl_loss": torch.mean(torch.stack([d["kl_loss"] for d in logs]))}
         else:  # :261-264
             log = {"aux_loss": torch.mean(torch.stack([d["aux_loss"] for d in logs])),
-                   "indices": torch.cat([d["indices"] for d in logs], dim=1)}
+                   "indices": torch.cat([d["indices"] for d in logs], dim=1),
+                   "pre_round": torch.cat([d["pre_round"] for d in logs], dim=1)}
         return (z, log, torch.cat(hs, dim=2)) if return_pre else (z, log)
 
     @torch.no_grad()

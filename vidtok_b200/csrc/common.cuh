@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#define VT_MAX_FSQ 8
+
 namespace vt {
 
 typedef __nv_bfloat16 bf16;

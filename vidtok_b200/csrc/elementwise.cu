@@ -1,0 +1,577 @@
+// Bandwidth-bound kernels of the path: per-position LayerNorm(+SiLU), GroupNorm(+SiLU), softmax rows,
+// KL reparameterisation, FSQ quantiser, weight repacking, trilinear time interpolation.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vt {
+
+thread_local long long g_launches = 0;
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+template <bool EXACT> __device__ __forceinline__ float act_silu(float x) {
+  return EXACT ? silu_exact(x) : silu_f(x);
+}
+
+// ---- LayerNorm over channels (model_3dcausal.py:62-80; eps 1e-6, affine), optional SiLU (:26-27) --------
+// One warp per position; VPL vectors of 4 channels per lane held in registers (C == 128*VPL).
+template <typename T, int VPL, bool SILU, bool EXACT>
+__global__ void __launch_bounds__(256) layernorm_vec_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, T* __restrict__ y,
+                                                            long long rows) {
+  constexpr int C = 128 * VPL;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const T* xr = x + row * C;
+  float v[VPL][4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    load4(xr + (i * 32 + lane) * 4, v[i]);
+    s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
+  }
+  const float mean = warp_sum(s) * (1.0f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float d = v[i][j] - mean;
+      q = fmaf(d, d, q);
+    }
+  const float var = warp_sum(q) * (1.0f / C);
+  const float rstd = EXACT ? (1.0f / sqrtf(var + 1e-6f)) : rsqrtf(var + 1e-6f);
+  T* yr = y + row * C;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    float g[4], b[4], o[4];
+    load4(gamma + c, g);
+    load4(beta + c, b);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float t = (v[i][j] - mean) * rstd * g[j] + b[j];
+      o[j] = SILU ? act_silu<EXACT>(t) : t;
+    }
+    store4(yr + c, o);
+  }
+}
+
+// generic C (tiny test models): one warp per position, strided scalar access
+template <typename T, bool SILU, bool EXACT>
+__global__ void __launch_bounds__(256) layernorm_gen_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, T* __restrict__ y,
+                                                            long long rows, int C) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const T* xr = x + row * C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += to_f(xr[c]);
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    float d = to_f(xr[c]) - mean;
+    q = fmaf(d, d, q);
+  }
+  const float var = warp_sum(q) / C;
+  const float rstd = 1.0f / sqrtf(var + 1e-6f);
+  T* yr = y + row * C;
+  for (int c = lane; c < C; c += 32) {
+    float t = (to_f(xr[c]) - mean) * rstd * gamma[c] + beta[c];
+    yr[c] = from_f<T>(SILU ? act_silu<EXACT>(t) : t);
+  }
+}
+
+// ---- GroupNorm(32 groups, eps 1e-6) per frame (model_3dcausal.py:30-32 applied on `(b t) c h w`) -----------
+// stats pass: one block per (frame, group): two-pass mean / variance over (positions x C/32)
+template <typename T>
+__global__ void __launch_bounds__(256) groupnorm_stats_kernel(const T* __restrict__ x, float* __restrict__ stats,
+                                                              long long pos_per_frame, int C) {
+  const int cpg = C / 32;
+  const long long frame = blockIdx.x / 32;
+  const int g = blockIdx.x % 32;
+  const T* base = x + frame * pos_per_frame * C + g * cpg;
+  const long long n = pos_per_frame * cpg;
+  __shared__ float red[32];
+  __shared__ float bc;
+  auto block_sum = [&](float v) -> float {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+      t = warp_sum(t);
+      if (threadIdx.x == 0) bc = t;
+    }
+    __syncthreads();
+    float r = bc;
+    __syncthreads();
+    return r;
+  };
+  float s = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) s += to_f(base[(i / cpg) * C + (i % cpg)]);
+  const float mean = block_sum(s) / (float)n;
+  float q = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    float d = to_f(base[(i / cpg) * C + (i % cpg)]) - mean;
+    q = fmaf(d, d, q);
+  }
+  const float var = block_sum(q) / (float)n;
+  if (threadIdx.x == 0) {
+    stats[2 * blockIdx.x] = mean;
+    stats[2 * blockIdx.x + 1] = 1.0f / sqrtf(var + 1e-6f);
+  }
+}
+template <typename T, bool SILU, bool EXACT>
+__global__ void __launch_bounds__(256) groupnorm_apply_kernel(const T* __restrict__ x, const float* __restrict__ stats,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, T* __restrict__ y,
+                                                              long long total, long long pos_per_frame, int C) {
+  const int cpg = C / 32;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long frame = (i / C) / pos_per_frame;
+    const float* st = stats + 2 * (frame * 32 + c / cpg);
+    float t = (to_f(x[i]) - st[0]) * st[1] * gamma[c] + beta[c];
+    y[i] = from_f<T>(SILU ? act_silu<EXACT>(t) : t);
+  }
+}
+// per-position variant: statistics over the C/32 channels of one position (the temporal 1D blocks,
+// model_3dcausal.py:474-480 -- see oracle/vidtok_oracle.py:norm)
+template <typename T, bool SILU, bool EXACT>
+__global__ void __launch_bounds__(256) groupnorm_pos_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, T* __restrict__ y,
+                                                            long long npos, int C) {
+  const int cpg = C / 32;
+  const long long total = npos * 32;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pos = i / 32;
+    const int g = (int)(i % 32);
+    const T* xr = x + pos * C + g * cpg;
+    float s = 0.f;
+    for (int c = 0; c < cpg; ++c) s += to_f(xr[c]);
+    const float mean = s / cpg;
+    float q = 0.f;
+    for (int c = 0; c < cpg; ++c) {
+      float d = to_f(xr[c]) - mean;
+      q = fmaf(d, d, q);
+    }
+    const float rstd = 1.0f / sqrtf(q / cpg + 1e-6f);
+    T* yr = y + pos * C + g * cpg;
+    for (int c = 0; c < cpg; ++c) {
+      float t = (to_f(xr[c]) - mean) * rstd * gamma[g * cpg + c] + beta[g * cpg + c];
+      yr[c] = from_f<T>(SILU ? act_silu<EXACT>(t) : t);
+    }
+  }
+}
+
+// ---- softmax over rows of fp32 scores -> P (attention, model_3dcausal.py:140) -----------------------------
+template <typename TOut>
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ S, TOut* __restrict__ P, int N) {
+  const float* s = S + (long long)blockIdx.x * N;
+  TOut* p = P + (long long)blockIdx.x * N;
+  __shared__ float red[8];
+  __shared__ float bc;
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < N; i += 256) m = fmaxf(m, s[i]);
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < 8 ? red[threadIdx.x] : -INFINITY;
+    t = warp_max(t);
+    if (threadIdx.x == 0) bc = t;
+  }
+  __syncthreads();
+  m = bc;
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < N; i += 256) sum += expf(s[i] - m);
+  sum = warp_sum(sum);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) bc = t;
+  }
+  __syncthreads();
+  const float inv = 1.0f / bc;
+  for (int i = threadIdx.x; i < N; i += 256) p[i] = from_f<TOut>(expf(s[i] - m) * inv);
+}
+
+// ---- KL: DiagonalGaussianDistribution (distributions.py:5-28) + regularizer (regularizers.py:82-92) ------
+// h [B,2z,P] fp32 (NCDHW flattened), noise/z [B,z,P]
+__global__ void __launch_bounds__(256) kl_kernel(const float* __restrict__ h, const float* __restrict__ noise, int zc,
+                                                 long long P, int B, int sample, float* __restrict__ z,
+                                                 double* __restrict__ kl_acc) {
+  const long long total = (long long)B * zc * P;
+  double local = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / (zc * P), r = i % (zc * P);
+    const float mean = h[b * 2 * zc * P + r];
+    float logvar = h[b * 2 * zc * P + zc * P + r];
+    logvar = fminf(fmaxf(logvar, -30.0f), 20.0f);
+    const float stdv = expf(0.5f * logvar);
+    const float var = expf(logvar);
+    z[i] = sample ? __fadd_rn(mean, __fmul_rn(stdv, noise[i])) : mean;
+    local += (double)(mean * mean + var - 1.0f - logvar);
+  }
+  __shared__ double red[8];
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    atomicAdd(kl_acc, t);
+  }
+}
+__global__ void kl_finish_kernel(const double* acc, int B, float* out) { *out = (float)(0.5 * acc[0] / B); }
+
+// ---- FSQ: bound -> round -> index (regularizers.py:153-178,206-262) --------------------------------------
+struct FsqConst {
+  int d;
+  float half_l[VT_MAX_FSQ], offset[VT_MAX_FSQ], shift[VT_MAX_FSQ], half_w[VT_MAX_FSQ];
+  int levels[VT_MAX_FSQ], basis[VT_MAX_FSQ];
+};
+__global__ void __launch_bounds__(256) fsq_kernel(const float* __restrict__ h, FsqConst c, long long P, int B,
+                                                  float* __restrict__ codes, int* __restrict__ indices) {
+  const long long total = (long long)B * P;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / P, pos = i % P;
+    float idx = 0.f;
+    for (int k = 0; k < c.d; ++k) {
+      const float zv = h[(b * c.d + k) * P + pos];
+      // fp32 op-by-op as the reference: tanh(z + shift) * half_l - offset, no FMA contraction
+      const float t = (float)tanh((double)__fadd_rn(zv, c.shift[k]));
+      const float bounded = __fsub_rn(__fmul_rn(t, c.half_l[k]), c.offset[k]);
+      const float q = rintf(bounded);  // half-to-even, torch.round
+      const float code = __fdiv_rn(q, c.half_w[k]);
+      codes[(b * c.d + k) * P + pos] = code;
+      idx = __fadd_rn(idx, __fmul_rn(__fadd_rn(__fmul_rn(code, c.half_w[k]), c.half_w[k]), (float)c.basis[k]));
+    }
+    if (indices) indices[i] = (int)idx;
+  }
+}
+__global__ void __launch_bounds__(256) fsq_i2c_kernel(const int* __restrict__ indices, FsqConst c, long long P, int B,
+                                                      float* __restrict__ codes) {
+  const long long total = (long long)B * P;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / P, pos = i % P;
+    const int idx = indices[i];
+    for (int k = 0; k < c.d; ++k) {
+      const int dgt = (idx / c.basis[k]) % c.levels[k];
+      const int hw = c.levels[k] / 2;
+      codes[(b * c.d + k) * P + pos] = (float)(dgt - hw) / (float)hw;
+    }
+  }
+}
+FsqConst make_fsq_const(int d, const int* levels) {
+  FsqConst c;
+  c.d = d;
+  int basis = 1;
+  for (int k = 0; k < d; ++k) {
+    const int L = levels[k];
+    c.levels[k] = L;
+    c.basis[k] = basis;
+    basis *= L;
+    // regularizers.py:155-157, evaluated in fp32 like torch does for an int32 tensor times a python float
+    const float half_l = ((float)(L - 1) * (float)(1.0 + 1e-3)) / 2.0f;
+    const float offset = (L % 2 == 0) ? 0.5f : 0.0f;
+    c.half_l[k] = half_l;
+    c.offset[k] = offset;
+    c.shift[k] = atanhf(offset / half_l);
+    c.half_w[k] = (float)(L / 2);
+  }
+  return c;
+}
+
+// ---- weight repacking -------------------------------------------------------------------------------------
+__global__ void pack_w_kn_kernel(const float* __restrict__ w, float* __restrict__ out, int Co, int Ci, int taps) {
+  const long long total = (long long)Co * Ci * taps;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Co);
+    const long long k = i / Co;
+    const int tap = (int)(k / Ci), ci = (int)(k % Ci);
+    out[i] = w[((long long)co * Ci + ci) * taps + tap];
+  }
+}
+__global__ void pack_w_nk_bf16_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Co, int Ci, int taps,
+                                      int Kpad) {
+  const long long total = (long long)Co * Kpad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % Kpad);
+    const int co = (int)(i / Kpad);
+    float v = 0.f;
+    if (k < Ci * taps) {
+      const int tap = k / Ci, ci = k % Ci;
+      v = w[((long long)co * Ci + ci) * taps + tap];
+    }
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// ---- trilinear 2x along T (F.interpolate(scale_factor=[2,1,1], mode="trilinear"), model_3dcausal_v1_1.py:328-339)
+template <typename T>
+__global__ void __launch_bounds__(256) time_interp2x_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int Tn,
+                                                            long long hwc) {
+  const long long total = (long long)B * 2 * Tn * hwc;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i % hwc;
+    const long long r = i / hwc;
+    const int j = (int)(r % (2 * Tn));
+    const long long b = r / (2 * Tn);
+    float src = 0.5f * ((float)j + 0.5f) - 0.5f;
+    src = src < 0.f ? 0.f : src;
+    const int i0 = (int)src;
+    const int i1 = i0 + ((i0 < Tn - 1) ? 1 : 0);
+    const float l1 = src - (float)i0, l0 = 1.0f - l1;
+    const float a = to_f(x[(b * Tn + i0) * hwc + e]);
+    const float c = to_f(x[(b * Tn + i1) * hwc + e]);
+    y[i] = from_f<T>(__fadd_rn(__fmul_rn(l0, a), __fmul_rn(l1, c)));
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) copy_frames_kernel(const T* __restrict__ src, T* __restrict__ dst, int B,
+                                                          long long src_bs, long long dst_bs, long long n) {
+  const long long total = (long long)B * n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / n, e = i % n;
+    dst[b * dst_bs + e] = src[b * src_bs + e];
+  }
+}
+
+// nearest-neighbour upsampling (F.interpolate(mode="nearest"), model_3dcausal.py:209,269) of channels-last x
+template <typename T>
+__global__ void __launch_bounds__(256) upsample_nearest_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int Tn,
+                                                               int H, int W, int C4, int ut, int uh, int uw) {
+  // C4 = C/4 vectors of 4 channels
+  const long long total = (long long)B * Tn * ut * H * uh * W * uw * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4);
+    long long r = i / C4;
+    const int w = (int)(r % (W * uw)); r /= (W * uw);
+    const int h = (int)(r % (H * uh)); r /= (H * uh);
+    const int t = (int)(r % (Tn * ut));
+    const long long b = r / (Tn * ut);
+    const long long src = ((((b * Tn + t / ut) * H + h / uh) * W + w / uw) * C4 + c) * 4;
+    float v[4];
+    load4(x + src, v);
+    store4(y + i * 4, v);
+  }
+}
+// external fp32 [B,C,T,H,W] -> channels-last [B,t_rep+T,H,W,C] with the first frame replicated t_rep times
+// (EncoderCausal3DPadding.forward, model_3dcausal_v1_1.py:755-760)
+template <typename T>
+__global__ void __launch_bounds__(256) ncdhw_to_cl_kernel(const float* __restrict__ x, T* __restrict__ y, int B, int C,
+                                                          int Tn, long long hw, int t_rep) {
+  const long long total = (long long)B * (Tn + t_rep) * hw * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const long long p = r % hw; r /= hw;
+    int t = (int)(r % (Tn + t_rep)) - t_rep;
+    const long long b = r / (Tn + t_rep);
+    t = t < 0 ? 0 : t;
+    y[i] = from_f<T>(x[((b * C + c) * Tn + t) * hw + p]);
+  }
+}
+// v1.1 causal cache update (model_3dcausal_v1_1.py:159-176,216-233): with xp = [pad (P frames)][x (Tc frames)],
+// new_cache[j] = xp[Tc - off + j], j in [0,P); pad = frame 0 of x (first chunk) or the old cache.
+template <typename T>
+__global__ void __launch_bounds__(256) cache_update_kernel(const T* __restrict__ x, const T* __restrict__ old_cache,
+                                                           T* __restrict__ new_cache, int B, int Tc, int P, int off,
+                                                           int first, long long fe, long long xbs) {
+  const long long total = (long long)B * P * fe;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i % fe;
+    const long long r = i / fe;
+    const int j = (int)(r % P);
+    const long long b = r / P;
+    const int idx = Tc - off + j;
+    T v;
+    if (idx >= P) v = x[b * xbs + (idx - P) * fe + e];
+    else if (first) v = x[b * xbs + e];
+    else v = old_cache[(b * P + (idx < 0 ? 0 : idx)) * fe + e];
+    new_cache[i] = v;
+  }
+}
+
+inline int grid_for(long long total, int block = 256) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148LL * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+cudaError_t launch_layernorm(DType t, const void* x, const float* gamma, const float* beta, void* y, long long rows,
+                             int C, bool silu, bool exact, cudaStream_t s) {
+  const int wpb = 8;
+  const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+  if (rows == 0) return cudaSuccess;
+#define VT_LN_VEC(T, VPL)                                                                                            \
+  do {                                                                                                               \
+    if (silu && exact) layernorm_vec_kernel<T, VPL, true, true><<<grid, 256, 0, s>>>((const T*)x, gamma, beta, (T*)y, rows);        \
+    else if (silu) layernorm_vec_kernel<T, VPL, true, false><<<grid, 256, 0, s>>>((const T*)x, gamma, beta, (T*)y, rows);           \
+    else if (exact) layernorm_vec_kernel<T, VPL, false, true><<<grid, 256, 0, s>>>((const T*)x, gamma, beta, (T*)y, rows);          \
+    else layernorm_vec_kernel<T, VPL, false, false><<<grid, 256, 0, s>>>((const T*)x, gamma, beta, (T*)y, rows);                    \
+  } while (0)
+#define VT_LN_GEN(T)                                                                                                 \
+  do {                                                                                                               \
+    if (silu) layernorm_gen_kernel<T, true, true><<<grid, 256, 0, s>>>((const T*)x, gamma, beta, (T*)y, rows, C);    \
+    else layernorm_gen_kernel<T, false, true><<<grid, 256, 0, s>>>((const T*)x, gamma, beta, (T*)y, rows, C);        \
+  } while (0)
+  if (t == DT_F32) {
+    if (C == 128) VT_LN_VEC(float, 1);
+    else if (C == 256) VT_LN_VEC(float, 2);
+    else if (C == 512) VT_LN_VEC(float, 4);
+    else VT_LN_GEN(float);
+  } else {
+    if (C == 128) VT_LN_VEC(bf16, 1);
+    else if (C == 256) VT_LN_VEC(bf16, 2);
+    else if (C == 512) VT_LN_VEC(bf16, 4);
+    else VT_LN_GEN(bf16);
+  }
+#undef VT_LN_VEC
+#undef VT_LN_GEN
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_groupnorm(DType t, const void* x, const float* gamma, const float* beta, void* y, long long frames,
+                             long long ppf, int C, bool per_position, bool silu, bool exact, float* stats,
+                             cudaStream_t s) {
+  if (C % 32 != 0) return cudaErrorInvalidValue;
+  const long long total = frames * ppf * C;
+  if (total == 0) return cudaSuccess;
+#define VT_GN(T)                                                                                                      \
+  do {                                                                                                                \
+    if (per_position) {                                                                                               \
+      const int g = grid_for(frames * ppf * 32);                                                                      \
+      if (silu) groupnorm_pos_kernel<T, true, true><<<g, 256, 0, s>>>((const T*)x, gamma, beta, (T*)y, frames * ppf, C); \
+      else groupnorm_pos_kernel<T, false, true><<<g, 256, 0, s>>>((const T*)x, gamma, beta, (T*)y, frames * ppf, C);  \
+      count_launch();                                                                                                 \
+    } else {                                                                                                          \
+      groupnorm_stats_kernel<T><<<(unsigned)(frames * 32), 256, 0, s>>>((const T*)x, stats, ppf, C);                  \
+      const int g = grid_for(total);                                                                                  \
+      if (silu) groupnorm_apply_kernel<T, true, true><<<g, 256, 0, s>>>((const T*)x, stats, gamma, beta, (T*)y, total, ppf, C); \
+      else groupnorm_apply_kernel<T, false, true><<<g, 256, 0, s>>>((const T*)x, stats, gamma, beta, (T*)y, total, ppf, C);     \
+      count_launch(2);                                                                                                \
+    }                                                                                                                 \
+  } while (0)
+  (void)exact;
+  if (t == DT_F32) VT_GN(float);
+  else VT_GN(bf16);
+#undef VT_GN
+  return cudaGetLastError();
+}
+
+cudaError_t launch_softmax_rows(DType tout, const float* S, void* P, long long rows, int N, cudaStream_t s) {
+  if (rows == 0) return cudaSuccess;
+  if (tout == DT_F32) softmax_rows_kernel<float><<<(unsigned)rows, 256, 0, s>>>(S, (float*)P, N);
+  else softmax_rows_kernel<bf16><<<(unsigned)rows, 256, 0, s>>>(S, (bf16*)P, N);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_kl(const float* h, const float* noise, int zc, long long P, int B, bool sample, float* z,
+                      float* kl_loss, double* scratch, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(double), s);
+  if (e != cudaSuccess) return e;
+  kl_kernel<<<grid_for((long long)B * zc * P), 256, 0, s>>>(h, noise, zc, P, B, sample ? 1 : 0, z, scratch);
+  count_launch();
+  if (kl_loss) {
+    kl_finish_kernel<<<1, 1, 0, s>>>(scratch, B, kl_loss);
+    count_launch();
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fsq(const float* h, int d, const int* levels, long long P, int B, float* codes, int* indices,
+                       cudaStream_t s) {
+  if (d > VT_MAX_FSQ) return cudaErrorInvalidValue;
+  FsqConst c = make_fsq_const(d, levels);
+  fsq_kernel<<<grid_for((long long)B * P), 256, 0, s>>>(h, c, P, B, codes, indices);
+  count_launch();
+  return cudaGetLastError();
+}
+cudaError_t launch_fsq_indices_to_codes(const int* indices, int d, const int* levels, long long P, int B, float* codes,
+                                        cudaStream_t s) {
+  if (d > VT_MAX_FSQ) return cudaErrorInvalidValue;
+  FsqConst c = make_fsq_const(d, levels);
+  fsq_i2c_kernel<<<grid_for((long long)B * P), 256, 0, s>>>(indices, c, P, B, codes);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_w_kn(const float* w, float* out, int Co, int Ci, int taps, cudaStream_t s) {
+  pack_w_kn_kernel<<<grid_for((long long)Co * Ci * taps), 256, 0, s>>>(w, out, Co, Ci, taps);
+  count_launch();
+  return cudaGetLastError();
+}
+cudaError_t launch_pack_w_nk_bf16(const float* w, bf16* out, int Co, int Ci, int taps, int Kpad, cudaStream_t s) {
+  pack_w_nk_bf16_kernel<<<grid_for((long long)Co * Kpad), 256, 0, s>>>(w, out, Co, Ci, taps, Kpad);
+  count_launch();
+  return cudaGetLastError();
+}
+cudaError_t launch_time_interp2x(DType t, const void* x, void* y, int B, int T, long long hwc, cudaStream_t s) {
+  const long long total = (long long)B * 2 * T * hwc;
+  if (total == 0) return cudaSuccess;
+  if (t == DT_F32) time_interp2x_kernel<float><<<grid_for(total), 256, 0, s>>>((const float*)x, (float*)y, B, T, hwc);
+  else time_interp2x_kernel<bf16><<<grid_for(total), 256, 0, s>>>((const bf16*)x, (bf16*)y, B, T, hwc);
+  count_launch();
+  return cudaGetLastError();
+}
+cudaError_t launch_upsample_nearest(DType t, const void* x, void* y, int B, int T, int H, int W, int C, int ut, int uh,
+                                    int uw, cudaStream_t s) {
+  if (C % 4 != 0) return cudaErrorInvalidValue;
+  const long long total = (long long)B * T * ut * H * uh * W * uw * (C / 4);
+  if (total == 0) return cudaSuccess;
+  if (t == DT_F32) upsample_nearest_kernel<float><<<grid_for(total), 256, 0, s>>>((const float*)x, (float*)y, B, T, H, W, C / 4, ut, uh, uw);
+  else upsample_nearest_kernel<bf16><<<grid_for(total), 256, 0, s>>>((const bf16*)x, (bf16*)y, B, T, H, W, C / 4, ut, uh, uw);
+  count_launch();
+  return cudaGetLastError();
+}
+cudaError_t launch_ncdhw_to_cl(DType t, const float* x, void* y, int B, int C, int T, int H, int W, int t_rep,
+                               cudaStream_t s) {
+  const long long total = (long long)B * (T + t_rep) * H * W * C;
+  if (total == 0) return cudaSuccess;
+  if (t == DT_F32) ncdhw_to_cl_kernel<float><<<grid_for(total), 256, 0, s>>>(x, (float*)y, B, C, T, (long long)H * W, t_rep);
+  else ncdhw_to_cl_kernel<bf16><<<grid_for(total), 256, 0, s>>>(x, (bf16*)y, B, C, T, (long long)H * W, t_rep);
+  count_launch();
+  return cudaGetLastError();
+}
+cudaError_t launch_cache_update(DType t, const void* x, const void* old_cache, void* new_cache, int B, int Tc, int P,
+                                int off, bool first, long long frame_elems, long long x_bs, cudaStream_t s) {
+  const long long total = (long long)B * P * frame_elems;
+  if (total == 0) return cudaSuccess;
+  if (t == DT_F32) cache_update_kernel<float><<<grid_for(total), 256, 0, s>>>((const float*)x, (const float*)old_cache, (float*)new_cache, B, Tc, P, off, first ? 1 : 0, frame_elems, x_bs);
+  else cache_update_kernel<bf16><<<grid_for(total), 256, 0, s>>>((const bf16*)x, (const bf16*)old_cache, (bf16*)new_cache, B, Tc, P, off, first ? 1 : 0, frame_elems, x_bs);
+  count_launch();
+  return cudaGetLastError();
+}
+cudaError_t launch_copy_frames(DType t, const void* src, void* dst, int B, long long src_bs, long long dst_bs,
+                               long long n, cudaStream_t s) {
+  const long long total = (long long)B * n;
+  if (total == 0) return cudaSuccess;
+  if (t == DT_F32) copy_frames_kernel<float><<<grid_for(total), 256, 0, s>>>((const float*)src, (float*)dst, B, src_bs, dst_bs, n);
+  else copy_frames_kernel<bf16><<<grid_for(total), 256, 0, s>>>((const bf16*)src, (bf16*)dst, B, src_bs, dst_bs, n);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace vt

@@ -1,0 +1,54 @@
+// Host-callable launchers of the vidtok_b200 kernels (internal; the public surface is include/vidtok_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace vt {
+
+enum DType { DT_F32 = 0, DT_BF16 = 1 };
+inline size_t dtype_size(DType t) { return t == DT_F32 ? 4 : 2; }
+
+// conv_simt.cu
+cudaError_t launch_conv_simt(const ConvP& p, DType tin, DType tout, DType tres, const void* x, const float* w_kn,
+                             void* out, cudaStream_t s);
+cudaError_t launch_gemm_simt(DType ta, DType tb, DType tc, const void* A, const void* B, void* C, int M, int N, int K,
+                             long long lda, long long sbn, long long sbk, long long ldc, int batch, long long bsA,
+                             long long bsB, long long bsC, float scale, cudaStream_t s);
+
+// elementwise.cu
+cudaError_t launch_layernorm(DType t, const void* x, const float* gamma, const float* beta, void* y, long long rows,
+                             int C, bool silu, bool exact, cudaStream_t s);
+// stats: float2 [frames*32] scratch (per-frame mode)
+cudaError_t launch_groupnorm(DType t, const void* x, const float* gamma, const float* beta, void* y, long long frames,
+                             long long pos_per_frame, int C, bool per_position, bool silu, bool exact, float* stats,
+                             cudaStream_t s);
+cudaError_t launch_softmax_rows(DType tout, const float* S, void* P, long long rows, int N, cudaStream_t s);
+cudaError_t launch_kl(const float* h, const float* noise, int zc, long long P, int B, bool sample, float* z,
+                      float* kl_loss, double* scratch, cudaStream_t s);
+cudaError_t launch_fsq(const float* h, int d, const int* levels_host, long long P, int B, float* codes, int* indices,
+                       cudaStream_t s);
+cudaError_t launch_fsq_indices_to_codes(const int* indices, int d, const int* levels_host, long long P, int B,
+                                        float* codes, cudaStream_t s);
+// weight repacking: w [Co][Ci][taps] (reference OIDHW flattened) -> [K = tap*Ci + ci][Co] fp32
+cudaError_t launch_pack_w_kn(const float* w, float* out, int Co, int Ci, int taps, cudaStream_t s);
+// -> [Co][K = tap*Ci + ci] bf16 (K-major rows for the tcgen05 B operand)
+cudaError_t launch_pack_w_nk_bf16(const float* w, bf16* out, int Co, int Ci, int taps, int Kpad, cudaStream_t s);
+// trilinear (align_corners=False) 2x upsampling along T of channels-last x [B,T,HWC] -> [B,2T,HWC]
+cudaError_t launch_time_interp2x(DType t, const void* x, void* y, int B, int T, long long hwc, cudaStream_t s);
+cudaError_t launch_upsample_nearest(DType t, const void* x, void* y, int B, int T, int H, int W, int C, int ut, int uh,
+                                    int uw, cudaStream_t s);
+cudaError_t launch_cache_update(DType t, const void* x, const void* old_cache, void* new_cache, int B, int Tc, int P,
+                                int off, bool first, long long frame_elems, long long x_bs, cudaStream_t s);
+cudaError_t launch_ncdhw_to_cl(DType t, const float* x, void* y, int B, int C, int T, int H, int W, int t_rep,
+                               cudaStream_t s);
+cudaError_t launch_copy_frames(DType t, const void* src, void* dst, int B, long long src_bs, long long dst_bs,
+                               long long n_per_batch, cudaStream_t s);
+
+// conv_tc.cu (tcgen05 / TMA implicit GEMM)
+bool conv_tc_supported(const ConvP& p);
+cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int Kpad, bf16* out, cudaStream_t s);
+const char* conv_tc_last_error();
+
+}  // namespace vt

@@ -1,0 +1,1272 @@
+// Model construction (parameter manifest with the reference's checkpoint keys), weight repacking, and the
+// executor that walks the encoder/decoder stacks launching the kernels.  Host-side C++; the layer order follows
+// EncoderCausal3D.forward / DecoderCausal3D.forward (vidtok/modules/model_3dcausal.py:631-671,828-870) and the
+// chunked v1.1 variants (vidtok/modules/model_3dcausal_v1_1.py).
+#include "model.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+namespace vt {
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+thread_local std::string g_err;
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define VT_CUDA(call)                                                                         \
+  do {                                                                                        \
+    cudaError_t _e = (call);                                                                  \
+    if (_e != cudaSuccess)                                                                    \
+      return fail(VT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// arena: first-fit allocator over the caller's workspace; `dry` mode only measures the peak
+// ------------------------------------------------------------------------------------------------
+static inline size_t align_up(size_t n, size_t a) { return (n + a - 1) / a * a; }
+void Arena::reset(void* b, size_t c, bool d) {
+  base = (char*)b;
+  cap = c;
+  dry = d;
+  peak = 0;
+  blks.clear();
+  blks.push_back({0, d ? ((size_t)1 << 60) : c, true});
+}
+void* Arena::alloc(size_t n) {
+  n = align_up(n ? n : 1, 1024);
+  for (size_t i = 0; i < blks.size(); ++i) {
+    if (blks[i].free && blks[i].size >= n) {
+      if (blks[i].size > n) {
+        Blk rest{blks[i].off + n, blks[i].size - n, true};
+        blks[i].size = n;
+        blks.insert(blks.begin() + i + 1, rest);
+      }
+      blks[i].free = false;
+      peak = std::max(peak, blks[i].off + n);
+      return base + blks[i].off;
+    }
+  }
+  return nullptr;
+}
+void Arena::release(void* p) {
+  if (!p) return;
+  size_t off = (char*)p - base;
+  for (size_t i = 0; i < blks.size(); ++i) {
+    if (blks[i].off == off && !blks[i].free) {
+      blks[i].free = true;
+      if (i + 1 < blks.size() && blks[i + 1].free) {
+        blks[i].size += blks[i + 1].size;
+        blks.erase(blks.begin() + i + 1);
+      }
+      if (i > 0 && blks[i - 1].free) {
+        blks[i - 1].size += blks[i].size;
+        blks.erase(blks.begin() + i);
+      }
+      return;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// manifest
+// ------------------------------------------------------------------------------------------------
+static int add_param(vt_model* m, const std::string& name, std::vector<int64_t> shape) {
+  Param p;
+  p.name = name;
+  p.shape = shape;
+  p.numel = 1;
+  for (auto s : shape) p.numel *= s;
+  p.offset = m->pool_elems;
+  m->pool_elems += (p.numel + 3) / 4 * 4;  // keep every tensor 16-byte aligned
+  m->index[name] = (int)m->params.size();
+  m->params.push_back(p);
+  return (int)m->params.size() - 1;
+}
+// CausalConv3d: "<key>.conv.{weight,bias}", weight [Co,Ci,kt,kh,kw]
+static void add_conv3d(vt_model* m, ConvW& c, const std::string& key, int Co, int Ci, int k) {
+  c.Co = Co; c.Ci = Ci; c.kt = c.kh = c.kw = k;
+  c.pw = add_param(m, key + ".conv.weight", {Co, Ci, k, k, k});
+  c.pb = add_param(m, key + ".conv.bias", {Co});
+  m->convs.push_back(&c);
+}
+// CausalConv1d: "<key>.conv.{weight,bias}", weight [Co,Ci,k]
+static void add_conv1d(vt_model* m, ConvW& c, const std::string& key, int Co, int Ci, int k) {
+  c.Co = Co; c.Ci = Ci; c.kt = k; c.kh = c.kw = 1;
+  c.pw = add_param(m, key + ".conv.weight", {Co, Ci, k});
+  c.pb = add_param(m, key + ".conv.bias", {Co});
+  m->convs.push_back(&c);
+}
+// nn.Conv2d: "<key>.{weight,bias}", weight [Co,Ci,k,k]
+static void add_conv2d(vt_model* m, ConvW& c, const std::string& key, int Co, int Ci, int k) {
+  c.Co = Co; c.Ci = Ci; c.kt = 1; c.kh = c.kw = k;
+  c.pw = add_param(m, key + ".weight", {Co, Ci, k, k});
+  c.pb = add_param(m, key + ".bias", {Co});
+  m->convs.push_back(&c);
+}
+static void add_norm(vt_model* m, NormW& n, const std::string& key, int C) {
+  n.C = C;
+  const std::string k = (m->desc.norm_type == VT_NORM_LAYERNORM) ? key + ".norm" : key;
+  n.pg = add_param(m, k + ".weight", {C});
+  n.pb = add_param(m, k + ".bias", {C});
+  m->norms.push_back(&n);
+}
+static void add_res2d(vt_model* m, ResBlockW& r, const std::string& key, int Ci, int Co) {
+  r.key = key;
+  add_norm(m, r.n1, key + ".norm1", Ci);
+  add_conv2d(m, r.c1, key + ".conv1", Co, Ci, 3);
+  add_norm(m, r.n2, key + ".norm2", Co);
+  add_conv2d(m, r.c2, key + ".conv2", Co, Co, 3);
+  r.has_nin = Ci != Co;
+  if (r.has_nin) add_conv2d(m, r.nin, key + ".nin_shortcut", Co, Ci, 1);
+}
+static void add_res1d(vt_model* m, ResBlockW& r, const std::string& key, int C) {
+  r.key = key;
+  add_norm(m, r.n1, key + ".norm1", C);
+  add_conv1d(m, r.c1, key + ".conv1", C, C, 3);
+  add_norm(m, r.n2, key + ".norm2", C);
+  add_conv1d(m, r.c2, key + ".conv2", C, C, 3);
+}
+static void add_res3d(vt_model* m, ResBlockW& r, const std::string& key, int C) {
+  r.key = key;
+  add_norm(m, r.n1, key + ".norm1", C);
+  add_conv3d(m, r.c1, key + ".conv1", C, C, 3);
+  add_norm(m, r.n2, key + ".norm2", C);
+  add_conv3d(m, r.c2, key + ".conv2", C, C, 3);
+}
+static void add_attn(vt_model* m, AttnW& a, const std::string& key, int C) {
+  a.key = key;
+  add_norm(m, a.n, key + ".norm", C);
+  add_conv3d(m, a.q, key + ".q", C, C, 1);
+  add_conv3d(m, a.k, key + ".k", C, C, 1);
+  add_conv3d(m, a.v, key + ".v", C, C, 1);
+  add_conv3d(m, a.proj, key + ".proj_out", C, C, 1);
+}
+static bool contains(const std::vector<int>& v, int x) { return std::find(v.begin(), v.end(), x) != v.end(); }
+
+static void build_manifest(vt_model* m) {
+  const vt_model_desc& d = m->desc;
+  const int L = d.num_levels;
+  auto pick = [&](int n, const int32_t* arr, std::vector<int> dflt) {
+    if (n < 0) return dflt;
+    return std::vector<int>(arr, arr + n);
+  };
+  std::vector<int> dsd, dsu;
+  for (int i = 0; i < L - 1; ++i) dsd.push_back(i);
+  for (int i = 1; i < L; ++i) dsu.push_back(i);
+  m->spatial_ds = pick(d.n_spatial_ds, d.spatial_ds, dsd);                 // model_3dcausal.py:539
+  m->tempo_ds = pick(d.n_tempo_ds, d.tempo_ds, {L - 2, L - 3});            // :540
+  m->spatial_us = pick(d.n_spatial_us, d.spatial_us, dsu);                 // :756
+  m->tempo_us = pick(d.n_tempo_us, d.tempo_us, {1, 2});                    // :757
+
+  // ---- encoder (model_3dcausal.py:535-620)
+  StackW& e = m->enc;
+  add_conv3d(m, e.conv_in, "encoder.conv_in", d.ch, d.in_channels, 3);
+  e.levels.resize(L);
+  int block_in = d.ch;
+  for (int l = 0; l < L; ++l) {
+    LevelW& lv = e.levels[l];
+    const int block_out = d.ch * d.ch_mult[l];
+    lv.blk.resize(d.num_res_blocks);
+    lv.tblk.resize(d.num_res_blocks);
+    for (int b = 0; b < d.num_res_blocks; ++b) {
+      add_res2d(m, lv.blk[b], "encoder.down." + std::to_string(l) + ".block." + std::to_string(b), block_in, block_out);
+      add_res1d(m, lv.tblk[b], "encoder.down_temporal." + std::to_string(l) + ".block." + std::to_string(b), block_out);
+      block_in = block_out;
+    }
+    if (contains(m->spatial_ds, l)) {
+      lv.has_resample = true;
+      add_conv2d(m, lv.resample, "encoder.down." + std::to_string(l) + ".downsample.conv", block_in, block_in, 3);
+      if (contains(m->tempo_ds, l)) {
+        lv.has_tres = true;
+        lv.tkey = "encoder.down_temporal." + std::to_string(l) + ".downsample";
+        lv.p_mix = add_param(m, lv.tkey + ".mix_factor", {1});
+        add_conv3d(m, lv.tconv, lv.tkey + ".conv", block_in, block_in, 3);
+      }
+    }
+  }
+  add_res3d(m, e.mid1, "encoder.mid.block_1", block_in);
+  add_attn(m, e.attn, "encoder.mid.attn_1", block_in);
+  add_res3d(m, e.mid2, "encoder.mid.block_2", block_in);
+  add_norm(m, e.norm_out, "encoder.norm_out", block_in);
+  add_conv3d(m, e.conv_out, "encoder.conv_out", d.double_z ? 2 * d.z_channels : d.z_channels, block_in, 3);
+
+  // ---- decoder (model_3dcausal.py:724-811; v1.1 num_temp_upsample: model_3dcausal_v1_1.py:856,880-882)
+  StackW& g = m->dec;
+  block_in = d.ch * d.ch_mult[L - 1];
+  add_conv3d(m, g.conv_in, "decoder.conv_in", block_in, d.z_channels, 3);
+  add_res3d(m, g.mid1, "decoder.mid.block_1", block_in);
+  add_attn(m, g.attn, "decoder.mid.attn_1", block_in);
+  add_res3d(m, g.mid2, "decoder.mid.block_2", block_in);
+  g.levels.resize(L);
+  int ntu = 1;
+  for (int l = L - 1; l >= 0; --l) {
+    LevelW& lv = g.levels[l];
+    const int block_out = d.ch * d.ch_mult[l];
+    lv.blk.resize(d.num_res_blocks + 1);
+    lv.tblk.resize(d.num_res_blocks + 1);
+    for (int b = 0; b <= d.num_res_blocks; ++b) {
+      add_res2d(m, lv.blk[b], "decoder.up." + std::to_string(l) + ".block." + std::to_string(b), block_in, block_out);
+      add_res1d(m, lv.tblk[b], "decoder.up_temporal." + std::to_string(l) + ".block." + std::to_string(b), block_out);
+      block_in = block_out;
+    }
+    if (contains(m->spatial_us, l)) {
+      lv.has_resample = true;
+      add_conv2d(m, lv.resample, "decoder.up." + std::to_string(l) + ".upsample.conv", block_in, block_in, 3);
+    }
+    if (contains(m->tempo_us, l)) {
+      lv.has_tres = true;
+      lv.tkey = "decoder.up_temporal." + std::to_string(l) + ".upsample";
+      lv.p_mix = add_param(m, lv.tkey + ".mix_factor", {1});
+      add_conv3d(m, lv.tconv, lv.tkey + ".conv", block_in, block_in, 3);
+      lv.num_temp_upsample = ntu;
+      ntu *= 2;
+    }
+  }
+  add_norm(m, g.norm_out, "decoder.norm_out", block_in);
+  add_conv3d(m, g.conv_out, "decoder.conv_out", d.out_ch, block_in, 3);
+}
+
+// ------------------------------------------------------------------------------------------------
+// executor
+// ------------------------------------------------------------------------------------------------
+struct Act {
+  void* p = nullptr;
+  int B = 0, T = 0, H = 0, W = 0, C = 0;
+  bool owned = false;            // allocated from the arena
+  long long elems() const { return (long long)B * T * H * W * C; }
+  long long frame() const { return (long long)H * W * C; }
+};
+
+struct CacheBuf {
+  void* buf[2] = {nullptr, nullptr};
+  int cur = 0;
+  int T = 0;
+  size_t bytes = 0;
+  bool valid = false;
+};
+
+}  // namespace vt
+
+struct vt_chunk_state {
+  vt_model* m = nullptr;
+  int prec = 0;
+  int B = 0, H = 0, W = 0;
+  bool is_decoder = false;
+  bool use_overlap = false;
+  bool first = true;
+  bool persist = true;           // false: one-shot "first chunk" context (untiled v1.1 forward)
+  std::map<std::string, vt::CacheBuf> caches;
+  ~vt_chunk_state() {
+    for (auto& kv : caches)
+      for (int i = 0; i < 2; ++i)
+        if (kv.second.buf[i]) cudaFree(kv.second.buf[i]);
+  }
+};
+
+namespace vt {
+
+struct ConvOpt {
+  int st = 1, sh = 1, sw = 1;
+  int ph0 = -1, pw0 = -1, ph1 = -1, pw1 = -1;  // -1: (k-1)/2
+  int ut = 1, uh = 1, uw = 1;
+  int t_rep = 0, to_off = 0;
+  int res_mode = 0;
+  const Act* res = nullptr;
+  long long res_bs = -1;          // residual batch stride override (views)
+  float ra = 1.f, rb = 1.f;
+  const float* ext_in = nullptr;  // external fp32 NCDHW input
+  float* ext_out = nullptr;       // external fp32 NCDHW output
+  long long in_bs = -1;           // input batch stride override (views into a larger tensor)
+  const char* cache_key = nullptr;  // v1.1 causal cache identity (checkpoint prefix of the conv)
+  bool force_simt = false;
+};
+
+struct Exec {
+  vt_model* m;
+  int prec;
+  DType ta;
+  bool exact;
+  cudaStream_t s;
+  Arena ar;
+  bool dry;
+  vt_chunk_state* ck = nullptr;   // v1.1 chunk context (null for v1.0)
+  int rc = VT_OK;
+
+  Exec(vt_model* m_, int prec_, cudaStream_t s_, void* ws, size_t ws_bytes, bool dry_)
+      : m(m_), prec(prec_), ta(prec_ == VT_PREC_EXACT ? DT_F32 : DT_BF16), exact(prec_ == VT_PREC_EXACT), s(s_),
+        dry(dry_) {
+    ar.reset(dry_ ? (void*)(uintptr_t)0x100000 : ws, ws_bytes, dry_);
+  }
+  bool ok() const { return rc == VT_OK; }
+  bool cuda(cudaError_t e, const char* what) {
+    if (e != cudaSuccess && rc == VT_OK) rc = fail(VT_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    return e == cudaSuccess;
+  }
+  void* alloc(size_t bytes) {
+    if (!ok()) return nullptr;
+    void* p = ar.alloc(bytes);
+    if (!p) rc = fail(VT_ERR_WORKSPACE, "workspace too small: need %zu more bytes (capacity %zu)", bytes, ar.cap);
+    return p;
+  }
+  Act new_act(int B, int T, int H, int W, int C) {
+    Act a;
+    a.B = B; a.T = T; a.H = H; a.W = W; a.C = C;
+    a.p = alloc((size_t)a.elems() * dtype_size(ta));
+    a.owned = true;
+    return a;
+  }
+  void free_act(Act& a) {
+    if (a.owned && a.p) ar.release(a.p);
+    a.p = nullptr;
+    a.owned = false;
+  }
+
+  // ---- v1.1 cache plumbing --------------------------------------------------------------------
+  int cache_offset_for(const std::string& key) const {
+    // autoencoder_v1_1.py:307-320 (tile_decode with use_overlap); longest-prefix rule
+    if (!ck || !ck->is_decoder || !ck->use_overlap) return 0;
+    const int tdf = m->desc.time_downsample_factor;
+    struct R { const char* p; int v; };
+    std::vector<R> rules;
+    rules.push_back({"decoder.", 1});
+    if (tdf == 4) {
+      rules.push_back({"decoder.up_temporal.2.upsample", 2});
+      rules.push_back({"decoder.up_temporal.1.", 2});
+      rules.push_back({"decoder.up_temporal.1.upsample", 4});
+      rules.push_back({"decoder.up_temporal.0.", 4});
+      rules.push_back({"decoder.conv_out", 4});
+    } else if (tdf == 2) {
+      rules.push_back({"decoder.up_temporal.2.upsample", 2});
+      rules.push_back({"decoder.up_temporal.1.", 2});
+      rules.push_back({"decoder.up_temporal.0.", 2});
+      rules.push_back({"decoder.conv_out", 2});
+    } else if (tdf == 8) {
+      rules.push_back({"decoder.up_temporal.3.upsample", 2});
+      rules.push_back({"decoder.up_temporal.2.", 2});
+      rules.push_back({"decoder.up_temporal.2.upsample", 4});
+      rules.push_back({"decoder.up_temporal.1.", 4});
+      rules.push_back({"decoder.up_temporal.1.upsample", 8});
+      rules.push_back({"decoder.up_temporal.0.", 8});
+      rules.push_back({"decoder.conv_out", 8});
+    }
+    int best = -1, val = 0;
+    for (auto& r : rules) {
+      const int n = (int)strlen(r.p);
+      if ((int)key.size() >= n && key.compare(0, n, r.p) == 0 && n > best) { best = n; val = r.v; }
+    }
+    return val;
+  }
+  CacheBuf* get_cache(const std::string& key, int T, size_t bytes) {
+    CacheBuf& c = ck->caches[key];
+    if (c.bytes != bytes) {
+      if (dry) { c.bytes = bytes; c.T = T; return &c; }
+      for (int i = 0; i < 2; ++i) {
+        if (c.buf[i]) cudaFree(c.buf[i]);
+        c.buf[i] = nullptr;
+        if (!cuda(cudaMalloc(&c.buf[i], bytes), "cudaMalloc(causal cache)")) return nullptr;
+      }
+      c.bytes = bytes; c.T = T; c.valid = false; c.cur = 0;
+    }
+    return &c;
+  }
+
+  // ---- convolution ----------------------------------------------------------------------------
+  Act conv(const ConvW& w, const Act& in, const ConvOpt& o) {
+    Act out;
+    if (!ok()) return out;
+    const bool v11 = m->desc.version == 1;
+    ConvP p;
+    memset(&p, 0, sizeof(p));
+    p.B = in.B; p.Ti = in.T; p.Hi = in.H; p.Wi = in.W; p.Ci = in.C;
+    if (in.C != w.Ci) { rc = fail(VT_ERR_INVALID, "conv: Cin mismatch %d vs %d", in.C, w.Ci); return out; }
+    if (o.ext_in) {
+      p.isC = (long long)in.T * in.H * in.W; p.isB = p.isC * in.C; p.isT = (long long)in.H * in.W; p.isH = in.W; p.isW = 1;
+    } else {
+      p.isC = 1; p.isW = in.C; p.isH = (long long)in.W * in.C; p.isT = p.isH * in.H; p.isB = o.in_bs >= 0 ? o.in_bs : p.isT * in.T;
+    }
+    p.kt = w.kt; p.kh = w.kh; p.kw = w.kw;
+    p.st = o.st; p.sh = o.sh; p.sw = o.sw;
+    p.ut = o.ut; p.uh = o.uh; p.uw = o.uw;
+    p.t_rep = o.t_rep; p.to_off = o.to_off;
+    p.pt = (w.kt - 1) + (1 - o.st);                       // model_3dcausal.py:177
+    const int hp = (w.kh - 1) + (1 - o.sh), wp = (w.kw - 1) + (1 - o.sw);   // :178-179
+    const int ph0 = o.ph0 >= 0 ? o.ph0 : hp / 2, ph1 = o.ph1 >= 0 ? o.ph1 : hp - hp / 2;
+    const int pw0 = o.pw0 >= 0 ? o.pw0 : wp / 2, pw1 = o.pw1 >= 0 ? o.pw1 : wp - wp / 2;
+    p.ph = ph0; p.pw = pw0;
+    const int Tv = o.t_rep + o.ut * in.T;
+    p.To = (Tv + p.pt - w.kt) / o.st + 1 - o.to_off;
+    p.Ho = (o.uh * in.H + ph0 + ph1 - w.kh) / o.sh + 1;
+    p.Wo = (o.uw * in.W + pw0 + pw1 - w.kw) / o.sw + 1;
+    p.Co = w.Co;
+    if (p.To <= 0 || p.Ho <= 0 || p.Wo <= 0) { rc = fail(VT_ERR_INVALID, "conv: empty output"); return out; }
+    out.B = in.B; out.T = p.To; out.H = p.Ho; out.W = p.Wo; out.C = w.Co;
+    if (o.ext_out) {
+      out.p = o.ext_out;
+      p.osC = (long long)p.To * p.Ho * p.Wo; p.osB = p.osC * p.Co; p.osT = (long long)p.Ho * p.Wo; p.osH = p.Wo; p.osW = 1;
+    } else {
+      out.p = alloc((size_t)out.elems() * dtype_size(ta));
+      out.owned = true;
+      p.osC = 1; p.osW = p.Co; p.osH = (long long)p.Wo * p.Co; p.osT = p.osH * p.Ho; p.osB = p.osT * p.To;
+    }
+    if (!ok()) return out;
+    // time padding mode
+    p.t_mode = 0;
+    CacheBuf* cb = nullptr;
+    int cache_off = 0;
+    if (v11 && w.kt > 1) {
+      p.t_mode = 1;
+      if (ck && o.cache_key && ck->persist) {
+        cache_off = cache_offset_for(o.cache_key);
+        cb = get_cache(o.cache_key, p.pt, (size_t)in.B * p.pt * in.frame() * dtype_size(o.ext_in ? DT_F32 : ta));
+        if (!ok()) return out;
+        if (!ck->first) {
+          if (!dry && !cb->valid) { rc = fail(VT_ERR_NOT_READY, "causal cache %s empty on a non-first chunk", o.cache_key); return out; }
+          p.t_mode = 2;
+          p.cache = cb->buf[cb->cur];
+          p.cacheT = p.pt;
+        }
+      }
+    }
+    p.bias = w.bias;
+    p.res_mode = o.res_mode;
+    p.ra = o.ra; p.rb = o.rb;
+    if (o.res_mode) {
+      const Act& r = *o.res;
+      p.res = r.p;
+      p.rsW = r.C; p.rsH = (long long)r.W * r.C; p.rsT = p.rsH * r.H; p.rsB = o.res_bs >= 0 ? o.res_bs : p.rsT * r.T;
+      p.resT = r.T;
+      if (r.C != w.Co) { rc = fail(VT_ERR_INVALID, "conv: residual channel mismatch"); return out; }
+      if (o.res_mode == 3) {
+        p.res_t_mode = 0;
+        if (v11) {
+          p.res_t_mode = 1;   // replicate (model_3dcausal_v1_1.py:293-294)
+          if (ck && ck->persist && o.cache_key) {
+            const std::string pk = std::string(o.cache_key) + "#pool";
+            CacheBuf* pc = get_cache(pk, 1, (size_t)r.B * r.frame() * dtype_size(ta));
+            if (!ok()) return out;
+            if (!ck->first) { p.res_t_mode = 2; p.res_cache = pc->buf[pc->cur]; }
+          }
+        }
+      }
+    }
+    if (!dry) {
+      const DType tin = o.ext_in ? DT_F32 : ta;
+      const DType tout = o.ext_out ? DT_F32 : ta;
+      const bool tc = (prec == VT_PREC_BF16) && !o.force_simt && !o.ext_in && !o.ext_out && w.w_nk && conv_tc_supported(p);
+      if (tc) {
+        if (!cuda(launch_conv_tc(p, (const bf16*)in.p, w.w_nk, w.Kpad, (bf16*)out.p, s), conv_tc_last_error())) return out;
+      } else {
+        if (!cuda(launch_conv_simt(p, tin, tout, ta, o.ext_in ? (const void*)o.ext_in : in.p, w.w_kn, out.p, s), "conv_simt")) return out;
+      }
+      // v1.1: cache := tail of the padded input (after the conv consumed the old cache)
+      if (cb) {
+        const int nxt = cb->cur ^ 1;
+        if (!cuda(launch_cache_update(tin, o.ext_in ? (const void*)o.ext_in : in.p, cb->buf[cb->cur], cb->buf[nxt], in.B, in.T,
+                                      p.pt, cache_off, ck->first, in.frame(), p.isB, s), "cache_update")) return out;
+        cb->cur = nxt;
+        cb->valid = true;
+      }
+      if (o.res_mode == 3 && v11 && ck && ck->persist && o.cache_key) {
+        // avg-pool branch cache = last frame of the padded input (model_3dcausal_v1_1.py:298)
+        CacheBuf& pc = ck->caches[std::string(o.cache_key) + "#pool"];
+        const Act& r = *o.res;
+        const int nxt = pc.cur ^ 1;
+        if (!cuda(launch_copy_frames(ta, (const char*)r.p + (size_t)(r.T - 1) * r.frame() * dtype_size(ta), pc.buf[nxt], r.B,
+                                     (long long)r.T * r.frame(), r.frame(), r.frame(), s), "pool cache")) return out;
+        pc.cur = nxt;
+        pc.valid = true;
+      }
+    }
+    return out;
+  }
+  // ext_in path needs channels-last cache update from an NCDHW tensor: only conv_in of the encoder; handled by
+  // converting the chunk to channels-last first (see run_encoder).
+
+  Act norm(const NormW& n, const Act& in, bool silu, bool per_position) {
+    Act out;
+    if (!ok()) return out;
+    out = new_act(in.B, in.T, in.H, in.W, in.C);
+    if (!ok() || dry) {
+      if (m->desc.norm_type == VT_NORM_GROUPNORM && !per_position && ok()) {
+        void* st = alloc((size_t)in.B * in.T * 32 * 2 * sizeof(float));
+        ar.release(st);
+      }
+      return out;
+    }
+    if (m->desc.norm_type == VT_NORM_LAYERNORM) {
+      cuda(launch_layernorm(ta, in.p, n.gamma, n.beta, out.p, (long long)in.B * in.T * in.H * in.W, in.C, silu, exact, s), "layernorm");
+    } else {
+      float* st = nullptr;
+      if (!per_position) st = (float*)alloc((size_t)in.B * in.T * 32 * 2 * sizeof(float));
+      if (ok())
+        cuda(launch_groupnorm(ta, in.p, n.gamma, n.beta, out.p, (long long)in.B * in.T, (long long)in.H * in.W, in.C,
+                              per_position, silu, exact, st, s), "groupnorm");
+      if (st) ar.release(st);
+    }
+    return out;
+  }
+
+  // ResnetBlock (2D, per frame): model_3dcausal.py:317-337
+  Act res2d(const ResBlockW& r, Act x) {
+    Act n1 = norm(r.n1, x, true, false);
+    Act h1 = conv(r.c1, n1, ConvOpt());
+    free_act(n1);
+    Act n2 = norm(r.n2, h1, true, false);
+    free_act(h1);
+    Act skip = x;
+    if (r.has_nin) skip = conv(r.nin, x, ConvOpt());
+    ConvOpt o;
+    o.res_mode = 1; o.res = &skip;
+    Act out = conv(r.c2, n2, o);
+    free_act(n2);
+    if (r.has_nin) free_act(skip);
+    free_act(x);
+    return out;
+  }
+  // ResnetCausalBlock1D: model_3dcausal.py:473-499 (GroupNorm statistics per position, see oracle)
+  Act res1d(const ResBlockW& r, Act x) {
+    const std::string k1 = r.key + ".conv1", k2 = r.key + ".conv2";
+    Act n1 = norm(r.n1, x, true, true);
+    ConvOpt o1; o1.cache_key = k1.c_str();
+    Act h1 = conv(r.c1, n1, o1);
+    free_act(n1);
+    Act n2 = norm(r.n2, h1, true, true);
+    free_act(h1);
+    ConvOpt o; o.res_mode = 1; o.res = &x; o.cache_key = k2.c_str();
+    Act out = conv(r.c2, n2, o);
+    free_act(n2);
+    free_act(x);
+    return out;
+  }
+  // ResnetCausalBlock (3D, mid): model_3dcausal.py:400-424
+  Act res3d(const ResBlockW& r, Act x) {
+    const std::string k1 = r.key + ".conv1", k2 = r.key + ".conv2";
+    Act n1 = norm(r.n1, x, true, false);
+    ConvOpt o1; o1.cache_key = k1.c_str();
+    Act h1 = conv(r.c1, n1, o1);
+    free_act(n1);
+    Act n2 = norm(r.n2, h1, true, false);
+    free_act(h1);
+    ConvOpt o; o.res_mode = 1; o.res = &x; o.cache_key = k2.c_str();
+    Act out = conv(r.c2, n2, o);
+    free_act(n2);
+    free_act(x);
+    return out;
+  }
+  // AttnBlockWrapper: model_3dcausal.py:114-141
+  Act attention_core(const Act& q, const Act& k, const Act& v) {
+    const int frames = q.B * q.T, tokens = q.H * q.W, C = q.C;
+    Act o = new_act(q.B, q.T, q.H, q.W, C);
+    float* S = (float*)alloc((size_t)frames * tokens * tokens * sizeof(float));
+    void* P = alloc((size_t)frames * tokens * tokens * dtype_size(ta));
+    if (ok() && !dry) {
+      const float scale = 1.0f / sqrtf((float)C);
+      const long long qs = (long long)tokens * C, ss = (long long)tokens * tokens;
+      cuda(launch_gemm_simt(ta, ta, DT_F32, q.p, k.p, S, tokens, tokens, C, C, C, 1, tokens, frames, qs, qs, ss, scale, s), "attn QK^T");
+      cuda(launch_softmax_rows(ta, S, P, (long long)frames * tokens, tokens, s), "attn softmax");
+      cuda(launch_gemm_simt(ta, ta, ta, P, v.p, o.p, tokens, C, tokens, tokens, 1, C, C, frames, ss, qs, qs, 1.0f, s), "attn PV");
+    }
+    ar.release(P);
+    ar.release(S);
+    return o;
+  }
+  Act attn(const AttnW& a, Act x) {
+    Act n = norm(a.n, x, false, false);
+    Act q = conv(a.q, n, ConvOpt());
+    Act k = conv(a.k, n, ConvOpt());
+    Act v = conv(a.v, n, ConvOpt());
+    free_act(n);
+    Act o = attention_core(q, k, v);
+    free_act(q); free_act(k); free_act(v);
+    ConvOpt op; op.res_mode = 1; op.res = &x;
+    Act out = conv(a.proj, o, op);
+    free_act(o);
+    free_act(x);
+    return out;
+  }
+  Act upsample_mat(const Act& x, int ut, int uh, int uw) {
+    Act y = new_act(x.B, x.T * ut, x.H * uh, x.W * uw, x.C);
+    if (ok() && !dry) cuda(launch_upsample_nearest(ta, x.p, y.p, x.B, x.T, x.H, x.W, x.C, ut, uh, uw, s), "upsample_nearest");
+    return y;
+  }
+  bool fold_upsample() const { return prec == VT_PREC_EXACT; }
+
+  // TimeDownsampleResCausal2x: model_3dcausal.py:247-252 / model_3dcausal_v1_1.py:289-302
+  Act time_down(const LevelW& lv, Act x) {
+    const std::string ck_ = lv.tkey + ".conv";
+    ConvOpt o;
+    o.st = 2; o.res_mode = 3; o.res = &x; o.ra = lv.alpha; o.rb = 1.f - lv.alpha; o.cache_key = ck_.c_str();
+    Act out = conv(lv.tconv, x, o);
+    free_act(x);
+    return out;
+  }
+  // TimeUpsampleResCausal2x: model_3dcausal.py:267-273 / model_3dcausal_v1_1.py:325-343
+  Act time_up(const LevelW& lv, Act x) {
+    const bool v11 = m->desc.version == 1;
+    const std::string ckey = lv.tkey + ".conv";
+    ConvOpt o;
+    o.ra = lv.alpha; o.rb = 1.f - lv.alpha; o.cache_key = ckey.c_str();
+    if (!v11) {
+      if (fold_upsample()) {
+        o.ut = 2; o.res_mode = 2; o.res = &x;
+        Act out = conv(lv.tconv, x, o);
+        free_act(x);
+        return out;
+      }
+      Act xu = upsample_mat(x, 2, 1, 1);
+      free_act(x);
+      o.res_mode = 1; o.res = &xu;
+      Act out = conv(lv.tconv, xu, o);
+      free_act(xu);
+      return out;
+    }
+    if (m->desc.interpolation_mode != VT_INTERP_TRILINEAR) {
+      Act xu = upsample_mat(x, 2, 1, 1);
+      free_act(x);
+      o.res_mode = 1; o.res = &xu;
+      Act out = conv(lv.tconv, xu, o);
+      free_act(xu);
+      return out;
+    }
+    // trilinear with cache (model_3dcausal_v1_1.py:329-340)
+    const int n = lv.num_temp_upsample;
+    const long long fe = x.frame();
+    const size_t es = dtype_size(ta);
+    const bool persist = ck && ck->persist;
+    const bool first = !ck || ck->first;
+    CacheBuf* cb = nullptr;
+    if (persist) {
+      cb = get_cache(lv.tkey + "#up", n, (size_t)x.B * n * fe * es);
+      if (!ok()) { free_act(x); return Act(); }
+    }
+    Act xu;
+    Act view;
+    long long bs = -1;
+    Act big;  // storage that backs `view` when it is a sub-range
+    if (first) {
+      // x[:n] and x[n:] interpolated separately, concatenated
+      xu = new_act(x.B, 2 * x.T, x.H, x.W, x.C);
+      if (ok() && !dry) {
+        const int na = std::min(n, x.T), nb = x.T - na;
+        // part a: frames [0,na) -> out frames [0,2na); part b: frames [na,T) -> out frames [2na,2T)
+        // both read/write with batch strides of the full tensors: run per part through strided views
+        for (int b = 0; b < x.B && ok(); ++b) {
+          const char* xb = (const char*)x.p + (size_t)b * x.T * fe * es;
+          char* yb = (char*)xu.p + (size_t)b * 2 * x.T * fe * es;
+          cuda(launch_time_interp2x(ta, xb, yb, 1, na, fe, s), "time_interp2x");
+          if (nb > 0) cuda(launch_time_interp2x(ta, xb + (size_t)na * fe * es, yb + (size_t)2 * na * fe * es, 1, nb, fe, s), "time_interp2x");
+        }
+        if (cb) {  // cache = x[:, -n:]
+          const int nxt = cb->cur ^ 1;
+          if (x.T < n) { rc = fail(VT_ERR_INVALID, "time_up: first chunk shorter than num_temp_upsample"); }
+          else cuda(launch_copy_frames(ta, (const char*)x.p + (size_t)(x.T - n) * fe * es, cb->buf[nxt], x.B, (long long)x.T * fe, (long long)n * fe, (long long)n * fe, s), "up cache");
+          cb->cur = nxt; cb->valid = true;
+        }
+      }
+      view = xu;
+    } else {
+      // xc = cat(cache, x); cache = xc[-2n:-n]; x' = interp(xc)[2n:]
+      Act xc = new_act(x.B, n + x.T, x.H, x.W, x.C);
+      big = new_act(x.B, 2 * (n + x.T), x.H, x.W, x.C);
+      if (ok() && !dry) {
+        if (!cb->valid) rc = fail(VT_ERR_NOT_READY, "time_up cache empty on a non-first chunk");
+        if (ok()) {
+          cuda(launch_copy_frames(ta, cb->buf[cb->cur], xc.p, x.B, (long long)n * fe, (long long)(n + x.T) * fe, (long long)n * fe, s), "up cat a");
+          cuda(launch_copy_frames(ta, x.p, (char*)xc.p + (size_t)n * fe * es, x.B, (long long)x.T * fe, (long long)(n + x.T) * fe, (long long)x.T * fe, s), "up cat b");
+          const int nxt = cb->cur ^ 1;
+          cuda(launch_copy_frames(ta, (const char*)xc.p + (size_t)(x.T - n) * fe * es, cb->buf[nxt], x.B, (long long)(n + x.T) * fe, (long long)n * fe, (long long)n * fe, s), "up cache");
+          cb->cur = nxt;
+          cuda(launch_time_interp2x(ta, xc.p, big.p, x.B, n + x.T, fe, s), "time_interp2x");
+        }
+      }
+      free_act(xc);
+      view = big;
+      view.owned = false;
+      view.p = (char*)big.p + (size_t)2 * n * fe * es;
+      view.T = 2 * x.T;
+      bs = (long long)2 * (n + x.T) * fe;
+    }
+    free_act(x);
+    o.res_mode = 1; o.res = &view; o.in_bs = bs; o.res_bs = bs;
+    Act out = conv(lv.tconv, view, o);
+    if (first) free_act(xu); else free_act(big);
+    return out;
+  }
+};
+
+// ---- encoder / decoder stacks ----------------------------------------------------------------------
+// x_ext: fp32 [B,Cin,T,H,W]; h_out: fp32 [B,Cz,Tz,Hz,Wz]
+static void run_encoder(Exec& ex, const float* x_ext, int B, int T, int H, int W, float* h_out) {
+  vt_model* m = ex.m;
+  const vt_model_desc& d = m->desc;
+  const StackW& e = m->enc;
+  const int tdf = d.time_downsample_factor;
+  int t_rep = 0;
+  if (T % tdf != 0) t_rep = (d.version == 0) ? (tdf - 1) : (tdf - T % tdf);  // model_3dcausal.py:685-689 / _v1_1.py:755-760
+  Act xin;
+  xin.p = (void*)x_ext; xin.B = B; xin.T = T; xin.H = H; xin.W = W; xin.C = d.in_channels;
+  Act h;
+  if (d.version == 1 && ex.ck && ex.ck->persist) {
+    // chunked v1.1: the causal cache of conv_in holds *padded input* frames; materialise the replicate-padded
+    // chunk channels-last so the cache update sees the same tensor the reference caches.
+    Act xp = ex.new_act(B, T + t_rep, H, W, d.in_channels);
+    if (ex.ok() && !ex.dry) {
+      // gather NCDHW fp32 -> channels-last activation type with replicate front pad via a 1x1x1 "copy conv" is
+      // overkill; use the conv kernel itself on the external tensor instead: conv_in reads x_ext with t_rep, and
+      // the cache is updated from a channels-last copy made here.
+      ex.cuda(launch_ncdhw_to_cl(ex.ta, x_ext, xp.p, B, d.in_channels, T, H, W, t_rep, ex.s), "ncdhw_to_cl");
+    }
+    ConvOpt o; o.cache_key = "encoder.conv_in";
+    h = ex.conv(e.conv_in, xp, o);
+    ex.free_act(xp);
+  } else {
+    ConvOpt o; o.ext_in = x_ext; o.t_rep = t_rep;
+    h = ex.conv(e.conv_in, xin, o);
+  }
+  for (size_t l = 0; l < e.levels.size(); ++l) {
+    const LevelW& lv = e.levels[l];
+    for (size_t b = 0; b < lv.blk.size(); ++b) {
+      h = ex.res2d(lv.blk[b], h);
+      h = ex.res1d(lv.tblk[b], h);
+    }
+    if (lv.has_resample) {
+      ConvOpt o; o.sh = 2; o.sw = 2; o.ph0 = 0; o.ph1 = 1; o.pw0 = 0; o.pw1 = 1;  // Downsample: model_3dcausal.py:223-227
+      Act y = ex.conv(lv.resample, h, o);
+      ex.free_act(h);
+      h = y;
+      if (lv.has_tres) h = ex.time_down(lv, h);
+    }
+  }
+  h = ex.res3d(e.mid1, h);
+  h = ex.attn(e.attn, h);
+  h = ex.res3d(e.mid2, h);
+  Act n = ex.norm(e.norm_out, h, true, false);
+  ex.free_act(h);
+  ConvOpt o; o.ext_out = h_out; o.cache_key = "encoder.conv_out";
+  ex.conv(e.conv_out, n, o);
+  ex.free_act(n);
+}
+
+// z_ext: fp32 [B,z,Tz,Hz,Wz]; x_out: fp32 [B,out_ch,Tout,H,W]
+static void run_decoder(Exec& ex, const float* z_ext, int B, int Tz, int Hz, int Wz, float* x_out) {
+  vt_model* m = ex.m;
+  const vt_model_desc& d = m->desc;
+  const StackW& g = m->dec;
+  Act zin;
+  zin.p = (void*)z_ext; zin.B = B; zin.T = Tz; zin.H = Hz; zin.W = Wz; zin.C = d.z_channels;
+  Act h;
+  if (d.version == 1 && ex.ck && ex.ck->persist) {
+    Act zp = ex.new_act(B, Tz, Hz, Wz, d.z_channels);
+    if (ex.ok() && !ex.dry) ex.cuda(launch_ncdhw_to_cl(ex.ta, z_ext, zp.p, B, d.z_channels, Tz, Hz, Wz, 0, ex.s), "ncdhw_to_cl");
+    ConvOpt o; o.cache_key = "decoder.conv_in";
+    h = ex.conv(g.conv_in, zp, o);
+    ex.free_act(zp);
+  } else {
+    ConvOpt o; o.ext_in = z_ext;
+    h = ex.conv(g.conv_in, zin, o);
+  }
+  h = ex.res3d(g.mid1, h);
+  h = ex.attn(g.attn, h);
+  h = ex.res3d(g.mid2, h);
+  for (int l = (int)g.levels.size() - 1; l >= 0; --l) {
+    const LevelW& lv = g.levels[l];
+    for (size_t b = 0; b < lv.blk.size(); ++b) {
+      h = ex.res2d(lv.blk[b], h);
+      h = ex.res1d(lv.tblk[b], h);
+    }
+    if (lv.has_resample) {
+      // Upsample: nearest 2x (H,W) + conv3x3 (model_3dcausal.py:208-212)
+      Act y;
+      if (ex.fold_upsample()) {
+        ConvOpt o; o.uh = 2; o.uw = 2;
+        y = ex.conv(lv.resample, h, o);
+        ex.free_act(h);
+      } else {
+        Act hu = ex.upsample_mat(h, 1, 2, 2);
+        ex.free_act(h);
+        y = ex.conv(lv.resample, hu, ConvOpt());
+        ex.free_act(hu);
+      }
+      h = y;
+      if (lv.has_tres) h = ex.time_up(lv, h);   // nested under spatial_us as in model_3dcausal.py:844-853
+    }
+  }
+  Act n = ex.norm(g.norm_out, h, true, false);
+  ex.free_act(h);
+  ConvOpt o; o.ext_out = x_out; o.cache_key = "decoder.conv_out";
+  if (d.version == 0) o.to_off = d.time_downsample_factor - 1;  // model_3dcausal.py:883-885
+  ex.conv(g.conv_out, n, o);
+  ex.free_act(n);
+}
+
+static int latent_shape(const vt_model* m, int T, int H, int W, int* Tz, int* Hz, int* Wz) {
+  const vt_model_desc& d = m->desc;
+  const int tdf = d.time_downsample_factor;
+  int t = T;
+  if (T % tdf != 0) t += (d.version == 0) ? (tdf - 1) : (tdf - T % tdf);
+  int h = H, w = W;
+  for (int l = 0; l < d.num_levels; ++l) {
+    if (contains(m->spatial_ds, l)) {
+      h = (h + 1 - 3) / 2 + 1;
+      w = (w + 1 - 3) / 2 + 1;
+      if (contains(m->tempo_ds, l)) t = (t + 1 - 3) / 2 + 1;
+    }
+  }
+  *Tz = t; *Hz = h; *Wz = w;
+  return VT_OK;
+}
+static void decoded_shape(const vt_model* m, int Tz, int Hz, int Wz, int* T, int* H, int* W) {
+  const vt_model_desc& d = m->desc;
+  int t = Tz, h = Hz, w = Wz;
+  for (int l = d.num_levels - 1; l >= 0; --l) {
+    if (contains(m->spatial_us, l)) {
+      h *= 2; w *= 2;
+      if (contains(m->tempo_us, l)) t *= 2;
+    }
+  }
+  if (d.version == 0) t -= d.time_downsample_factor - 1;
+  *T = t; *H = h; *W = w;
+}
+
+static int regularize(vt_model* m, const float* h_pre, const float* noise, int B, int Tz, int Hz, int Wz, float* z,
+                      int32_t* indices, float* kl_loss, cudaStream_t s) {
+  const vt_model_desc& d = m->desc;
+  const long long P = (long long)Tz * Hz * Wz;
+  if (d.regularizer == VT_REG_KL) {
+    if (d.kl_sample && !noise) return fail(VT_ERR_INVALID, "KL regularizer with sample=True needs the noise tensor");
+    VT_CUDA(launch_kl(h_pre, noise, d.z_channels, P, B, d.kl_sample != 0, z, kl_loss, m->kl_scratch, s));
+  } else {
+    VT_CUDA(launch_fsq(h_pre, d.z_channels, d.fsq_levels, P, B, z, indices, s));
+  }
+  return VT_OK;
+}
+
+}  // namespace vt
+
+// ====================================================================================================
+// C ABI
+// ====================================================================================================
+using namespace vt;
+
+extern "C" {
+
+const char* vt_last_error(void) { return g_err.c_str(); }
+int32_t vt_abi_version(void) { return 1; }
+int64_t vt_launch_count(int32_t reset) {
+  const long long v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+int32_t vt_model_create(const vt_model_desc* desc, int32_t device, vt_model** out) {
+  if (!desc || !out) return fail(VT_ERR_INVALID, "null argument");
+  const vt_model_desc& d = *desc;
+  if (d.num_levels < 2 || d.num_levels > VT_MAX_LEVELS) return fail(VT_ERR_INVALID, "num_levels out of range");
+  if (d.ch <= 0 || d.ch % 4 != 0) return fail(VT_ERR_INVALID, "ch must be a positive multiple of 4");
+  if (d.norm_type == VT_NORM_GROUPNORM && d.ch % 32 != 0) return fail(VT_ERR_INVALID, "groupnorm needs ch %% 32 == 0");
+  if (d.regularizer == VT_REG_FSQ) {
+    if (d.fsq_num_levels != d.z_channels) return fail(VT_ERR_INVALID, "FSQ with projections (dim != len(levels)) is not on the path");
+    if (d.double_z) return fail(VT_ERR_INVALID, "FSQ needs double_z = false");
+  } else if (!d.double_z) {
+    return fail(VT_ERR_INVALID, "KL needs double_z = true");
+  }
+  vt_model* m = new vt_model();
+  m->desc = d;
+  m->device = device;
+  build_manifest(m);
+  *out = m;
+  return VT_OK;
+}
+
+void vt_model_destroy(vt_model* m) {
+  if (!m) return;
+  if (m->pool) cudaFree(m->pool);
+  if (m->packed_kn) cudaFree(m->packed_kn);
+  if (m->packed_nk) cudaFree(m->packed_nk);
+  if (m->kl_scratch) cudaFree(m->kl_scratch);
+  delete m;
+}
+
+int32_t vt_model_num_params(const vt_model* m) { return m ? (int32_t)m->params.size() : 0; }
+
+int32_t vt_model_param_info(const vt_model* m, int32_t i, char* name, int32_t cap, int64_t* shape5, int32_t* ndim) {
+  if (!m || i < 0 || i >= (int)m->params.size()) return fail(VT_ERR_INVALID, "bad parameter index");
+  const Param& p = m->params[i];
+  if (name && cap > 0) {
+    strncpy(name, p.name.c_str(), cap - 1);
+    name[cap - 1] = 0;
+  }
+  if (ndim) *ndim = (int)p.shape.size();
+  if (shape5)
+    for (size_t k = 0; k < 5; ++k) shape5[k] = k < p.shape.size() ? p.shape[k] : 1;
+  return VT_OK;
+}
+
+static int ensure_device(vt_model* m) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(VT_ERR_NO_DEVICE, "no CUDA device visible: vidtok_b200 has no CPU fallback");
+  }
+  VT_CUDA(cudaSetDevice(m->device));
+  if (!m->pool) {
+    VT_CUDA(cudaMalloc(&m->pool, (size_t)m->pool_elems * sizeof(float)));
+    VT_CUDA(cudaMalloc(&m->kl_scratch, sizeof(double)));
+  }
+  return VT_OK;
+}
+
+int32_t vt_model_load_param(vt_model* m, const char* name, const float* data, int64_t numel, int32_t is_device,
+                            void* stream) {
+  if (!m || !name || !data) return fail(VT_ERR_INVALID, "null argument");
+  auto it = m->index.find(name);
+  if (it == m->index.end()) return fail(VT_ERR_INVALID, "unknown parameter %s", name);
+  Param& p = m->params[it->second];
+  if (p.numel != numel) return fail(VT_ERR_INVALID, "parameter %s: expected %lld elements, got %lld", name, (long long)p.numel, (long long)numel);
+  int rc = ensure_device(m);
+  if (rc) return rc;
+  VT_CUDA(cudaMemcpyAsync(m->pool + p.offset, data, (size_t)numel * sizeof(float),
+                          is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  p.loaded = true;
+  m->finalized = false;
+  return VT_OK;
+}
+
+int32_t vt_model_finalize(vt_model* m, void* stream) {
+  if (!m) return fail(VT_ERR_INVALID, "null model");
+  int rc = ensure_device(m);
+  if (rc) return rc;
+  for (auto& p : m->params)
+    if (!p.loaded) return fail(VT_ERR_NOT_READY, "parameter %s was never loaded", p.name.c_str());
+  cudaStream_t s = (cudaStream_t)stream;
+  // sizes
+  size_t kn = 0, nk = 0;
+  for (ConvW* c : m->convs) {
+    const int K = c->taps() * c->Ci;
+    kn += align_up((size_t)K * c->Co, 64);
+    c->Kpad = 0;
+    if (c->Ci % 64 == 0 && c->Co % 16 == 0) {
+      c->Kpad = K;
+      nk += align_up((size_t)c->Co * K, 512);
+    }
+  }
+  if (!m->packed_kn) VT_CUDA(cudaMalloc(&m->packed_kn, kn * sizeof(float)));
+  if (!m->packed_nk && nk) VT_CUDA(cudaMalloc(&m->packed_nk, nk * sizeof(bf16)));
+  size_t okn = 0, onk = 0;
+  for (ConvW* c : m->convs) {
+    const int K = c->taps() * c->Ci;
+    const float* w = m->pool + m->params[c->pw].offset;
+    c->bias = m->pool + m->params[c->pb].offset;
+    c->w_kn = m->packed_kn + okn;
+    okn += align_up((size_t)K * c->Co, 64);
+    VT_CUDA(launch_pack_w_kn(w, c->w_kn, c->Co, c->Ci, c->taps(), s));
+    if (c->Kpad) {
+      c->w_nk = m->packed_nk + onk;
+      onk += align_up((size_t)c->Co * K, 512);
+      VT_CUDA(launch_pack_w_nk_bf16(w, c->w_nk, c->Co, c->Ci, c->taps(), c->Kpad, s));
+    }
+  }
+  for (NormW* n : m->norms) {
+    n->gamma = m->pool + m->params[n->pg].offset;
+    n->beta = m->pool + m->params[n->pb].offset;
+  }
+  VT_CUDA(cudaStreamSynchronize(s));
+  auto set_alpha = [&](LevelW& lv) -> int {
+    if (!lv.has_tres) return VT_OK;
+    float mix = 0.f;
+    VT_CUDA(cudaMemcpy(&mix, m->pool + m->params[lv.p_mix].offset, sizeof(float), cudaMemcpyDeviceToHost));
+    lv.alpha = 1.0f / (1.0f + expf(-mix));  // torch.sigmoid(self.mix_factor), model_3dcausal.py:248,268
+    return VT_OK;
+  };
+  for (auto& lv : m->enc.levels) { rc = set_alpha(lv); if (rc) return rc; }
+  for (auto& lv : m->dec.levels) { rc = set_alpha(lv); if (rc) return rc; }
+  m->finalized = true;
+  return VT_OK;
+}
+
+int32_t vt_latent_shape(const vt_model* m, int32_t T, int32_t H, int32_t W, int32_t* Tz, int32_t* Hz, int32_t* Wz) {
+  if (!m || !Tz || !Hz || !Wz) return fail(VT_ERR_INVALID, "null argument");
+  return latent_shape(m, T, H, W, Tz, Hz, Wz);
+}
+int32_t vt_decoded_frames(const vt_model* m, int32_t Tz) {
+  int t, h, w;
+  decoded_shape(m, Tz, 1, 1, &t, &h, &w);
+  return t;
+}
+
+static int check_hw(const vt_model* m, int H, int W) {
+  int f = 1;
+  for (int l = 0; l < m->desc.num_levels; ++l)
+    if (contains(m->spatial_ds, l)) f *= 2;
+  if (H % f != 0 || W % f != 0) return fail(VT_ERR_INVALID, "H and W must be multiples of %d", f);
+  return VT_OK;
+}
+
+int64_t vt_workspace_bytes(const vt_model* m, int32_t precision, int32_t B, int32_t T, int32_t H, int32_t W) {
+  if (!m || B <= 0 || T <= 0) { fail(VT_ERR_INVALID, "bad shape"); return -1; }
+  if (check_hw(m, H, W)) return -1;
+  vt_model* mm = const_cast<vt_model*>(m);
+  int Tz, Hz, Wz;
+  latent_shape(m, T, H, W, &Tz, &Hz, &Wz);
+  size_t peak = 0;
+  {
+    Exec ex(mm, precision, 0, nullptr, 0, true);
+    vt_chunk_state one; one.m = mm; one.persist = false; one.first = true;
+    if (m->desc.version == 1) ex.ck = &one;
+    float* hpre = (float*)ex.alloc((size_t)B * (m->desc.double_z ? 2 : 1) * m->desc.z_channels * Tz * Hz * Wz * sizeof(float));
+    (void)hpre;
+    run_encoder(ex, (const float*)(uintptr_t)0x1000, B, T, H, W, (float*)(uintptr_t)0x1000);
+    if (!ex.ok()) return -1;
+    peak = std::max(peak, ex.ar.peak);
+  }
+  {
+    Exec ex(mm, precision, 0, nullptr, 0, true);
+    vt_chunk_state one; one.m = mm; one.persist = false; one.first = true; one.is_decoder = true;
+    if (m->desc.version == 1) ex.ck = &one;
+    float* zc = (float*)ex.alloc((size_t)B * m->desc.z_channels * Tz * Hz * Wz * sizeof(float));  // codes from indices
+    (void)zc;
+    run_decoder(ex, (const float*)(uintptr_t)0x1000, B, Tz, Hz, Wz, (float*)(uintptr_t)0x1000);
+    if (!ex.ok()) return -1;
+    peak = std::max(peak, ex.ar.peak);
+  }
+  return (int64_t)(peak + 4096);
+}
+
+int32_t vt_encode(vt_model* m, int32_t precision, const float* x, int32_t B, int32_t T, int32_t H, int32_t W,
+                  const float* noise, float* z, int32_t* indices, float* kl_loss, float* h_pre, void* workspace,
+                  int64_t workspace_bytes, void* stream) {
+  if (!m || !x || !z) return fail(VT_ERR_INVALID, "null argument");
+  if (!m->finalized) return fail(VT_ERR_NOT_READY, "vt_model_finalize has not been called");
+  int rc = check_hw(m, H, W);
+  if (rc) return rc;
+  VT_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  int Tz, Hz, Wz;
+  latent_shape(m, T, H, W, &Tz, &Hz, &Wz);
+  Exec ex(m, precision, s, workspace, (size_t)workspace_bytes, false);
+  vt_chunk_state one; one.m = m; one.persist = false; one.first = true;
+  if (m->desc.version == 1) ex.ck = &one;
+  const size_t hb = (size_t)B * (m->desc.double_z ? 2 : 1) * m->desc.z_channels * Tz * Hz * Wz * sizeof(float);
+  float* hp = h_pre ? h_pre : (float*)ex.alloc(hb);
+  if (!ex.ok()) return ex.rc;
+  run_encoder(ex, x, B, T, H, W, hp);
+  if (!ex.ok()) return ex.rc;
+  return regularize(m, hp, noise, B, Tz, Hz, Wz, z, indices, kl_loss, s);
+}
+
+int32_t vt_decode(vt_model* m, int32_t precision, const void* z, int32_t from_indices, int32_t B, int32_t Tz, int32_t Hz,
+                  int32_t Wz, float* x_out, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!m || !z || !x_out) return fail(VT_ERR_INVALID, "null argument");
+  if (!m->finalized) return fail(VT_ERR_NOT_READY, "vt_model_finalize has not been called");
+  VT_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  Exec ex(m, precision, s, workspace, (size_t)workspace_bytes, false);
+  vt_chunk_state one; one.m = m; one.persist = false; one.first = true; one.is_decoder = true;
+  if (m->desc.version == 1) ex.ck = &one;
+  const float* zf = (const float*)z;
+  if (from_indices) {
+    if (m->desc.regularizer != VT_REG_FSQ) return fail(VT_ERR_INVALID, "decode_from_indices needs an FSQ model");
+    float* codes = (float*)ex.alloc((size_t)B * m->desc.z_channels * Tz * Hz * Wz * sizeof(float));
+    if (!ex.ok()) return ex.rc;
+    VT_CUDA(launch_fsq_indices_to_codes((const int*)z, m->desc.z_channels, m->desc.fsq_levels, (long long)Tz * Hz * Wz, B, codes, s));
+    zf = codes;
+  }
+  run_decoder(ex, zf, B, Tz, Hz, Wz, x_out);
+  return ex.rc;
+}
+
+// ---- chunked v1.1 ------------------------------------------------------------------------------------
+int32_t vt_chunk_state_create(vt_model* m, int32_t precision, int32_t B, int32_t H, int32_t W, int32_t is_decoder,
+                              int32_t use_overlap, vt_chunk_state** out) {
+  if (!m || !out) return fail(VT_ERR_INVALID, "null argument");
+  if (m->desc.version != 1) return fail(VT_ERR_INVALID, "temporal tiling exists only in the v1.1 model family");
+  vt_chunk_state* st = new vt_chunk_state();
+  st->m = m; st->prec = precision; st->B = B; st->H = H; st->W = W;
+  st->is_decoder = is_decoder != 0; st->use_overlap = use_overlap != 0;
+  st->first = true; st->persist = true;
+  *out = st;
+  return VT_OK;
+}
+void vt_chunk_state_destroy(vt_chunk_state* s) { delete s; }
+
+int64_t vt_chunk_workspace_bytes(const vt_chunk_state* cs, int32_t Tc) {
+  if (!cs) { fail(VT_ERR_INVALID, "null state"); return -1; }
+  vt_chunk_state tmp;  // measure with throw-away cache bookkeeping
+  tmp.m = cs->m; tmp.prec = cs->prec; tmp.B = cs->B; tmp.H = cs->H; tmp.W = cs->W;
+  tmp.is_decoder = cs->is_decoder; tmp.use_overlap = cs->use_overlap; tmp.persist = true;
+  size_t peak = 0;
+  for (int first = 0; first < 2; ++first) {
+    tmp.first = first != 0;
+    Exec ex(cs->m, cs->prec, 0, nullptr, 0, true);
+    ex.ck = &tmp;
+    if (cs->is_decoder) {
+      run_decoder(ex, (const float*)(uintptr_t)0x1000, cs->B, Tc, cs->H, cs->W, (float*)(uintptr_t)0x1000);
+    } else {
+      int Tz, Hz, Wz;
+      latent_shape(cs->m, Tc, cs->H, cs->W, &Tz, &Hz, &Wz);
+      ex.alloc((size_t)cs->B * 2 * cs->m->desc.z_channels * Tz * Hz * Wz * sizeof(float));
+      run_encoder(ex, (const float*)(uintptr_t)0x1000, cs->B, Tc, cs->H, cs->W, (float*)(uintptr_t)0x1000);
+    }
+    if (!ex.ok()) return -1;
+    peak = std::max(peak, ex.ar.peak);
+  }
+  return (int64_t)(peak + 4096);
+}
+
+int32_t vt_encode_chunk(vt_chunk_state* cs, int32_t is_first, const float* x_chunk, int32_t Tc, const float* noise,
+                        float* z, int32_t* indices, float* kl_loss, void* workspace, int64_t workspace_bytes,
+                        void* stream) {
+  if (!cs || !x_chunk || !z) return fail(VT_ERR_INVALID, "null argument");
+  if (cs->is_decoder) return fail(VT_ERR_INVALID, "decoder state passed to vt_encode_chunk");
+  vt_model* m = cs->m;
+  if (!m->finalized) return fail(VT_ERR_NOT_READY, "vt_model_finalize has not been called");
+  VT_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  cs->first = is_first != 0;
+  int Tz, Hz, Wz;
+  latent_shape(m, Tc, cs->H, cs->W, &Tz, &Hz, &Wz);
+  Exec ex(m, cs->prec, s, workspace, (size_t)workspace_bytes, false);
+  ex.ck = cs;
+  float* hp = (float*)ex.alloc((size_t)cs->B * (m->desc.double_z ? 2 : 1) * m->desc.z_channels * Tz * Hz * Wz * sizeof(float));
+  if (!ex.ok()) return ex.rc;
+  run_encoder(ex, x_chunk, cs->B, Tc, cs->H, cs->W, hp);
+  if (!ex.ok()) return ex.rc;
+  return regularize(m, hp, noise, cs->B, Tz, Hz, Wz, z, indices, kl_loss, s);
+}
+
+int32_t vt_decode_chunk(vt_chunk_state* cs, int32_t is_first, const float* z_chunk, int32_t Tzc, float* x_out,
+                        void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!cs || !z_chunk || !x_out) return fail(VT_ERR_INVALID, "null argument");
+  if (!cs->is_decoder) return fail(VT_ERR_INVALID, "encoder state passed to vt_decode_chunk");
+  vt_model* m = cs->m;
+  if (!m->finalized) return fail(VT_ERR_NOT_READY, "vt_model_finalize has not been called");
+  VT_CUDA(cudaSetDevice(m->device));
+  cs->first = is_first != 0;
+  Exec ex(m, cs->prec, (cudaStream_t)stream, workspace, (size_t)workspace_bytes, false);
+  ex.ck = cs;
+  run_decoder(ex, z_chunk, cs->B, Tzc, cs->H, cs->W, x_out);
+  return ex.rc;
+}
+
+// ---- single operators (parity tests) -----------------------------------------------------------------
+int32_t vt_op_conv(int32_t precision, int32_t force_simt, const vt_conv_desc* d, const void* x, const float* w,
+                   const float* bias, const void* res, void* out, void* stream) {
+  if (!d || !x || !w || !out) return fail(VT_ERR_INVALID, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const DType ta = precision == VT_PREC_EXACT ? DT_F32 : DT_BF16;
+  ConvP p;
+  memset(&p, 0, sizeof(p));
+  p.B = d->B; p.Ti = d->Ti; p.Hi = d->Hi; p.Wi = d->Wi; p.Ci = d->Ci;
+  p.isC = 1; p.isW = d->Ci; p.isH = (long long)d->Wi * d->Ci; p.isT = p.isH * d->Hi; p.isB = p.isT * d->Ti;
+  p.kt = d->kt; p.kh = d->kh; p.kw = d->kw; p.st = d->st; p.sh = d->sh; p.sw = d->sw;
+  p.ut = d->ut; p.uh = d->uh; p.uw = d->uw;
+  p.pt = d->pt; p.ph = d->ph0; p.pw = d->pw0;
+  p.To = (d->ut * d->Ti + d->pt - d->kt) / d->st + 1;
+  p.Ho = (d->uh * d->Hi + d->ph0 + d->ph1 - d->kh) / d->sh + 1;
+  p.Wo = (d->uw * d->Wi + d->pw0 + d->pw1 - d->kw) / d->sw + 1;
+  p.Co = d->Co;
+  p.osC = 1; p.osW = p.Co; p.osH = (long long)p.Wo * p.Co; p.osT = p.osH * p.Ho; p.osB = p.osT * p.To;
+  p.bias = bias;
+  p.res_mode = d->res_mode;
+  p.res = res;
+  if (d->res_mode == 1 || d->res_mode == 2) {
+    const int rT = d->res_mode == 2 ? (p.To + 1) / 2 : p.To;
+    p.rsW = p.Co; p.rsH = (long long)p.Wo * p.Co; p.rsT = p.rsH * p.Ho; p.rsB = p.rsT * rT; p.resT = rT;
+    p.ra = d->res_mode == 2 ? d->alpha : 1.f; p.rb = d->res_mode == 2 ? 1.f - d->alpha : 1.f;
+  } else if (d->res_mode == 3) {
+    p.rsW = p.Co; p.rsH = (long long)p.Wo * p.Co; p.rsT = p.rsH * p.Ho; p.rsB = p.rsT * d->Ti; p.resT = d->Ti;
+    p.ra = d->alpha; p.rb = 1.f - d->alpha;
+  } else {
+    p.ra = 0.f; p.rb = 1.f;
+  }
+  const int taps = d->kt * d->kh * d->kw, K = taps * d->Ci;
+  float* wkn = nullptr;
+  bf16* wnk = nullptr;
+  VT_CUDA(cudaMalloc(&wkn, (size_t)K * d->Co * sizeof(float)));
+  VT_CUDA(launch_pack_w_kn(w, wkn, d->Co, d->Ci, taps, s));
+  cudaError_t e;
+  const bool tc = precision == VT_PREC_BF16 && !force_simt && d->Ci % 64 == 0 && d->Co % 16 == 0 && conv_tc_supported(p);
+  if (tc) {
+    VT_CUDA(cudaMalloc(&wnk, (size_t)K * d->Co * sizeof(bf16)));
+    VT_CUDA(launch_pack_w_nk_bf16(w, wnk, d->Co, d->Ci, taps, K, s));
+    e = launch_conv_tc(p, (const bf16*)x, wnk, K, (bf16*)out, s);
+  } else {
+    if (precision == VT_PREC_BF16 && !force_simt) {
+      cudaFree(wkn);
+      return fail(VT_ERR_INVALID, "tcgen05 conv does not support this geometry: %s", conv_tc_last_error());
+    }
+    e = launch_conv_simt(p, ta, ta, ta, x, wkn, out, s);
+  }
+  cudaError_t e2 = cudaStreamSynchronize(s);
+  cudaFree(wkn);
+  if (wnk) cudaFree(wnk);
+  if (e != cudaSuccess) return fail(VT_ERR_CUDA, "conv launch: %s %s", cudaGetErrorString(e), conv_tc_last_error());
+  if (e2 != cudaSuccess) return fail(VT_ERR_CUDA, "conv execution: %s", cudaGetErrorString(e2));
+  return VT_OK;
+}
+
+int32_t vt_op_layernorm(int32_t precision, const void* x, const float* gamma, const float* beta, void* y, int64_t rows,
+                        int32_t C, int32_t apply_silu, void* stream) {
+  const DType ta = precision == VT_PREC_EXACT ? DT_F32 : DT_BF16;
+  VT_CUDA(launch_layernorm(ta, x, gamma, beta, y, rows, C, apply_silu != 0, precision == VT_PREC_EXACT, (cudaStream_t)stream));
+  return VT_OK;
+}
+int32_t vt_op_groupnorm(int32_t precision, const void* x, const float* gamma, const float* beta, void* y, int64_t frames,
+                        int64_t ppf, int32_t C, int32_t per_position, int32_t apply_silu, void* workspace,
+                        int64_t workspace_bytes, void* stream) {
+  const DType ta = precision == VT_PREC_EXACT ? DT_F32 : DT_BF16;
+  if (!per_position && workspace_bytes < (int64_t)(frames * 32 * 2 * sizeof(float))) return fail(VT_ERR_WORKSPACE, "groupnorm stats need %lld bytes", (long long)(frames * 64 * sizeof(float)));
+  VT_CUDA(launch_groupnorm(ta, x, gamma, beta, y, frames, ppf, C, per_position != 0, apply_silu != 0, precision == VT_PREC_EXACT,
+                           (float*)workspace, (cudaStream_t)stream));
+  return VT_OK;
+}
+int32_t vt_op_attention(int32_t precision, const void* q, const void* k, const void* v, void* o, int32_t frames,
+                        int32_t tokens, int32_t C, void* workspace, int64_t workspace_bytes, void* stream) {
+  const DType ta = precision == VT_PREC_EXACT ? DT_F32 : DT_BF16;
+  const size_t sb = align_up((size_t)frames * tokens * tokens * sizeof(float), 1024);
+  const size_t pb = (size_t)frames * tokens * tokens * dtype_size(ta);
+  if ((size_t)workspace_bytes < sb + pb) return fail(VT_ERR_WORKSPACE, "attention needs %zu workspace bytes", sb + pb);
+  float* S = (float*)workspace;
+  void* P = (char*)workspace + sb;
+  cudaStream_t s = (cudaStream_t)stream;
+  const float scale = 1.0f / sqrtf((float)C);
+  const long long qs = (long long)tokens * C, ss = (long long)tokens * tokens;
+  VT_CUDA(launch_gemm_simt(ta, ta, DT_F32, q, k, S, tokens, tokens, C, C, C, 1, tokens, frames, qs, qs, ss, scale, s));
+  VT_CUDA(launch_softmax_rows(ta, S, P, (long long)frames * tokens, tokens, s));
+  VT_CUDA(launch_gemm_simt(ta, ta, ta, P, v, o, tokens, C, tokens, tokens, 1, C, C, frames, ss, qs, qs, 1.0f, s));
+  return VT_OK;
+}
+int32_t vt_op_fsq(const float* h, int32_t d, const int32_t* levels, int64_t P, int32_t B, float* codes, int32_t* indices,
+                  void* stream) {
+  VT_CUDA(launch_fsq(h, d, levels, P, B, codes, indices, (cudaStream_t)stream));
+  return VT_OK;
+}
+int32_t vt_op_fsq_indices_to_codes(const int32_t* indices, int32_t d, const int32_t* levels, int64_t P, int32_t B,
+                                   float* codes, void* stream) {
+  VT_CUDA(launch_fsq_indices_to_codes(indices, d, levels, P, B, codes, (cudaStream_t)stream));
+  return VT_OK;
+}
+int32_t vt_op_kl(const float* h, const float* noise, int32_t zc, int64_t P, int32_t B, int32_t sample, float* z,
+                 float* kl_loss, void* stream) {
+  double* scratch = nullptr;
+  VT_CUDA(cudaMalloc(&scratch, sizeof(double)));
+  cudaError_t e = launch_kl(h, noise, zc, P, B, sample != 0, z, kl_loss, scratch, (cudaStream_t)stream);
+  cudaStreamSynchronize((cudaStream_t)stream);
+  cudaFree(scratch);
+  if (e != cudaSuccess) return fail(VT_ERR_CUDA, "kl: %s", cudaGetErrorString(e));
+  return VT_OK;
+}
+
+}  // extern "C"

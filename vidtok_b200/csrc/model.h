@@ -1,0 +1,98 @@
+// Internal model representation: parameter manifest, packed weights, layer structure (mirrors the module
+// tree of vidtok/modules/model_3dcausal.py:502-885) and the arena used by the executor.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/vidtok_b200.h"
+#include "kernels.h"
+
+namespace vt {
+
+struct Param {
+  std::string name;
+  std::vector<int64_t> shape;
+  int64_t numel = 0;
+  int64_t offset = 0;  // element offset into the raw fp32 pool
+  bool loaded = false;
+};
+
+struct ConvW {
+  int Co = 0, Ci = 0, kt = 1, kh = 1, kw = 1;
+  int pw = -1, pb = -1;      // param indices (weight, bias)
+  float* w_kn = nullptr;     // [K][Co] fp32
+  bf16* w_nk = nullptr;      // [Co][Kpad] bf16 (tcgen05 B operand), may be null
+  int Kpad = 0;
+  const float* bias = nullptr;
+  int taps() const { return kt * kh * kw; }
+};
+struct NormW {
+  int C = 0;
+  int pg = -1, pb = -1;
+  const float* gamma = nullptr;
+  const float* beta = nullptr;
+};
+struct ResBlockW {           // ResnetBlock / ResnetCausalBlock1D / ResnetCausalBlock
+  NormW n1, n2;
+  ConvW c1, c2, nin;
+  bool has_nin = false;
+  std::string key;           // checkpoint prefix (identifies the causal caches in v1.1)
+};
+struct AttnW {
+  NormW n;
+  ConvW q, k, v, proj;
+  std::string key;
+};
+struct LevelW {
+  std::vector<ResBlockW> blk;   // spatial 2D blocks
+  std::vector<ResBlockW> tblk;  // temporal 1D blocks
+  bool has_resample = false;    // Downsample / Upsample conv
+  ConvW resample;
+  bool has_tres = false;        // TimeDownsampleResCausal2x / TimeUpsampleResCausal2x
+  ConvW tconv;
+  int p_mix = -1;
+  float alpha = 0.f;            // sigmoid(mix_factor)
+  int num_temp_upsample = 1;    // v1.1 decoder (model_3dcausal_v1_1.py:856,880-882)
+  std::string tkey;
+};
+struct StackW {
+  ConvW conv_in, conv_out;
+  std::vector<LevelW> levels;
+  ResBlockW mid1, mid2;
+  AttnW attn;
+  NormW norm_out;
+};
+
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0;
+  bool dry = false;
+  size_t peak = 0;
+  struct Blk { size_t off, size; bool free; };
+  std::vector<Blk> blks;
+  void reset(void* b, size_t c, bool d);
+  void* alloc(size_t n);
+  void release(void* p);
+};
+
+}  // namespace vt
+
+struct vt_model {
+  vt_model_desc desc;
+  int device = 0;
+  std::vector<vt::Param> params;
+  std::map<std::string, int> index;
+  float* pool = nullptr;        // raw fp32 parameters (reference layout)
+  int64_t pool_elems = 0;
+  float* packed_kn = nullptr;   // all [K][Co] fp32 repacks
+  vt::bf16* packed_nk = nullptr;
+  bool finalized = false;
+  vt::StackW enc, dec;
+  std::vector<int> spatial_ds, tempo_ds, spatial_us, tempo_us;
+  double* kl_scratch = nullptr;
+  std::vector<vt::ConvW*> convs;   // every conv of both stacks (for packing)
+  std::vector<vt::NormW*> norms;
+};
