@@ -221,3 +221,50 @@ def test_kl_reparameterise():
     torch.cuda.synchronize()
     assert float((z.cpu() - z_ref).abs().max()) <= 1e-5 * float(z_ref.abs().max())
     assert abs(float(kl) - float(log["kl_loss"])) <= 1e-5 * abs(float(log["kl_loss"]))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# tcgen05 / TMA implicit-GEMM kernel (BF16 mode) against fp32 torch on the same bf16-rounded operands
+# ---------------------------------------------------------------------------------------------------------------
+TC_CASES = [
+    # name, Ci, Co, k, stride, (B,T,H,W), res_mode
+    ("tc_k333", 64, 64, (3, 3, 3), (1, 1, 1), (1, 3, 16, 16), 0),
+    ("tc_k133_n256", 128, 256, (1, 3, 3), (1, 1, 1), (1, 2, 32, 32), 0),
+    ("tc_k311", 64, 128, (3, 1, 1), (1, 1, 1), (1, 5, 8, 16), 1),
+    ("tc_k111_two_ntiles", 256, 512, (1, 1, 1), (1, 1, 1), (2, 1, 16, 16), 0),
+    ("tc_bt2", 64, 64, (3, 3, 3), (1, 1, 1), (1, 4, 8, 8), 1),
+    ("tc_partial_tiles", 64, 96, (1, 3, 3), (1, 1, 1), (1, 2, 12, 20), 0),
+    ("tc_tstride_avgpool", 64, 64, (3, 3, 3), (2, 1, 1), (2, 6, 16, 16), 3),
+    ("tc_many_tiles", 64, 64, (3, 3, 3), (1, 1, 1), (2, 4, 64, 64), 1),
+    ("tc_k333_c512", 512, 512, (3, 3, 3), (1, 1, 1), (1, 3, 16, 16), 1),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=[c[0] for c in TC_CASES])
+def test_conv_tc(case):
+    from gpu_util import op_conv
+    _, Ci, Co, k, stride, (B, T, H, W), res_mode = case
+    K = Ci * k[0] * k[1] * k[2]
+    x = rnd(B, Ci, T, H, W, seed=1).bfloat16().float()
+    w = rnd(Co, Ci, *k, seed=2, scale=1 / math.sqrt(K)).bfloat16().float()
+    b = rnd(Co, seed=3)
+    conv = ref_causal_conv(x.double(), w.double(), b.double(), stride).float()
+    alpha = 0.6
+    res = None
+    if res_mode == 1:
+        res = rnd(*conv.shape, seed=4).bfloat16().float()
+        ref = res + conv
+    elif res_mode == 3:
+        res = x
+        x1 = F.avg_pool3d(F.pad(x, (0, 0, 0, 0, 1, 0)), (3, 1, 1), stride=(2, 1, 1))
+        ref = alpha * x1 + (1 - alpha) * conv
+    else:
+        ref = conv
+    got = op_conv(x, w, b, stride=stride, res=res, res_mode=res_mode, alpha=alpha, precision=N.PREC_BF16)
+    assert got.shape == ref.shape
+    err = (got - ref).abs()
+    tol = 2.0 ** -7 * ref.abs() + 2e-2
+    assert bool((err <= tol).all()), f"max err {float(err.max()):.4f} at ref {float(ref.flatten()[err.argmax()]):.4f}"
+    # and the FMA kernel on the same bf16 operands agrees (same math, different engine)
+    simt = op_conv(x, w, b, stride=stride, res=res, res_mode=res_mode, alpha=alpha, precision=N.PREC_BF16, force_simt=True)
+    assert float((got - simt).abs().max()) <= 2.0 ** -6 * float(ref.abs().max()) + 2e-2

@@ -1,6 +1,532 @@
+// tcgen05 / TMA implicit-GEMM convolution for sm_100a (the BF16-mode hot kernel).
+//
+// GEMM view of a causal convolution on channels-last activations [B,T,H,W,C]:
+//   M = output positions, tiled as boxes of BT x BH x BW = 128 positions (one UMMA M=128 tile),
+//   N = Cout tile (BN <= 256 TMEM columns, fp32 accumulators, double-buffered: 2*BN columns),
+//   K = taps x Cin, consumed in steps of 64 channels (one 128-byte swizzle row) per tap.
+// A operand: for every (tap, 64-channel chunk) ONE 5-D TMA box load of the shifted input window
+//   {64, BW, BH, BT, 1} at (c0, w0+dw, h0+dh, t, b): spatial/temporal zero padding is the TMA out-of-bounds
+//   fill, the causal front pad is either skipped taps (zeros), a clamped coordinate (replicate, v1.1 first chunk)
+//   or a second tensor map over the per-layer cache (v1.1 later chunks).  No im2col buffer, no padded copy.
+// B operand: 2-D TMA box {64, BN} of the pre-packed K-major bf16 weights [Cout][taps*Cin].
+// Both land in shared memory in the canonical K-major SWIZZLE_128B layout and feed
+// tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) issued by one thread; accumulators live in TMEM.
+// Warp roles (persistent CTA, one per SM): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator,
+// warps 4-7 = epilogue (tcgen05.ld -> bias / residual / mix -> bf16 -> 16-byte global stores), overlapping the
+// next tile's main loop through the second TMEM accumulator stage.
+#include <cuda.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "common.cuh"
 #include "kernels.h"
+
 namespace vt {
-bool conv_tc_supported(const ConvP&) { return false; }
-cudaError_t launch_conv_tc(const ConvP&, const bf16*, const bf16*, int, bf16*, cudaStream_t) { return cudaErrorNotSupported; }
-const char* conv_tc_last_error() { return ""; }
+
+namespace {
+
+thread_local std::string g_tc_err;
+
+struct TcParams {
+  int B, To, Ho, Wo, Co, Ti;
+  int BW, BH, BT;
+  int tilesW, tilesH, tilesT;
+  int num_n_tiles, BN;
+  long long num_tiles;
+  int kt, kh, kw, Ci, num_kc;
+  int st, pt, ph, pw, to_off;
+  int t_mode, cacheT;
+  int stages;
+  uint32_t tmem_cols;
+  const float* bias;
+  int res_mode;
+  const bf16* res;
+  long long rsB, rsT, rsH, rsW;
+  int resT, res_t_mode;
+  const bf16* res_cache;
+  float ra, rb;
+  bf16* out;
+  long long osB, osT, osH, osW;
+};
+
+constexpr int kThreads = 256;
+constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start>>4 [0,14) | LBO>>4 = 1 [16,30) | SBO>>4 = 64 (8 rows x 128 B) [32,46) | version = 1 [46,48) | layout = 2 [61,64)
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)64 << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
+__device__ __forceinline__ uint32_t make_idesc(int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __low2float(h[i]);
+    f[2 * i + 1] = __high2float(h[i]);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+
+struct TileCoord {
+  int b, t0, h0, w0, n0;
+};
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, long long tile) {
+  TileCoord c;
+  const int nt = (int)(tile % p.num_n_tiles);
+  long long m = tile / p.num_n_tiles;
+  const int tw = (int)(m % p.tilesW); m /= p.tilesW;
+  const int th = (int)(m % p.tilesH); m /= p.tilesH;
+  const int tt = (int)(m % p.tilesT);
+  c.b = (int)(m / p.tilesT);
+  c.t0 = tt * p.BT; c.h0 = th * p.BH; c.w0 = tw * p.BW; c.n0 = nt * p.BN;
+  return c;
+}
+// time coordinate of a tap for a tile; returns false when the whole box is causal zero padding (tap skipped)
+__device__ __forceinline__ bool tap_time(const TcParams& p, int t0, int a, int& tv, bool& from_cache) {
+  tv = (t0 + p.to_off) * p.st + a - p.pt;
+  from_cache = false;
+  if (tv + p.BT <= 0) {
+    if (p.t_mode == 0) return false;
+    if (p.t_mode == 1) { tv = 0; return true; }
+    from_cache = true;
+    tv = p.cacheT + tv;
+    return true;
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmC,
+               const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t b_bytes = (uint32_t)p.BN * 128u;
+  const uint32_t stage_bytes = kABytes + b_bytes;
+  const uint32_t bar_base = smem_base + p.stages * stage_bytes;
+  // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2]; then tmem ptr; then bias[2][256]
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * p.stages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * p.stages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 4);
+  const uint32_t bias_base = tmem_slot + 16u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+  float* sbias = reinterpret_cast<float*>(smem_gen + (bias_base - smem_base));
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    prefetch_tmap(&tmC);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int ntaps = p.kt * p.kh * p.kw;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile);
+        for (int tap = 0; tap < ntaps; ++tap) {
+          const int c = tap % p.kw, bb = (tap / p.kw) % p.kh, a = tap / (p.kw * p.kh);
+          int tv;
+          bool from_cache;
+          if (!tap_time(p, tc.t0, a, tv, from_cache)) continue;
+          const CUtensorMap* mapA = from_cache ? &tmC : &tmA;
+          for (int kc = 0; kc < p.num_kc; ++kc) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_expect_tx(full_bar(stage), stage_bytes);
+            const uint32_t sa = smem_base + stage * stage_bytes;
+            tma_load_5d(sa, mapA, full_bar(stage), kc * 64, tc.w0 + c - p.pw, tc.h0 + bb - p.ph, tv, tc.b);
+            tma_load_2d(sa + kABytes, &tmB, full_bar(stage), tap * p.Ci + kc * 64, tc.n0);
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(p.BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t it = 0;
+      for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const TileCoord tc = decode_tile(p, tile);
+        const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * (uint32_t)p.BN;
+        uint32_t accum = 0;
+        for (int tap = 0; tap < ntaps; ++tap) {
+          const int a = tap / (p.kw * p.kh);
+          int tv;
+          bool from_cache;
+          if (!tap_time(p, tc.t0, a, tv, from_cache)) continue;
+          for (int kc = 0; kc < p.num_kc; ++kc) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t sa = smem_base + stage * stage_bytes;
+            const uint64_t adesc = make_sdesc(sa), bdesc = make_sdesc(sa + kABytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accum);
+              accum = 1;
+            }
+            umma_commit(empty_bar(stage));
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+        umma_commit(tfull_bar(as));
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int dw = row % p.BW, dh = (row / p.BW) % p.BH, dt = row / (p.BW * p.BH);
+    const int et = threadIdx.x - 128;
+    uint32_t it = 0;
+    for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const TileCoord tc = decode_tile(p, tile);
+      const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
+      float* bias_s = sbias + as * 256;
+      for (int i = et; i < p.BN; i += 128) bias_s[i] = p.bias ? p.bias[tc.n0 + i] : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const int t = tc.t0 + dt, h = tc.h0 + dh, w = tc.w0 + dw;
+      const bool valid = (t < p.To) && (h < p.Ho) && (w < p.Wo);
+      bf16* orow = p.out + (long long)tc.b * p.osB + (long long)t * p.osT + (long long)h * p.osH + (long long)w * p.osW + tc.n0;
+      const bf16* r0 = nullptr;
+      const bf16* r1 = nullptr;
+      const bf16* r2 = nullptr;
+      if (valid && p.res_mode == 1) {
+        r0 = p.res + (long long)tc.b * p.rsB + (long long)t * p.rsT + (long long)h * p.rsH + (long long)w * p.rsW + tc.n0;
+      } else if (valid && p.res_mode == 3) {
+        // avg-pool of residual frames 2t-1, 2t, 2t+1 (front pad: zero / frame 0 / 1-frame cache)
+        const long long sp = (long long)tc.b * p.rsB + (long long)h * p.rsH + (long long)w * p.rsW + tc.n0;
+        const int ta = 2 * t - 1, tb = 2 * t, tcn = 2 * t + 1;
+        if (ta >= 0) r0 = p.res + sp + (long long)ta * p.rsT;
+        else if (p.res_t_mode == 1) r0 = p.res + sp;
+        else if (p.res_t_mode == 2) r0 = p.res_cache + (((long long)tc.b * p.Ho + h) * p.Wo + w) * (long long)p.Co + tc.n0;
+        if (tb < p.resT) r1 = p.res + sp + (long long)tb * p.rsT;
+        if (tcn < p.resT) r2 = p.res + sp + (long long)tcn * p.rsT;
+      }
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)p.BN;
+      for (int j = 0; j < p.BN; j += 32) {
+        uint32_t v[32];
+        tmem_ld32(tbase + (uint32_t)j, v);
+        tmem_ld_wait();
+        if (valid) {
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = p.rb * (__uint_as_float(v[i]) + bias_s[j + i]);
+          if (p.res_mode == 1) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float rr[8];
+              unpack8(*reinterpret_cast<const uint4*>(r0 + j + g * 8), rr);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[g * 8 + i] = fmaf(p.ra, rr[i], f[g * 8 + i]);
+            }
+          } else if (p.res_mode == 3) {
+            const float s3 = p.ra * (1.0f / 3.0f);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+              float rr[8];
+              if (r0) { unpack8(*reinterpret_cast<const uint4*>(r0 + j + g * 8), rr);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] += rr[i]; }
+              if (r1) { unpack8(*reinterpret_cast<const uint4*>(r1 + j + g * 8), rr);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] += rr[i]; }
+              if (r2) { unpack8(*reinterpret_cast<const uint4*>(r2 + j + g * 8), rr);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] += rr[i]; }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[g * 8 + i] = fmaf(s3, acc[i], f[g * 8 + i]);
+            }
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(orow + j + g * 8) = pack8(f + g * 8);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+bool choose_tile(const ConvP& p, int& BW, int& BH, int& BT) {
+  const bool allow_bt = (p.st == 1) && (p.t_mode == 0);
+  long long best = -1;
+  auto ceil_to = [](int v, int b) { return (long long)((v + b - 1) / b) * b; };
+  for (int bw = 128; bw >= 8; bw >>= 1) {
+    for (int bh = 128 / bw; bh >= 1; bh >>= 1) {
+      const int bt = 128 / (bw * bh);
+      if (bt > 1 && !allow_bt) continue;
+      if (bt > 16) continue;
+      const long long padded = ceil_to(p.Wo, bw) * ceil_to(p.Ho, bh) * ceil_to(p.To, bt);
+      // prefer less padding; then square-ish spatial tiles (halo reuse in L2); then BT == 1
+      const long long cost = padded * 1024 + (long long)(bw > 16 ? bw - 16 : 16 - bw) * 4 + (bt - 1);
+      if (best < 0 || cost < best) { best = cost; BW = bw; BH = bh; BT = bt; }
+    }
+  }
+  return best >= 0;
+}
+int choose_bn(int Co) {
+  if (Co % 32 != 0) return 0;
+  if (Co <= 256) return Co;
+  if (Co % 256 == 0) return 256;
+  if (Co % 128 == 0) return 128;
+  if (Co % 64 == 0) return 64;
+  return 0;
+}
+
+}  // namespace
+
+const char* conv_tc_last_error() { return g_tc_err.c_str(); }
+
+bool conv_tc_supported(const ConvP& p) {
+  g_tc_err.clear();
+  auto no = [&](const char* why) { g_tc_err = why; return false; };
+  if (p.Ci % 64 != 0) return no("Cin % 64 != 0");
+  if (choose_bn(p.Co) == 0) return no("Cout has no valid N tile");
+  if (p.isC != 1 || p.isW != p.Ci || p.isH != (long long)p.Wi * p.Ci || p.isT != (long long)p.Hi * p.Wi * p.Ci) return no("input is not dense channels-last");
+  if (p.isB % 8 != 0) return no("batch stride not 16-byte aligned");
+  if (p.osC != 1 || p.osW != p.Co) return no("output is not channels-last");
+  if (p.sh != 1 || p.sw != 1) return no("spatial stride");
+  if (p.st != 1 && p.st != 2) return no("time stride");
+  if (p.ut != 1 || p.uh != 1 || p.uw != 1 || p.t_rep != 0) return no("folded upsampling / replicate prefix");
+  if (p.res_mode != 0 && p.res_mode != 1 && p.res_mode != 3) return no("residual mode");
+  if (p.t_mode == 2 && (!p.cache || p.cacheT <= 0)) return no("cache mode without cache");
+  if (p.Wi > 65535 || p.Hi > 65535) return no("extent");
+  if (!get_encode()) return no("cuTensorMapEncodeTiled unavailable");
+  return true;
+}
+
+cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int Kpad, bf16* out, cudaStream_t s) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { g_tc_err = "cuTensorMapEncodeTiled unavailable"; return cudaErrorNotSupported; }
+  TcParams t;
+  memset(&t, 0, sizeof(t));
+  if (!choose_tile(p, t.BW, t.BH, t.BT)) { g_tc_err = "no tile shape"; return cudaErrorInvalidValue; }
+  t.BN = choose_bn(p.Co);
+  t.B = p.B; t.To = p.To; t.Ho = p.Ho; t.Wo = p.Wo; t.Co = p.Co; t.Ti = p.Ti;
+  t.tilesW = (p.Wo + t.BW - 1) / t.BW; t.tilesH = (p.Ho + t.BH - 1) / t.BH; t.tilesT = (p.To + t.BT - 1) / t.BT;
+  t.num_n_tiles = p.Co / t.BN;
+  t.num_tiles = (long long)p.B * t.tilesT * t.tilesH * t.tilesW * t.num_n_tiles;
+  t.kt = p.kt; t.kh = p.kh; t.kw = p.kw; t.Ci = p.Ci; t.num_kc = p.Ci / 64;
+  t.st = p.st; t.pt = p.pt; t.ph = p.ph; t.pw = p.pw; t.to_off = p.to_off;
+  t.t_mode = p.t_mode; t.cacheT = p.cacheT;
+  t.bias = p.bias; t.res_mode = p.res_mode; t.res = (const bf16*)p.res;
+  t.rsB = p.rsB; t.rsT = p.rsT; t.rsH = p.rsH; t.rsW = p.rsW; t.resT = p.resT; t.res_t_mode = p.res_t_mode;
+  t.res_cache = (const bf16*)p.res_cache; t.ra = p.ra; t.rb = p.rb;
+  t.out = out; t.osB = p.osB; t.osT = p.osT; t.osH = p.osH; t.osW = p.osW;
+  const size_t stage_bytes = kABytes + (size_t)t.BN * 128;
+  const size_t budget = 220 * 1024;
+  const size_t fixed = 1024 /*align*/ + 8 * 2 * 8 + 64 + 2 * 256 * 4 + 256;
+  int stages = (int)((budget - fixed) / stage_bytes);
+  if (stages > 8) stages = 8;
+  if (stages < 2) { g_tc_err = "not enough shared memory for 2 stages"; return cudaErrorInvalidValue; }
+  t.stages = stages;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(2 * t.BN)) cols <<= 1;
+  t.tmem_cols = cols;
+  const size_t smem = fixed + (size_t)stages * stage_bytes + 8 * (2 * stages + 4);
+
+  CUtensorMap mA, mC, mB;
+  auto encode_act = [&](CUtensorMap* m, const void* base, int Tn, long long bs) -> bool {
+    cuuint64_t dims[5] = {(cuuint64_t)p.Ci, (cuuint64_t)p.Wi, (cuuint64_t)p.Hi, (cuuint64_t)Tn, (cuuint64_t)p.B};
+    cuuint64_t strides[4] = {(cuuint64_t)p.Ci * 2, (cuuint64_t)p.Wi * p.Ci * 2, (cuuint64_t)p.Hi * p.Wi * p.Ci * 2,
+                             (cuuint64_t)bs * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)t.BW, (cuuint32_t)t.BH, (cuuint32_t)t.BT, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { g_tc_err = "cuTensorMapEncodeTiled(activation) failed: " + std::to_string((int)r); return false; }
+    return true;
+  };
+  if (!encode_act(&mA, x, p.Ti, p.isB)) return cudaErrorInvalidValue;
+  if (p.t_mode == 2) {
+    if (!encode_act(&mC, p.cache, p.cacheT, (long long)p.cacheT * p.Hi * p.Wi * p.Ci)) return cudaErrorInvalidValue;
+  } else {
+    mC = mA;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)Kpad, (cuuint64_t)p.Co};
+    cuuint64_t strides[1] = {(cuuint64_t)Kpad * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)t.BN};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&mB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(w_nk), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { g_tc_err = "cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r); return cudaErrorInvalidValue; }
+  }
+  static int num_sms = 0;
+  static size_t smem_set = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e != cudaSuccess) { g_tc_err = "cudaFuncSetAttribute(smem)"; return e; }
+    smem_set = 227 * 1024;
+  }
+  const unsigned grid = (unsigned)(t.num_tiles < num_sms ? t.num_tiles : num_sms);
+  conv_tc_kernel<<<grid, kThreads, smem, s>>>(mA, mC, mB, t);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace vt
