@@ -84,6 +84,13 @@ int32_t vt_abi_version(void);
 /* number of kernels launched by this library on this thread since the last call with reset != 0 */
 int64_t vt_launch_count(int32_t reset);
 
+/* Optional per-kernel profile of everything this thread launches between start and stop: CUDA events on the launch
+ * stream around every kernel (adds launch gaps: use it to attribute time, not to measure throughput).
+ * vt_profile_stop synchronises the device and writes a JSON object
+ * {"kernel": {"launches": n, "ms": total, "flops": algorithmic, "bytes": algorithmic}, ...}; returns its length. */
+void vt_profile_start(void);
+int32_t vt_profile_stop(char* json, int32_t cap);
+
 /* ---- model lifetime (replaces AutoencodingEngine.__init__, autoencoder.py:103-144) ---- */
 int32_t vt_model_create(const vt_model_desc* desc, int32_t device, vt_model** out);
 void vt_model_destroy(vt_model* m);

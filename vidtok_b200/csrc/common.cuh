@@ -14,6 +14,14 @@ typedef __nv_bfloat16 bf16;
 extern thread_local long long g_launches;
 inline void count_launch(int n = 1) { g_launches += n; }
 
+// ---- optional per-launch profiler (vt_profile_start/stop): CUDA events on the launch stream around every kernel
+struct ProfScope {
+  int idx;
+  cudaStream_t s;
+  ProfScope(const char* name, double flops, double bytes, cudaStream_t stream);
+  ~ProfScope();
+};
+
 // ---- element helpers ------------------------------------------------------------------------------
 __device__ __forceinline__ float to_f(float v) { return v; }
 __device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }

@@ -248,6 +248,8 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvP p, const TIn
 template <typename TIn, typename TOut, typename TRes>
 cudaError_t launch_typed(const ConvP& p, const void* x, const float* w, void* out, cudaStream_t s) {
   const long long M = (long long)p.B * p.To * p.Ho * p.Wo;
+  ProfScope _ps("conv_simt", 2.0 * M * p.kt * p.kh * p.kw * p.Ci * p.Co,
+                (double)p.B * p.Ti * p.Hi * p.Wi * p.Ci * sizeof(TIn) + (double)M * p.Co * sizeof(TOut), s);
   const bool veca = (p.Ci % 4 == 0) && (p.isC == 1) && (p.isW % 4 == 0) && (p.isH % 4 == 0) && (p.isT % 4 == 0) &&
                     (p.isB % 4 == 0);
   const TIn* xi = reinterpret_cast<const TIn*>(x);
@@ -358,6 +360,7 @@ cudaError_t launch_gemm_simt(DType ta, DType tb, DType tc, const void* A, const 
                              long long lda, long long sbn, long long sbk, long long ldc, int batch, long long bsA,
                              long long bsB, long long bsC, float scale, cudaStream_t s) {
   dim3 grid((M + 63) / 64, (N + 63) / 64, batch);
+  ProfScope _ps("gemm_simt", 2.0 * M * N * K * batch, 0.0, s);
 #define VT_GEMM(TA, TB, TC)                                                                                       \
   gemm_simt_kernel<TA, TB, TC><<<grid, 256, 0, s>>>((const TA*)A, (const TB*)B, (TC*)C, M, N, K, lda, sbn, sbk, ldc, \
                                                     bsA, bsB, bsC, scale)

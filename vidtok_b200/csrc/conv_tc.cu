@@ -524,6 +524,9 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
     smem_set = 227 * 1024;
   }
   const unsigned grid = (unsigned)(t.num_tiles < num_sms ? t.num_tiles : num_sms);
+  const double Mrows = (double)p.B * p.To * p.Ho * p.Wo;
+  ProfScope _ps("conv_tc", 2.0 * Mrows * p.kt * p.kh * p.kw * p.Ci * p.Co,
+                2.0 * ((double)p.B * p.Ti * p.Hi * p.Wi * p.Ci + Mrows * p.Co), s);
   conv_tc_kernel<<<grid, kThreads, smem, s>>>(mA, mC, mB, t);
   count_launch();
   return cudaGetLastError();

@@ -1,11 +1,70 @@
 // Bandwidth-bound kernels of the path: per-position LayerNorm(+SiLU), GroupNorm(+SiLU), softmax rows,
 // KL reparameterisation, FSQ quantiser, weight repacking, trilinear time interpolation.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
 #include "common.cuh"
 #include "kernels.h"
 
 namespace vt {
 
 thread_local long long g_launches = 0;
+
+struct ProfRec { const char* name; double flops, bytes; cudaEvent_t e0, e1; };
+thread_local bool g_prof_on = false;
+thread_local std::vector<ProfRec> g_prof;
+thread_local std::vector<cudaEvent_t> g_prof_pool;
+static cudaEvent_t prof_event() {
+  cudaEvent_t e;
+  if (!g_prof_pool.empty()) { e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEventCreate(&e);
+  return e;
+}
+ProfScope::ProfScope(const char* name, double flops, double bytes, cudaStream_t stream) : idx(-1), s(stream) {
+  if (!g_prof_on) return;
+  ProfRec r{name, flops, bytes, prof_event(), prof_event()};
+  cudaEventRecord(r.e0, s);
+  idx = (int)g_prof.size();
+  g_prof.push_back(r);
+}
+ProfScope::~ProfScope() {
+  if (idx >= 0) cudaEventRecord(g_prof[idx].e1, s);
+}
+void prof_start() {
+  for (auto& r : g_prof) { g_prof_pool.push_back(r.e0); g_prof_pool.push_back(r.e1); }
+  g_prof.clear();
+  g_prof_on = true;
+}
+// aggregates per kernel name into a JSON object; returns the number of bytes written (0 if it does not fit)
+int prof_stop(char* buf, int cap) {
+  g_prof_on = false;
+  cudaDeviceSynchronize();
+  struct Agg { const char* name; long long n; double ms, flops, bytes; };
+  std::vector<Agg> aggs;
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    Agg* a = nullptr;
+    for (auto& x : aggs) if (strcmp(x.name, r.name) == 0) a = &x;
+    if (!a) { aggs.push_back({r.name, 0, 0, 0, 0}); a = &aggs.back(); }
+    a->n++; a->ms += ms; a->flops += r.flops; a->bytes += r.bytes;
+    g_prof_pool.push_back(r.e0); g_prof_pool.push_back(r.e1);
+  }
+  g_prof.clear();
+  std::string out = "{";
+  for (size_t i = 0; i < aggs.size(); ++i) {
+    char tmp[256];
+    snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"launches\": %lld, \"ms\": %.6f, \"flops\": %.6e, \"bytes\": %.6e}", i ? ", " : "",
+             aggs[i].name, aggs[i].n, aggs[i].ms, aggs[i].flops, aggs[i].bytes);
+    out += tmp;
+  }
+  out += "}";
+  if ((int)out.size() + 1 > cap) return 0;
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return (int)out.size();
+}
 
 namespace {
 
@@ -420,6 +479,7 @@ inline int grid_for(long long total, int block = 256) {
 
 cudaError_t launch_layernorm(DType t, const void* x, const float* gamma, const float* beta, void* y, long long rows,
                              int C, bool silu, bool exact, cudaStream_t s) {
+  ProfScope _ps("layernorm", 0.0, 2.0 * rows * C * (double)dtype_size(t), s);
   const int wpb = 8;
   const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
   if (rows == 0) return cudaSuccess;
@@ -455,6 +515,7 @@ cudaError_t launch_layernorm(DType t, const void* x, const float* gamma, const f
 cudaError_t launch_groupnorm(DType t, const void* x, const float* gamma, const float* beta, void* y, long long frames,
                              long long ppf, int C, bool per_position, bool silu, bool exact, float* stats,
                              cudaStream_t s) {
+  ProfScope _ps("groupnorm", 0.0, 2.0 * frames * ppf * C * (double)dtype_size(t), s);
   if (C % 32 != 0) return cudaErrorInvalidValue;
   const long long total = frames * ppf * C;
   if (total == 0) return cudaSuccess;
@@ -481,6 +542,7 @@ cudaError_t launch_groupnorm(DType t, const void* x, const float* gamma, const f
 }
 
 cudaError_t launch_softmax_rows(DType tout, const float* S, void* P, long long rows, int N, cudaStream_t s) {
+  ProfScope _ps("softmax", 0.0, (double)rows * N * (4.0 + dtype_size(tout)), s);
   if (rows == 0) return cudaSuccess;
   if (tout == DT_F32) softmax_rows_kernel<float><<<(unsigned)rows, 256, 0, s>>>(S, (float*)P, N);
   else softmax_rows_kernel<bf16><<<(unsigned)rows, 256, 0, s>>>(S, (bf16*)P, N);
@@ -529,6 +591,7 @@ cudaError_t launch_pack_w_nk_bf16(const float* w, bf16* out, int Co, int Ci, int
   return cudaGetLastError();
 }
 cudaError_t launch_time_interp2x(DType t, const void* x, void* y, int B, int T, long long hwc, cudaStream_t s) {
+  ProfScope _ps("time_interp2x", 0.0, 3.0 * B * T * hwc * (double)dtype_size(t), s);
   const long long total = (long long)B * 2 * T * hwc;
   if (total == 0) return cudaSuccess;
   if (t == DT_F32) time_interp2x_kernel<float><<<grid_for(total), 256, 0, s>>>((const float*)x, (float*)y, B, T, hwc);
@@ -538,6 +601,7 @@ cudaError_t launch_time_interp2x(DType t, const void* x, void* y, int B, int T, 
 }
 cudaError_t launch_upsample_nearest(DType t, const void* x, void* y, int B, int T, int H, int W, int C, int ut, int uh,
                                     int uw, cudaStream_t s) {
+  ProfScope _ps("upsample_nearest", 0.0, (double)B * T * H * W * C * dtype_size(t) * (1.0 + ut * uh * uw), s);
   if (C % 4 != 0) return cudaErrorInvalidValue;
   const long long total = (long long)B * T * ut * H * uh * W * uw * (C / 4);
   if (total == 0) return cudaSuccess;

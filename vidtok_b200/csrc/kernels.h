@@ -10,6 +10,9 @@ namespace vt {
 enum DType { DT_F32 = 0, DT_BF16 = 1 };
 inline size_t dtype_size(DType t) { return t == DT_F32 ? 4 : 2; }
 
+void prof_start();
+int prof_stop(char* buf, int cap);
+
 // conv_simt.cu
 cudaError_t launch_conv_simt(const ConvP& p, DType tin, DType tout, DType tres, const void* x, const float* w_kn,
                              void* out, cudaStream_t s);

@@ -870,6 +870,9 @@ int64_t vt_launch_count(int32_t reset) {
   return v;
 }
 
+void vt_profile_start(void) { prof_start(); }
+int32_t vt_profile_stop(char* json, int32_t cap) { return prof_stop(json, cap); }
+
 int32_t vt_model_create(const vt_model_desc* desc, int32_t device, vt_model** out) {
   if (!desc || !out) return fail(VT_ERR_INVALID, "null argument");
   const vt_model_desc& d = *desc;
