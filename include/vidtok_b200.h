@@ -89,6 +89,7 @@ int64_t vt_launch_count(int32_t reset);
  * vt_profile_stop synchronises the device and writes a JSON object
  * {"kernel": {"launches": n, "ms": total, "flops": algorithmic, "bytes": algorithmic}, ...}; returns its length. */
 void vt_profile_start(void);
+void vt_profile_start_detailed(void); /* keys additionally carry the layer geometry */
 int32_t vt_profile_stop(char* json, int32_t cap);
 
 /* ---- model lifetime (replaces AutoencodingEngine.__init__, autoencoder.py:103-144) ---- */

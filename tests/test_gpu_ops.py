@@ -268,3 +268,34 @@ def test_conv_tc(case):
     # and the FMA kernel on the same bf16 operands agrees (same math, different engine)
     simt = op_conv(x, w, b, stride=stride, res=res, res_mode=res_mode, alpha=alpha, precision=N.PREC_BF16, force_simt=True)
     assert float((got - simt).abs().max()) <= 2.0 ** -6 * float(ref.abs().max()) + 2e-2
+
+
+def test_conv_tc_downsample_stride2():
+    """Downsample (pad (0,1,0,1), 3x3 stride 2) on the tcgen05 path: parity-view tensor maps."""
+    from gpu_util import op_conv
+    for (B, T, H, W, Ci, Co) in [(1, 2, 32, 32, 64, 64), (2, 3, 64, 32, 128, 128)]:
+        x = rnd(B, Ci, T, H, W, seed=1).bfloat16().float()
+        w = rnd(Co, Ci, 1, 3, 3, seed=2, scale=1 / math.sqrt(9 * Ci)).bfloat16().float()
+        b = rnd(Co, seed=3)
+        y = F.conv2d(F.pad(x.permute(0, 2, 1, 3, 4).reshape(B * T, Ci, H, W), (0, 1, 0, 1)), w[:, :, 0], b, stride=2)
+        ref = y.reshape(B, T, Co, H // 2, W // 2).permute(0, 2, 1, 3, 4)
+        got = op_conv(x, w, b, stride=(1, 2, 2), pads=(0, 1, 0, 1), precision=N.PREC_BF16)
+        assert got.shape == ref.shape
+        err = (got - ref).abs()
+        assert bool((err <= 2.0 ** -7 * ref.abs() + 2e-2).all()), float(err.max())
+
+
+def test_layernorm_bf16_large_rows():
+    """persistent bf16 LayerNorm kernel: row counts that do not divide the per-pass row groups"""
+    for C_ in (128, 256, 512):
+        for rows in (1, 3, 31, 4099):
+            x = (rnd(rows, C_, seed=rows, scale=2.0) + 0.5).bfloat16()
+            g, b = 1 + 0.1 * rnd(C_, seed=2), 0.1 * rnd(C_, seed=3)
+            ref = F.layer_norm(x.float(), (C_,), g, b, eps=1e-6)
+            ref = ref * torch.sigmoid(ref)
+            xd, gd, bd = x.cuda(), g.cuda(), b.cuda()
+            y = torch.empty_like(xd)
+            N.check(N.lib().vt_op_layernorm(N.PREC_BF16, C.c_void_p(xd.data_ptr()), C.c_void_p(gd.data_ptr()), C.c_void_p(bd.data_ptr()),
+                                            C.c_void_p(y.data_ptr()), rows, C_, 1, None))
+            torch.cuda.synchronize()
+            assert float((y.float().cpu() - ref).abs().max()) < 0.04

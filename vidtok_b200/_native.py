@@ -37,6 +37,7 @@ _SIGS = {
     "vt_abi_version": (_I32, []),
     "vt_launch_count": (_I64, [_I32]),
     "vt_profile_start": (None, []),
+    "vt_profile_start_detailed": (None, []),
     "vt_profile_stop": (_I32, [C.c_char_p, _I32]),
     "vt_model_create": (_I32, [C.POINTER(ModelDesc), _I32, C.POINTER(_P)]),
     "vt_model_destroy": (None, [_P]),

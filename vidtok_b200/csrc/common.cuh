@@ -18,9 +18,10 @@ inline void count_launch(int n = 1) { g_launches += n; }
 struct ProfScope {
   int idx;
   cudaStream_t s;
-  ProfScope(const char* name, double flops, double bytes, cudaStream_t stream);
+  ProfScope(const char* name, double flops, double bytes, cudaStream_t stream, const char* detail = nullptr);
   ~ProfScope();
 };
+bool prof_enabled();
 
 // ---- element helpers ------------------------------------------------------------------------------
 __device__ __forceinline__ float to_f(float v) { return v; }

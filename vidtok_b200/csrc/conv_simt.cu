@@ -2,6 +2,8 @@
 // does not take: Cin=3 stem, Cout<=8 heads).  One kernel covers every convolution geometry of the path via
 // ConvP (common.cuh).  GEMM view: M = B*To*Ho*Wo output positions, N = Cout, K = kt*kh*kw*Cin ordered
 // tap-major / channel-minor; weights are pre-packed as [K][Cout] fp32.
+#include <cstdio>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -248,8 +250,10 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvP p, const TIn
 template <typename TIn, typename TOut, typename TRes>
 cudaError_t launch_typed(const ConvP& p, const void* x, const float* w, void* out, cudaStream_t s) {
   const long long M = (long long)p.B * p.To * p.Ho * p.Wo;
+  char det[96] = "";
+  if (prof_enabled()) snprintf(det, sizeof(det), "k%d%d%d s%d%d%d u%d%d%d %d->%d @%dx%dx%d", p.kt, p.kh, p.kw, p.st, p.sh, p.sw, p.ut, p.uh, p.uw, p.Ci, p.Co, p.To, p.Ho, p.Wo);
   ProfScope _ps("conv_simt", 2.0 * M * p.kt * p.kh * p.kw * p.Ci * p.Co,
-                (double)p.B * p.Ti * p.Hi * p.Wi * p.Ci * sizeof(TIn) + (double)M * p.Co * sizeof(TOut), s);
+                (double)p.B * p.Ti * p.Hi * p.Wi * p.Ci * sizeof(TIn) + (double)M * p.Co * sizeof(TOut), s, det);
   const bool veca = (p.Ci % 4 == 0) && (p.isC == 1) && (p.isW % 4 == 0) && (p.isH % 4 == 0) && (p.isT % 4 == 0) &&
                     (p.isB % 4 == 0);
   const TIn* xi = reinterpret_cast<const TIn*>(x);

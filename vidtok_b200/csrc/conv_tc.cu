@@ -37,6 +37,7 @@ struct TcParams {
   long long num_tiles;
   int kt, kh, kw, Ci, num_kc;
   int st, pt, ph, pw, to_off;
+  int sp;                    // spatial stride (1 or 2, same in H and W)
   int t_mode, cacheT;
   int stages;
   uint32_t tmem_cols;
@@ -47,8 +48,16 @@ struct TcParams {
   int resT, res_t_mode;
   const bf16* res_cache;
   float ra, rb;
-  bf16* out;
-  long long osB, osT, osH, osW;
+  void* out;
+  long long osB, osT, osH, osW, osC;
+  int out_f32;               // 1: fp32 output with channel stride osC (external NCDHW heads), only n < Co_real stored
+  int Co_real;
+};
+
+struct TcMaps {
+  CUtensorMap a[4];          // activation maps; [1..3] are the odd-parity views used by stride-2 convolutions
+  CUtensorMap c;             // v1.1 causal cache
+  CUtensorMap b;             // weights
 };
 
 constexpr int kThreads = 256;
@@ -190,8 +199,7 @@ __device__ __forceinline__ bool tap_time(const TcParams& p, int t0, int a, int& 
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmC,
-               const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -210,9 +218,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   float* sbias = reinterpret_cast<float*>(smem_gen + (bias_base - smem_base));
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmA);
-    prefetch_tmap(&tmB);
-    prefetch_tmap(&tmC);
+    prefetch_tmap(&maps.a[0]);
+    prefetch_tmap(&maps.b);
+    if (p.sp == 2) { prefetch_tmap(&maps.a[1]); prefetch_tmap(&maps.a[2]); prefetch_tmap(&maps.a[3]); }
+    if (p.t_mode == 2) prefetch_tmap(&maps.c);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -248,13 +257,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           int tv;
           bool from_cache;
           if (!tap_time(p, tc.t0, a, tv, from_cache)) continue;
-          const CUtensorMap* mapA = from_cache ? &tmC : &tmA;
+          // input coordinates of the box origin.  Stride 2: tap (bb,c) reads rows 2*h + (bb-ph), i.e. row h + ((bb-ph)>>1)
+          // of the parity-((bb-ph)&1) view (a tensor map over every second row/column, see launch_conv_tc).
+          const int dh = bb - p.ph, dw2 = c - p.pw;
+          int ch, cw;
+          const CUtensorMap* mapA;
+          if (p.sp == 2) {
+            mapA = &maps.a[(dh & 1) * 2 + (dw2 & 1)];
+            ch = tc.h0 + (dh >> 1);
+            cw = tc.w0 + (dw2 >> 1);
+          } else {
+            mapA = &maps.a[0];
+            ch = tc.h0 + dh;
+            cw = tc.w0 + dw2;
+          }
+          if (from_cache) mapA = &maps.c;
           for (int kc = 0; kc < p.num_kc; ++kc) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             mbar_expect_tx(full_bar(stage), stage_bytes);
             const uint32_t sa = smem_base + stage * stage_bytes;
-            tma_load_5d(sa, mapA, full_bar(stage), kc * 64, tc.w0 + c - p.pw, tc.h0 + bb - p.ph, tv, tc.b);
-            tma_load_2d(sa + kABytes, &tmB, full_bar(stage), tap * p.Ci + kc * 64, tc.n0);
+            tma_load_5d(sa, mapA, full_bar(stage), kc * 64, cw, ch, tv, tc.b);
+            tma_load_2d(sa + kABytes, &maps.b, full_bar(stage), tap * p.Ci + kc * 64, tc.n0);
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -307,13 +330,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const TileCoord tc = decode_tile(p, tile);
       const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
       float* bias_s = sbias + as * 256;
-      for (int i = et; i < p.BN; i += 128) bias_s[i] = p.bias ? p.bias[tc.n0 + i] : 0.f;
+      for (int i = et; i < p.BN; i += 128) bias_s[i] = (p.bias && tc.n0 + i < p.Co_real) ? p.bias[tc.n0 + i] : 0.f;
       asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const int t = tc.t0 + dt, h = tc.h0 + dh, w = tc.w0 + dw;
       const bool valid = (t < p.To) && (h < p.Ho) && (w < p.Wo);
-      bf16* orow = p.out + (long long)tc.b * p.osB + (long long)t * p.osT + (long long)h * p.osH + (long long)w * p.osW + tc.n0;
+      const long long ooff = (long long)tc.b * p.osB + (long long)t * p.osT + (long long)h * p.osH + (long long)w * p.osW;
+      bf16* orow = reinterpret_cast<bf16*>(p.out) + ooff + tc.n0;
       const bf16* r0 = nullptr;
       const bf16* r1 = nullptr;
       const bf16* r2 = nullptr;
@@ -365,8 +389,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int i = 0; i < 8; ++i) f[g * 8 + i] = fmaf(s3, acc[i], f[g * 8 + i]);
             }
           }
+          if (p.out_f32) {
+            float* of = reinterpret_cast<float*>(p.out) + ooff;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(orow + j + g * 8) = pack8(f + g * 8);
+            for (int i = 0; i < 32; ++i)
+              if (tc.n0 + j + i < p.Co_real) of[(long long)(tc.n0 + j + i) * p.osC] = f[i];
+          } else {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(orow + j + g * 8) = pack8(f + g * 8);
+          }
         }
       }
       tc_fence_before();
@@ -433,42 +464,52 @@ int choose_bn(int Co) {
 
 const char* conv_tc_last_error() { return g_tc_err.c_str(); }
 
-bool conv_tc_supported(const ConvP& p) {
+bool conv_tc_supported(const ConvP& p, DType tout) {
   g_tc_err.clear();
   auto no = [&](const char* why) { g_tc_err = why; return false; };
   if (p.Ci % 64 != 0) return no("Cin % 64 != 0");
-  if (choose_bn(p.Co) == 0) return no("Cout has no valid N tile");
+  const int Co_pad = (p.Co + 31) / 32 * 32;
+  if (choose_bn(Co_pad) == 0) return no("Cout has no valid N tile");
   if (p.isC != 1 || p.isW != p.Ci || p.isH != (long long)p.Wi * p.Ci || p.isT != (long long)p.Hi * p.Wi * p.Ci) return no("input is not dense channels-last");
   if (p.isB % 8 != 0) return no("batch stride not 16-byte aligned");
-  if (p.osC != 1 || p.osW != p.Co) return no("output is not channels-last");
-  if (p.sh != 1 || p.sw != 1) return no("spatial stride");
+  if (tout == DT_BF16) {
+    if (p.Co % 32 != 0) return no("bf16 output needs Cout % 32 == 0");
+    if (p.osC != 1 || p.osW % 8 != 0 || p.osH % 8 != 0 || p.osT % 8 != 0 || p.osB % 8 != 0) return no("output rows are not 16-byte aligned channels-last");
+  }
+  if (!((p.sh == 1 && p.sw == 1) || (p.sh == 2 && p.sw == 2))) return no("spatial stride");
+  if (p.sh == 2 && ((p.Hi | p.Wi) & 1)) return no("stride-2 needs even H, W");
   if (p.st != 1 && p.st != 2) return no("time stride");
   if (p.ut != 1 || p.uh != 1 || p.uw != 1 || p.t_rep != 0) return no("folded upsampling / replicate prefix");
   if (p.res_mode != 0 && p.res_mode != 1 && p.res_mode != 3) return no("residual mode");
+  if (p.res_mode != 0 && tout != DT_BF16) return no("residual with fp32 output");
   if (p.t_mode == 2 && (!p.cache || p.cacheT <= 0)) return no("cache mode without cache");
   if (p.Wi > 65535 || p.Hi > 65535) return no("extent");
   if (!get_encode()) return no("cuTensorMapEncodeTiled unavailable");
   return true;
 }
 
-cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int Kpad, bf16* out, cudaStream_t s) {
+// w_nk: [Co_pad][Kpad] bf16 with Co_pad = roundup(Co, 32) (rows >= Co are zero).
+cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int Kpad, void* out, DType tout, cudaStream_t s) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { g_tc_err = "cuTensorMapEncodeTiled unavailable"; return cudaErrorNotSupported; }
   TcParams t;
   memset(&t, 0, sizeof(t));
   if (!choose_tile(p, t.BW, t.BH, t.BT)) { g_tc_err = "no tile shape"; return cudaErrorInvalidValue; }
-  t.BN = choose_bn(p.Co);
+  const int Co_pad = (p.Co + 31) / 32 * 32;
+  t.BN = choose_bn(Co_pad);
   t.B = p.B; t.To = p.To; t.Ho = p.Ho; t.Wo = p.Wo; t.Co = p.Co; t.Ti = p.Ti;
   t.tilesW = (p.Wo + t.BW - 1) / t.BW; t.tilesH = (p.Ho + t.BH - 1) / t.BH; t.tilesT = (p.To + t.BT - 1) / t.BT;
-  t.num_n_tiles = p.Co / t.BN;
+  t.num_n_tiles = Co_pad / t.BN;
   t.num_tiles = (long long)p.B * t.tilesT * t.tilesH * t.tilesW * t.num_n_tiles;
   t.kt = p.kt; t.kh = p.kh; t.kw = p.kw; t.Ci = p.Ci; t.num_kc = p.Ci / 64;
-  t.st = p.st; t.pt = p.pt; t.ph = p.ph; t.pw = p.pw; t.to_off = p.to_off;
+  t.st = p.st; t.pt = p.pt; t.ph = p.ph; t.pw = p.pw; t.to_off = p.to_off; t.sp = p.sh;
   t.t_mode = p.t_mode; t.cacheT = p.cacheT;
   t.bias = p.bias; t.res_mode = p.res_mode; t.res = (const bf16*)p.res;
   t.rsB = p.rsB; t.rsT = p.rsT; t.rsH = p.rsH; t.rsW = p.rsW; t.resT = p.resT; t.res_t_mode = p.res_t_mode;
   t.res_cache = (const bf16*)p.res_cache; t.ra = p.ra; t.rb = p.rb;
-  t.out = out; t.osB = p.osB; t.osT = p.osT; t.osH = p.osH; t.osW = p.osW;
+  t.out = out; t.osB = p.osB; t.osT = p.osT; t.osH = p.osH; t.osW = p.osW; t.osC = p.osC;
+  t.out_f32 = (tout == DT_F32) ? 1 : 0;
+  t.Co_real = p.Co;
   const size_t stage_bytes = kABytes + (size_t)t.BN * 128;
   const size_t budget = 220 * 1024;
   const size_t fixed = 1024 /*align*/ + 8 * 2 * 8 + 64 + 2 * 256 * 4 + 256;
@@ -481,53 +522,66 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   t.tmem_cols = cols;
   const size_t smem = fixed + (size_t)stages * stage_bytes + 8 * (2 * stages + 4);
 
-  CUtensorMap mA, mC, mB;
-  auto encode_act = [&](CUtensorMap* m, const void* base, int Tn, long long bs) -> bool {
-    cuuint64_t dims[5] = {(cuuint64_t)p.Ci, (cuuint64_t)p.Wi, (cuuint64_t)p.Hi, (cuuint64_t)Tn, (cuuint64_t)p.B};
-    cuuint64_t strides[4] = {(cuuint64_t)p.Ci * 2, (cuuint64_t)p.Wi * p.Ci * 2, (cuuint64_t)p.Hi * p.Wi * p.Ci * 2,
-                             (cuuint64_t)bs * 2};
+  TcMaps maps;
+  // activation view: element (c, w, h, t, b) at base + c + w*sw_ + h*sh_ + t*isT + b*bs  (elements)
+  auto encode_act = [&](CUtensorMap* m, const bf16* base, int Wn, int Hn, long long sw_, long long sh_, int Tn, long long st_, long long bs) -> bool {
+    cuuint64_t dims[5] = {(cuuint64_t)p.Ci, (cuuint64_t)Wn, (cuuint64_t)Hn, (cuuint64_t)Tn, (cuuint64_t)p.B};
+    cuuint64_t strides[4] = {(cuuint64_t)sw_ * 2, (cuuint64_t)sh_ * 2, (cuuint64_t)st_ * 2, (cuuint64_t)bs * 2};
     cuuint32_t box[5] = {64, (cuuint32_t)t.BW, (cuuint32_t)t.BH, (cuuint32_t)t.BT, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<bf16*>(base), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { g_tc_err = "cuTensorMapEncodeTiled(activation) failed: " + std::to_string((int)r); return false; }
     return true;
   };
-  if (!encode_act(&mA, x, p.Ti, p.isB)) return cudaErrorInvalidValue;
-  if (p.t_mode == 2) {
-    if (!encode_act(&mC, p.cache, p.cacheT, (long long)p.cacheT * p.Hi * p.Wi * p.Ci)) return cudaErrorInvalidValue;
+  if (p.sh == 1) {
+    if (!encode_act(&maps.a[0], x, p.Wi, p.Hi, p.isW, p.isH, p.Ti, p.isT, p.isB)) return cudaErrorInvalidValue;
+    maps.a[1] = maps.a[2] = maps.a[3] = maps.a[0];
   } else {
-    mC = mA;
+    // parity views: rows hp, hp+2, ... and columns wp, wp+2, ...
+    for (int hp = 0; hp < 2; ++hp)
+      for (int wp = 0; wp < 2; ++wp)
+        if (!encode_act(&maps.a[hp * 2 + wp], x + (long long)hp * p.isH + (long long)wp * p.isW, (p.Wi - wp + 1) / 2,
+                        (p.Hi - hp + 1) / 2, 2 * p.isW, 2 * p.isH, p.Ti, p.isT, p.isB))
+          return cudaErrorInvalidValue;
+  }
+  if (p.t_mode == 2) {
+    if (p.sh != 1) { g_tc_err = "cache mode with spatial stride"; return cudaErrorInvalidValue; }
+    if (!encode_act(&maps.c, (const bf16*)p.cache, p.Wi, p.Hi, p.isW, p.isH, p.cacheT, p.isT, (long long)p.cacheT * p.Hi * p.Wi * p.Ci)) return cudaErrorInvalidValue;
+  } else {
+    maps.c = maps.a[0];
   }
   {
-    cuuint64_t dims[2] = {(cuuint64_t)Kpad, (cuuint64_t)p.Co};
+    cuuint64_t dims[2] = {(cuuint64_t)Kpad, (cuuint64_t)Co_pad};
     cuuint64_t strides[1] = {(cuuint64_t)Kpad * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)t.BN};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(&mB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(w_nk), dims, strides, box, es,
+    CUresult r = enc(&maps.b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(w_nk), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { g_tc_err = "cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r); return cudaErrorInvalidValue; }
   }
   static int num_sms = 0;
-  static size_t smem_set = 0;
+  static bool smem_set = false;
   if (num_sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (num_sms <= 0) num_sms = 148;
   }
-  if (smem > smem_set) {
+  if (!smem_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) { g_tc_err = "cudaFuncSetAttribute(smem)"; return e; }
-    smem_set = 227 * 1024;
+    smem_set = true;
   }
   const unsigned grid = (unsigned)(t.num_tiles < num_sms ? t.num_tiles : num_sms);
   const double Mrows = (double)p.B * p.To * p.Ho * p.Wo;
+  char det[96] = "";
+  if (prof_enabled()) snprintf(det, sizeof(det), "k%d%d%d s%d%d %d->%d @%dx%dx%d tile%dx%dx%d bn%d", p.kt, p.kh, p.kw, p.st, p.sh, p.Ci, p.Co, p.To, p.Ho, p.Wo, t.BT, t.BH, t.BW, t.BN);
   ProfScope _ps("conv_tc", 2.0 * Mrows * p.kt * p.kh * p.kw * p.Ci * p.Co,
-                2.0 * ((double)p.B * p.Ti * p.Hi * p.Wi * p.Ci + Mrows * p.Co), s);
-  conv_tc_kernel<<<grid, kThreads, smem, s>>>(mA, mC, mB, t);
+                2.0 * ((double)p.B * p.Ti * p.Hi * p.Wi * p.Ci) + Mrows * p.Co * (tout == DT_F32 ? 4.0 : 2.0), s, det);
+  conv_tc_kernel<<<grid, kThreads, smem, s>>>(maps, t);
   count_launch();
   return cudaGetLastError();
 }

@@ -12,8 +12,12 @@ namespace vt {
 
 thread_local long long g_launches = 0;
 
-struct ProfRec { const char* name; double flops, bytes; cudaEvent_t e0, e1; };
 thread_local bool g_prof_on = false;
+static bool g_prof_on_flag() { return g_prof_on; }
+struct ProfRec { std::string name; double flops, bytes; cudaEvent_t e0, e1; };
+thread_local bool g_prof_detail = false;
+bool prof_enabled() { return g_prof_on_flag(); }
+
 thread_local std::vector<ProfRec> g_prof;
 thread_local std::vector<cudaEvent_t> g_prof_pool;
 static cudaEvent_t prof_event() {
@@ -22,9 +26,11 @@ static cudaEvent_t prof_event() {
   cudaEventCreate(&e);
   return e;
 }
-ProfScope::ProfScope(const char* name, double flops, double bytes, cudaStream_t stream) : idx(-1), s(stream) {
+ProfScope::ProfScope(const char* name, double flops, double bytes, cudaStream_t stream, const char* detail) : idx(-1), s(stream) {
   if (!g_prof_on) return;
-  ProfRec r{name, flops, bytes, prof_event(), prof_event()};
+  std::string nm = name;
+  if (g_prof_detail && detail) { nm += " "; nm += detail; }
+  ProfRec r{nm, flops, bytes, prof_event(), prof_event()};
   cudaEventRecord(r.e0, s);
   idx = (int)g_prof.size();
   g_prof.push_back(r);
@@ -32,6 +38,7 @@ ProfScope::ProfScope(const char* name, double flops, double bytes, cudaStream_t 
 ProfScope::~ProfScope() {
   if (idx >= 0) cudaEventRecord(g_prof[idx].e1, s);
 }
+void prof_set_detail(bool on) { g_prof_detail = on; }
 void prof_start() {
   for (auto& r : g_prof) { g_prof_pool.push_back(r.e0); g_prof_pool.push_back(r.e1); }
   g_prof.clear();
@@ -41,13 +48,13 @@ void prof_start() {
 int prof_stop(char* buf, int cap) {
   g_prof_on = false;
   cudaDeviceSynchronize();
-  struct Agg { const char* name; long long n; double ms, flops, bytes; };
+  struct Agg { std::string name; long long n; double ms, flops, bytes; };
   std::vector<Agg> aggs;
   for (auto& r : g_prof) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, r.e0, r.e1);
     Agg* a = nullptr;
-    for (auto& x : aggs) if (strcmp(x.name, r.name) == 0) a = &x;
+    for (auto& x : aggs) if (x.name == r.name) a = &x;
     if (!a) { aggs.push_back({r.name, 0, 0, 0, 0}); a = &aggs.back(); }
     a->n++; a->ms += ms; a->flops += r.flops; a->bytes += r.bytes;
     g_prof_pool.push_back(r.e0); g_prof_pool.push_back(r.e1);
@@ -55,9 +62,9 @@ int prof_stop(char* buf, int cap) {
   g_prof.clear();
   std::string out = "{";
   for (size_t i = 0; i < aggs.size(); ++i) {
-    char tmp[256];
+    char tmp[512];
     snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"launches\": %lld, \"ms\": %.6f, \"flops\": %.6e, \"bytes\": %.6e}", i ? ", " : "",
-             aggs[i].name, aggs[i].n, aggs[i].ms, aggs[i].flops, aggs[i].bytes);
+             aggs[i].name.c_str(), aggs[i].n, aggs[i].ms, aggs[i].flops, aggs[i].bytes);
     out += tmp;
   }
   out += "}";
@@ -124,6 +131,85 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const T* __restrict_
       o[j] = SILU ? act_silu<EXACT>(t) : t;
     }
     store4(yr + c, o);
+  }
+}
+
+// bf16 fast path: persistent warps, 16-byte loads (8 channels per lane), two row-groups in flight per warp.
+// C = 128: half a warp per row (two rows per warp pass); C = 256: one warp per row; C = 512: two vectors per lane.
+template <int C, bool SILU>
+__global__ void __launch_bounds__(256) layernorm_bf16_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, bf16* __restrict__ y,
+                                                             long long rows) {
+  constexpr int LPR = (C / 8) < 32 ? (C / 8) : 32;  // lanes per row
+  constexpr int V = C / (8 * LPR);                  // 16-byte vectors per lane
+  constexpr int RPW = 32 / LPR;                     // rows per warp pass
+  constexpr int U = 2;                              // passes in flight
+  const int lane = threadIdx.x & 31, sub = lane / LPR, l = lane % LPR;
+  const long long gw = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long nw = (long long)gridDim.x * 8;
+  float g[V][8], b[V][8];
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const int c = (v * LPR + l) * 8;
+    float4 t0 = *reinterpret_cast<const float4*>(gamma + c), t1 = *reinterpret_cast<const float4*>(gamma + c + 4);
+    g[v][0] = t0.x; g[v][1] = t0.y; g[v][2] = t0.z; g[v][3] = t0.w; g[v][4] = t1.x; g[v][5] = t1.y; g[v][6] = t1.z; g[v][7] = t1.w;
+    t0 = *reinterpret_cast<const float4*>(beta + c); t1 = *reinterpret_cast<const float4*>(beta + c + 4);
+    b[v][0] = t0.x; b[v][1] = t0.y; b[v][2] = t0.z; b[v][3] = t0.w; b[v][4] = t1.x; b[v][5] = t1.y; b[v][6] = t1.z; b[v][7] = t1.w;
+  }
+  for (long long r0 = gw * (RPW * U); r0 < rows; r0 += nw * (RPW * U)) {
+    uint4 raw[U][V];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long row = r0 + u * RPW + sub;
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+        raw[u][v] = row < rows ? *reinterpret_cast<const uint4*>(x + row * C + (v * LPR + l) * 8) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long row = r0 + u * RPW + sub;
+      float f[V][8];
+      float s = 0.f;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[u][v]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          f[v][2 * i] = __low2float(h[i]);
+          f[v][2 * i + 1] = __high2float(h[i]);
+          s += f[v][2 * i] + f[v][2 * i + 1];
+        }
+      }
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s * (1.0f / C);
+      float q = 0.f;
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float d = f[v][i] - mean;
+          q = fmaf(d, d, q);
+        }
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = rsqrtf(q * (1.0f / C) + 1e-6f);
+      if (row < rows) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          uint4 o4;
+          __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o4);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float a0 = (f[v][2 * i] - mean) * rstd * g[v][2 * i] + b[v][2 * i];
+            float a1 = (f[v][2 * i + 1] - mean) * rstd * g[v][2 * i + 1] + b[v][2 * i + 1];
+            if (SILU) { a0 = silu_f(a0); a1 = silu_f(a1); }
+            ho[i] = __floats2bfloat162_rn(a0, a1);
+          }
+          *reinterpret_cast<uint4*>(y + row * C + (v * LPR + l) * 8) = o4;
+        }
+      }
+    }
   }
 }
 
@@ -368,14 +454,34 @@ __global__ void pack_w_kn_kernel(const float* __restrict__ w, float* __restrict_
     out[i] = w[((long long)co * Ci + ci) * taps + tap];
   }
 }
-__global__ void pack_w_nk_bf16_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Co, int Ci, int taps,
+struct CollapseMap { int mt[3], mh[3], mw[3]; };
+__global__ void pack_w_collapsed_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Co, int Co_pad, int Ci,
+                                        int kt, int kh, int kw, CollapseMap cm, int kt2, int kh2, int kw2) {
+  const int K2 = kt2 * kh2 * kw2 * Ci;
+  const long long total = (long long)Co_pad * K2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K2);
+    const int co = (int)(i / K2);
+    const int ci = k % Ci, tap2 = k / Ci;
+    const int c2 = tap2 % kw2, b2 = (tap2 / kw2) % kh2, a2 = tap2 / (kw2 * kh2);
+    float v = 0.f;
+    if (co < Co)
+      for (int a = 0; a < kt; ++a)
+        for (int b = 0; b < kh; ++b)
+          for (int c = 0; c < kw; ++c)
+            if (cm.mt[a] == a2 && cm.mh[b] == b2 && cm.mw[c] == c2)
+              v += w[((long long)co * Ci + ci) * (kt * kh * kw) + (a * kh + b) * kw + c];
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+__global__ void pack_w_nk_bf16_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Co, int Co_pad, int Ci, int taps,
                                       int Kpad) {
-  const long long total = (long long)Co * Kpad;
+  const long long total = (long long)Co_pad * Kpad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(i % Kpad);
     const int co = (int)(i / Kpad);
     float v = 0.f;
-    if (k < Ci * taps) {
+    if (co < Co && k < Ci * taps) {
       const int tap = k / Ci, ci = k % Ci;
       v = w[((long long)co * Ci + ci) * taps + tap];
     }
@@ -500,11 +606,21 @@ cudaError_t launch_layernorm(DType t, const void* x, const float* gamma, const f
     else if (C == 256) VT_LN_VEC(float, 2);
     else if (C == 512) VT_LN_VEC(float, 4);
     else VT_LN_GEN(float);
+  } else if (C == 128 || C == 256 || C == 512) {
+    const long long per_block = (C == 128) ? 8 * 2 * 2 : 8 * 2;
+    long long gb = (rows + per_block - 1) / per_block;
+    if (gb > 148 * 8) gb = 148 * 8;
+#define VT_LN_BF(CC)                                                                                                  \
+  do {                                                                                                                \
+    if (silu) layernorm_bf16_kernel<CC, true><<<(unsigned)gb, 256, 0, s>>>((const bf16*)x, gamma, beta, (bf16*)y, rows); \
+    else layernorm_bf16_kernel<CC, false><<<(unsigned)gb, 256, 0, s>>>((const bf16*)x, gamma, beta, (bf16*)y, rows);  \
+  } while (0)
+    if (C == 128) VT_LN_BF(128);
+    else if (C == 256) VT_LN_BF(256);
+    else VT_LN_BF(512);
+#undef VT_LN_BF
   } else {
-    if (C == 128) VT_LN_VEC(bf16, 1);
-    else if (C == 256) VT_LN_VEC(bf16, 2);
-    else if (C == 512) VT_LN_VEC(bf16, 4);
-    else VT_LN_GEN(bf16);
+    VT_LN_GEN(bf16);
   }
 #undef VT_LN_VEC
 #undef VT_LN_GEN
@@ -585,8 +701,16 @@ cudaError_t launch_pack_w_kn(const float* w, float* out, int Co, int Ci, int tap
   count_launch();
   return cudaGetLastError();
 }
-cudaError_t launch_pack_w_nk_bf16(const float* w, bf16* out, int Co, int Ci, int taps, int Kpad, cudaStream_t s) {
-  pack_w_nk_bf16_kernel<<<grid_for((long long)Co * Kpad), 256, 0, s>>>(w, out, Co, Ci, taps, Kpad);
+cudaError_t launch_pack_w_collapsed(const float* w, bf16* out, int Co, int Co_pad, int Ci, int kt, int kh, int kw,
+                                    const int* mt, const int* mh, const int* mw, int kt2, int kh2, int kw2, cudaStream_t s) {
+  CollapseMap cm;
+  for (int i = 0; i < 3; ++i) { cm.mt[i] = i < kt ? mt[i] : -1; cm.mh[i] = i < kh ? mh[i] : -1; cm.mw[i] = i < kw ? mw[i] : -1; }
+  pack_w_collapsed_kernel<<<grid_for((long long)Co_pad * kt2 * kh2 * kw2 * Ci), 256, 0, s>>>(w, out, Co, Co_pad, Ci, kt, kh, kw, cm, kt2, kh2, kw2);
+  count_launch();
+  return cudaGetLastError();
+}
+cudaError_t launch_pack_w_nk_bf16(const float* w, bf16* out, int Co, int Co_pad, int Ci, int taps, int Kpad, cudaStream_t s) {
+  pack_w_nk_bf16_kernel<<<grid_for((long long)Co_pad * Kpad), 256, 0, s>>>(w, out, Co, Co_pad, Ci, taps, Kpad);
   count_launch();
   return cudaGetLastError();
 }

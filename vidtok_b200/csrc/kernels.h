@@ -11,6 +11,7 @@ enum DType { DT_F32 = 0, DT_BF16 = 1 };
 inline size_t dtype_size(DType t) { return t == DT_F32 ? 4 : 2; }
 
 void prof_start();
+void prof_set_detail(bool on);
 int prof_stop(char* buf, int cap);
 
 // conv_simt.cu
@@ -37,7 +38,11 @@ cudaError_t launch_fsq_indices_to_codes(const int* indices, int d, const int* le
 // weight repacking: w [Co][Ci][taps] (reference OIDHW flattened) -> [K = tap*Ci + ci][Co] fp32
 cudaError_t launch_pack_w_kn(const float* w, float* out, int Co, int Ci, int taps, cudaStream_t s);
 // -> [Co][K = tap*Ci + ci] bf16 (K-major rows for the tcgen05 B operand)
-cudaError_t launch_pack_w_nk_bf16(const float* w, bf16* out, int Co, int Ci, int taps, int Kpad, cudaStream_t s);
+cudaError_t launch_pack_w_nk_bf16(const float* w, bf16* out, int Co, int Co_pad, int Ci, int taps, int Kpad, cudaStream_t s);
+// phase-collapsed weights of "nearest-2x upsample then conv": original taps (a,b,c) of a kt x kh x kw kernel are
+// summed into tap (mt[a], mh[b], mw[c]) of a kt2 x kh2 x kw2 kernel; output [Co_pad][kt2*kh2*kw2*Ci] bf16
+cudaError_t launch_pack_w_collapsed(const float* w, bf16* out, int Co, int Co_pad, int Ci, int kt, int kh, int kw,
+                                    const int* mt, const int* mh, const int* mw, int kt2, int kh2, int kw2, cudaStream_t s);
 // trilinear (align_corners=False) 2x upsampling along T of channels-last x [B,T,HWC] -> [B,2T,HWC]
 cudaError_t launch_time_interp2x(DType t, const void* x, void* y, int B, int T, long long hwc, cudaStream_t s);
 cudaError_t launch_upsample_nearest(DType t, const void* x, void* y, int B, int T, int H, int W, int C, int ut, int uh,
@@ -50,8 +55,8 @@ cudaError_t launch_copy_frames(DType t, const void* src, void* dst, int B, long 
                                long long n_per_batch, cudaStream_t s);
 
 // conv_tc.cu (tcgen05 / TMA implicit GEMM)
-bool conv_tc_supported(const ConvP& p);
-cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int Kpad, bf16* out, cudaStream_t s);
+bool conv_tc_supported(const ConvP& p, DType tout);
+cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int Kpad, void* out, DType tout, cudaStream_t s);
 const char* conv_tc_last_error();
 
 }  // namespace vt

@@ -291,6 +291,8 @@ struct ConvOpt {
   long long in_bs = -1;           // input batch stride override (views into a larger tensor)
   const char* cache_key = nullptr;  // v1.1 causal cache identity (checkpoint prefix of the conv)
   bool force_simt = false;
+  void* out_view = nullptr;       // write into an existing channels-last tensor through these element strides
+  long long ov_sB = 0, ov_sT = 0, ov_sH = 0, ov_sW = 0;
 };
 
 struct Exec {
@@ -415,6 +417,9 @@ struct Exec {
     if (o.ext_out) {
       out.p = o.ext_out;
       p.osC = (long long)p.To * p.Ho * p.Wo; p.osB = p.osC * p.Co; p.osT = (long long)p.Ho * p.Wo; p.osH = p.Wo; p.osW = 1;
+    } else if (o.out_view) {
+      out.p = o.out_view;
+      p.osC = 1; p.osW = o.ov_sW; p.osH = o.ov_sH; p.osT = o.ov_sT; p.osB = o.ov_sB;
     } else {
       out.p = alloc((size_t)out.elems() * dtype_size(ta));
       out.owned = true;
@@ -464,9 +469,12 @@ struct Exec {
     if (!dry) {
       const DType tin = o.ext_in ? DT_F32 : ta;
       const DType tout = o.ext_out ? DT_F32 : ta;
-      const bool tc = (prec == VT_PREC_BF16) && !o.force_simt && !o.ext_in && !o.ext_out && w.w_nk && conv_tc_supported(p);
+      const bool tc = (prec == VT_PREC_BF16) && !o.force_simt && !o.ext_in && w.w_nk && conv_tc_supported(p, tout);
       if (tc) {
-        if (!cuda(launch_conv_tc(p, (const bf16*)in.p, w.w_nk, w.Kpad, (bf16*)out.p, s), conv_tc_last_error())) return out;
+        if (!cuda(launch_conv_tc(p, (const bf16*)in.p, w.w_nk, w.Kpad, out.p, tout, s), conv_tc_last_error())) return out;
+      } else if (!w.w_kn) {
+        rc = fail(VT_ERR_INVALID, "phase-collapsed conv rejected by the tcgen05 path: %s", conv_tc_last_error());
+        return out;
       } else {
         if (!cuda(launch_conv_simt(p, tin, tout, ta, o.ext_in ? (const void*)o.ext_in : in.p, w.w_kn, out.p, s), "conv_simt")) return out;
       }
@@ -622,6 +630,20 @@ struct Exec {
       if (fold_upsample()) {
         o.ut = 2; o.res_mode = 2; o.res = &x;
         Act out = conv(lv.tconv, x, o);
+        free_act(x);
+        return out;
+      }
+      if (lv.has_tup_phase && prec == VT_PREC_BF16) {
+        // even / odd output frames: 2x3x3 convs on the un-upsampled input, mixed with x[t/2] in the epilogue
+        Act out = new_act(x.B, 2 * x.T, x.H, x.W, lv.tconv.Co);
+        const long long fr = (long long)x.H * x.W * lv.tconv.Co;
+        for (int pt = 0; pt < 2 && ok(); ++pt) {
+          ConvOpt op;
+          op.ra = lv.alpha; op.rb = 1.f - lv.alpha; op.res_mode = 1; op.res = &x;
+          op.out_view = dry ? out.p : (void*)((char*)out.p + (size_t)(pt * fr) * dtype_size(ta));
+          op.ov_sW = lv.tconv.Co; op.ov_sH = (long long)x.W * lv.tconv.Co; op.ov_sT = 2 * fr; op.ov_sB = 2 * fr * x.T;
+          conv(lv.tup_ph[pt], x, op);
+        }
         free_act(x);
         return out;
       }
@@ -793,6 +815,19 @@ static void run_decoder(Exec& ex, const float* z_ext, int B, int Tz, int Hz, int
         ConvOpt o; o.uh = 2; o.uw = 2;
         y = ex.conv(lv.resample, h, o);
         ex.free_act(h);
+      } else if (lv.has_up_phase && ex.prec == VT_PREC_BF16) {
+        // four parity classes of the 2x-upsampled output, each a 1x2x2 conv on the low-resolution input
+        y = ex.new_act(h.B, h.T, 2 * h.H, 2 * h.W, lv.resample.Co);
+        const long long C = lv.resample.Co, Wo2 = 2 * h.W, Ho2 = 2 * h.H;
+        for (int py = 0; py < 2 && ex.ok(); ++py)
+          for (int px = 0; px < 2 && ex.ok(); ++px) {
+            ConvOpt o;
+            o.ph0 = py == 0 ? 1 : 0; o.ph1 = 1 - o.ph0; o.pw0 = px == 0 ? 1 : 0; o.pw1 = 1 - o.pw0;
+            o.out_view = ex.dry ? y.p : (void*)((char*)y.p + (size_t)((py * Wo2 + px) * C) * dtype_size(ex.ta));
+            o.ov_sW = 2 * C; o.ov_sH = 2 * Wo2 * C; o.ov_sT = Ho2 * Wo2 * C; o.ov_sB = o.ov_sT * h.T;
+            ex.conv(lv.up_ph[py * 2 + px], h, o);
+          }
+        ex.free_act(h);
       } else {
         Act hu = ex.upsample_mat(h, 1, 2, 2);
         ex.free_act(h);
@@ -870,7 +905,8 @@ int64_t vt_launch_count(int32_t reset) {
   return v;
 }
 
-void vt_profile_start(void) { prof_start(); }
+void vt_profile_start(void) { prof_set_detail(false); prof_start(); }
+void vt_profile_start_detailed(void) { prof_set_detail(true); prof_start(); }
 int32_t vt_profile_stop(char* json, int32_t cap) { return prof_stop(json, cap); }
 
 int32_t vt_model_create(const vt_model_desc* desc, int32_t device, vt_model** out) {
@@ -960,10 +996,18 @@ int32_t vt_model_finalize(vt_model* m, void* stream) {
     const int K = c->taps() * c->Ci;
     kn += align_up((size_t)K * c->Co, 64);
     c->Kpad = 0;
-    if (c->Ci % 64 == 0 && c->Co % 16 == 0) {
+    c->Co_pad = (c->Co + 31) / 32 * 32;
+    if (c->Ci % 64 == 0) {
       c->Kpad = K;
-      nk += align_up((size_t)c->Co * K, 512);
+      nk += align_up((size_t)c->Co_pad * K, 512);
     }
+  }
+  // phase-collapsed weights for "nearest 2x upsample then conv" (decoder Upsample / v1.0 TimeUpsampleResCausal2x)
+  for (auto& lv : m->dec.levels) {
+    lv.has_up_phase = lv.has_resample && lv.resample.Ci % 64 == 0 && lv.resample.Co % 32 == 0;
+    lv.has_tup_phase = lv.has_tres && m->desc.version == 0 && lv.tconv.Ci % 64 == 0 && lv.tconv.Co % 32 == 0;
+    if (lv.has_up_phase) nk += 4 * align_up((size_t)lv.resample.Co * 4 * lv.resample.Ci, 512);
+    if (lv.has_tup_phase) nk += 2 * align_up((size_t)lv.tconv.Co * 18 * lv.tconv.Ci, 512);
   }
   if (!m->packed_kn) VT_CUDA(cudaMalloc(&m->packed_kn, kn * sizeof(float)));
   if (!m->packed_nk && nk) VT_CUDA(cudaMalloc(&m->packed_nk, nk * sizeof(bf16)));
@@ -977,8 +1021,38 @@ int32_t vt_model_finalize(vt_model* m, void* stream) {
     VT_CUDA(launch_pack_w_kn(w, c->w_kn, c->Co, c->Ci, c->taps(), s));
     if (c->Kpad) {
       c->w_nk = m->packed_nk + onk;
-      onk += align_up((size_t)c->Co * K, 512);
-      VT_CUDA(launch_pack_w_nk_bf16(w, c->w_nk, c->Co, c->Ci, c->taps(), c->Kpad, s));
+      onk += align_up((size_t)c->Co_pad * K, 512);
+      VT_CUDA(launch_pack_w_nk_bf16(w, c->w_nk, c->Co, c->Co_pad, c->Ci, c->taps(), c->Kpad, s));
+    }
+  }
+  for (auto& lv : m->dec.levels) {
+    const int id3[3] = {0, 1, 2}, id1[3] = {0, 0, 0};
+    const int lo[3] = {0, 1, 1}, hi[3] = {0, 0, 1};   // parity 0: taps {0 | 1,2}; parity 1: taps {0,1 | 2}
+    if (lv.has_up_phase) {
+      const ConvW& c = lv.resample;
+      const float* w = m->pool + m->params[c.pw].offset;
+      for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+          ConvW& ph = lv.up_ph[py * 2 + px];
+          ph = ConvW();
+          ph.Co = c.Co; ph.Ci = c.Ci; ph.kt = 1; ph.kh = 2; ph.kw = 2; ph.Co_pad = c.Co; ph.Kpad = 4 * c.Ci;
+          ph.bias = c.bias; ph.w_nk = m->packed_nk + onk;
+          onk += align_up((size_t)c.Co * 4 * c.Ci, 512);
+          VT_CUDA(launch_pack_w_collapsed(w, ph.w_nk, c.Co, c.Co, c.Ci, 1, 3, 3, id1, py == 0 ? lo : hi, px == 0 ? lo : hi, 1, 2, 2, s));
+        }
+    }
+    if (lv.has_tup_phase) {
+      const ConvW& c = lv.tconv;
+      const float* w = m->pool + m->params[c.pw].offset;
+      for (int pt = 0; pt < 2; ++pt) {
+        ConvW& ph = lv.tup_ph[pt];
+        ph = ConvW();
+        ph.Co = c.Co; ph.Ci = c.Ci; ph.kt = 2; ph.kh = 3; ph.kw = 3; ph.Co_pad = c.Co; ph.Kpad = 18 * c.Ci;
+        ph.bias = c.bias; ph.w_nk = m->packed_nk + onk;
+        onk += align_up((size_t)c.Co * 18 * c.Ci, 512);
+        // even frames t'=2i read x'[2i-2..2i] = x[i-1],x[i-1],x[i]; odd frames read x[i-1],x[i],x[i]
+        VT_CUDA(launch_pack_w_collapsed(w, ph.w_nk, c.Co, c.Co, c.Ci, 3, 3, 3, pt == 0 ? hi : lo, id3, id3, 2, 3, 3, s));
+      }
     }
   }
   for (NormW* n : m->norms) {
@@ -1200,11 +1274,12 @@ int32_t vt_op_conv(int32_t precision, int32_t force_simt, const vt_conv_desc* d,
   VT_CUDA(cudaMalloc(&wkn, (size_t)K * d->Co * sizeof(float)));
   VT_CUDA(launch_pack_w_kn(w, wkn, d->Co, d->Ci, taps, s));
   cudaError_t e;
-  const bool tc = precision == VT_PREC_BF16 && !force_simt && d->Ci % 64 == 0 && d->Co % 16 == 0 && conv_tc_supported(p);
+  const bool tc = precision == VT_PREC_BF16 && !force_simt && d->Ci % 64 == 0 && conv_tc_supported(p, DT_BF16);
   if (tc) {
-    VT_CUDA(cudaMalloc(&wnk, (size_t)K * d->Co * sizeof(bf16)));
-    VT_CUDA(launch_pack_w_nk_bf16(w, wnk, d->Co, d->Ci, taps, K, s));
-    e = launch_conv_tc(p, (const bf16*)x, wnk, K, (bf16*)out, s);
+    const int Co_pad = (d->Co + 31) / 32 * 32;
+    VT_CUDA(cudaMalloc(&wnk, (size_t)K * Co_pad * sizeof(bf16)));
+    VT_CUDA(launch_pack_w_nk_bf16(w, wnk, d->Co, Co_pad, d->Ci, taps, K, s));
+    e = launch_conv_tc(p, (const bf16*)x, wnk, K, out, DT_BF16, s);
   } else {
     if (precision == VT_PREC_BF16 && !force_simt) {
       cudaFree(wkn);

@@ -24,8 +24,9 @@ struct ConvW {
   int Co = 0, Ci = 0, kt = 1, kh = 1, kw = 1;
   int pw = -1, pb = -1;      // param indices (weight, bias)
   float* w_kn = nullptr;     // [K][Co] fp32
-  bf16* w_nk = nullptr;      // [Co][Kpad] bf16 (tcgen05 B operand), may be null
+  bf16* w_nk = nullptr;      // [Co_pad][Kpad] bf16 (tcgen05 B operand), may be null
   int Kpad = 0;
+  int Co_pad = 0;            // Cout rounded up to 32 (zero rows)
   const float* bias = nullptr;
   int taps() const { return kt * kh * kw; }
 };
@@ -56,6 +57,11 @@ struct LevelW {
   int p_mix = -1;
   float alpha = 0.f;            // sigmoid(mix_factor)
   int num_temp_upsample = 1;    // v1.1 decoder (model_3dcausal_v1_1.py:856,880-882)
+  // phase-collapsed weights (BF16 mode): nearest-2x upsample followed by a conv == one small conv per output parity
+  bool has_up_phase = false;    // spatial Upsample: 4 convs with 1x2x2 taps
+  ConvW up_ph[4];
+  bool has_tup_phase = false;   // v1.0 TimeUpsampleResCausal2x: 2 convs with 2x3x3 taps
+  ConvW tup_ph[2];
   std::string tkey;
 };
 struct StackW {

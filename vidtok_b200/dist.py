@@ -51,7 +51,7 @@ def psnr_partial(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     y01 = (y.clamp(-1, 1) + 1) / 2
     mse = ((x01 - y01) ** 2).mean(dim=(1, 3, 4))  # [B,T]
     ps = -10.0 * torch.log10(mse + 1e-8)
-    return torch.stack([ps.sum().double(), torch.tensor(float(ps.numel()), dtype=torch.float64, device=ps.device)])
+    return torch.stack([ps.double().sum(), torch.tensor(float(ps.numel()), dtype=torch.float64, device=ps.device)])
 
 
 def allreduce_sum(t: torch.Tensor) -> torch.Tensor:
