@@ -31,7 +31,8 @@ thread_local std::string g_tc_err;
 
 struct TcParams {
   int B, To, Ho, Wo, Co, Ti;
-  int BW, BH, BT;
+  int BW, BH, BT;            // TMA box = BT x BH x BW positions = MT * 128 rows
+  int MT;                    // M tiles (UMMA M=128 each) per CTA tile: 2 when BN <= 128 (shares one B tile)
   int tilesW, tilesH, tilesT;
   int num_n_tiles, BN;
   long long num_tiles;
@@ -60,7 +61,8 @@ struct TcMaps {
   CUtensorMap b;             // weights
 };
 
-constexpr int kThreads = 256;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 128 + kEpiWarps * 32;
 constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
 
 // ---------------------------------------------------------------------------------------------------
@@ -198,13 +200,16 @@ __device__ __forceinline__ bool tap_time(const TcParams& p, int t0, int a, int& 
   return true;
 }
 
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle, 4..11 = epilogue (two warps per TMEM
+// lane quarter, alternating 32-column chunks).
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t a_bytes = (uint32_t)p.MT * kABytes;
   const uint32_t b_bytes = (uint32_t)p.BN * 128u;
-  const uint32_t stage_bytes = kABytes + b_bytes;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
   const uint32_t bar_base = smem_base + p.stages * stage_bytes;
   // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2]; then tmem ptr; then bias[2][256]
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -230,7 +235,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);
+      mbar_init(tempty_bar(s), kEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -277,7 +282,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             mbar_expect_tx(full_bar(stage), stage_bytes);
             const uint32_t sa = smem_base + stage * stage_bytes;
             tma_load_5d(sa, mapA, full_bar(stage), kc * 64, cw, ch, tv, tc.b);
-            tma_load_2d(sa + kABytes, &maps.b, full_bar(stage), tap * p.Ci + kc * 64, tc.n0);
+            tma_load_2d(sa + a_bytes, &maps.b, full_bar(stage), tap * p.Ci + kc * 64, tc.n0);
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -295,7 +300,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
         mbar_wait(tempty_bar(as), aphase ^ 1u);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * (uint32_t)p.BN;
+        const uint32_t tmem_d = tmem_base + as * (uint32_t)(p.MT * p.BN);
         uint32_t accum = 0;
         for (int tap = 0; tap < ntaps; ++tap) {
           const int a = tap / (p.kw * p.kh);
@@ -306,12 +311,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
             const uint32_t sa = smem_base + stage * stage_bytes;
-            const uint64_t adesc = make_sdesc(sa), bdesc = make_sdesc(sa + kABytes);
+            const uint64_t bdesc = make_sdesc(sa + a_bytes);
+            for (int mt = 0; mt < p.MT; ++mt) {
+              const uint64_t adesc = make_sdesc(sa + mt * kABytes);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              umma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accum);
-              accum = 1;
+              for (int k = 0; k < 4; ++k)
+                umma_f16(tmem_d + (uint32_t)(mt * p.BN), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accum | (uint32_t)k);
             }
+            accum = 1;
             umma_commit(empty_bar(stage));
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
@@ -321,84 +328,117 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int dw = row % p.BW, dh = (row / p.BW) % p.BH, dt = row / (p.BW * p.BH);
+    const int q = warp & 3;            // TMEM lane quarter this warp may read
+    const int half = (warp - 4) >> 2;  // even / odd 32-column chunks
     const int et = threadIdx.x - 128;
+    const int nchunks = p.BN / 32;
     uint32_t it = 0;
     for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const TileCoord tc = decode_tile(p, tile);
       const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
       float* bias_s = sbias + as * 256;
-      for (int i = et; i < p.BN; i += 128) bias_s[i] = (p.bias && tc.n0 + i < p.Co_real) ? p.bias[tc.n0 + i] : 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      mbar_wait(tfull_bar(as), aphase);
-      tc_fence_after();
-      const int t = tc.t0 + dt, h = tc.h0 + dh, w = tc.w0 + dw;
-      const bool valid = (t < p.To) && (h < p.Ho) && (w < p.Wo);
-      const long long ooff = (long long)tc.b * p.osB + (long long)t * p.osT + (long long)h * p.osH + (long long)w * p.osW;
-      bf16* orow = reinterpret_cast<bf16*>(p.out) + ooff + tc.n0;
-      const bf16* r0 = nullptr;
-      const bf16* r1 = nullptr;
-      const bf16* r2 = nullptr;
-      if (valid && p.res_mode == 1) {
-        r0 = p.res + (long long)tc.b * p.rsB + (long long)t * p.rsT + (long long)h * p.rsH + (long long)w * p.rsW + tc.n0;
-      } else if (valid && p.res_mode == 3) {
-        // avg-pool of residual frames 2t-1, 2t, 2t+1 (front pad: zero / frame 0 / 1-frame cache)
-        const long long sp = (long long)tc.b * p.rsB + (long long)h * p.rsH + (long long)w * p.rsW + tc.n0;
-        const int ta = 2 * t - 1, tb = 2 * t, tcn = 2 * t + 1;
-        if (ta >= 0) r0 = p.res + sp + (long long)ta * p.rsT;
-        else if (p.res_t_mode == 1) r0 = p.res + sp;
-        else if (p.res_t_mode == 2) r0 = p.res_cache + (((long long)tc.b * p.Ho + h) * p.Wo + w) * (long long)p.Co + tc.n0;
-        if (tb < p.resT) r1 = p.res + sp + (long long)tb * p.rsT;
-        if (tcn < p.resT) r2 = p.res + sp + (long long)tcn * p.rsT;
-      }
-      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)p.BN;
-      for (int j = 0; j < p.BN; j += 32) {
-        uint32_t v[32];
-        tmem_ld32(tbase + (uint32_t)j, v);
-        tmem_ld_wait();
-        if (valid) {
-          float f[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = p.rb * (__uint_as_float(v[i]) + bias_s[j + i]);
-          if (p.res_mode == 1) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float rr[8];
-              unpack8(*reinterpret_cast<const uint4*>(r0 + j + g * 8), rr);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) f[g * 8 + i] = fmaf(p.ra, rr[i], f[g * 8 + i]);
-            }
-          } else if (p.res_mode == 3) {
-            const float s3 = p.ra * (1.0f / 3.0f);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-              float rr[8];
-              if (r0) { unpack8(*reinterpret_cast<const uint4*>(r0 + j + g * 8), rr);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) acc[i] += rr[i]; }
-              if (r1) { unpack8(*reinterpret_cast<const uint4*>(r1 + j + g * 8), rr);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) acc[i] += rr[i]; }
-              if (r2) { unpack8(*reinterpret_cast<const uint4*>(r2 + j + g * 8), rr);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) acc[i] += rr[i]; }
-#pragma unroll
-              for (int i = 0; i < 8; ++i) f[g * 8 + i] = fmaf(s3, acc[i], f[g * 8 + i]);
-            }
-          }
-          if (p.out_f32) {
-            float* of = reinterpret_cast<float*>(p.out) + ooff;
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (tc.n0 + j + i < p.Co_real) of[(long long)(tc.n0 + j + i) * p.osC] = f[i];
-          } else {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(orow + j + g * 8) = pack8(f + g * 8);
-          }
+      for (int i = et; i < p.BN; i += kEpiWarps * 32) bias_s[i] = (p.bias && tc.n0 + i < p.Co_real) ? p.bias[tc.n0 + i] : 0.f;
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+      bool waited = false;
+      for (int mt = 0; mt < p.MT; ++mt) {
+        const int row = mt * 128 + q * 32 + lane;
+        const int dw = row % p.BW, dh = (row / p.BW) % p.BH, dt = row / (p.BW * p.BH);
+        const int t = tc.t0 + dt, h = tc.h0 + dh, w = tc.w0 + dw;
+        const bool valid = (t < p.To) && (h < p.Ho) && (w < p.Wo);
+        const long long ooff = (long long)tc.b * p.osB + (long long)t * p.osT + (long long)h * p.osH + (long long)w * p.osW;
+        bf16* orow = reinterpret_cast<bf16*>(p.out) + ooff + tc.n0;
+        const bf16* r0 = nullptr;
+        const bf16* r1 = nullptr;
+        const bf16* r2 = nullptr;
+        if (valid && p.res_mode == 1) {
+          r0 = p.res + (long long)tc.b * p.rsB + (long long)t * p.rsT + (long long)h * p.rsH + (long long)w * p.rsW + tc.n0;
+        } else if (valid && p.res_mode == 3) {
+          // avg-pool of residual frames 2t-1, 2t, 2t+1 (front pad: zero / frame 0 / 1-frame cache)
+          const long long sp = (long long)tc.b * p.rsB + (long long)h * p.rsH + (long long)w * p.rsW + tc.n0;
+          const int ta = 2 * t - 1, tb = 2 * t, tcn = 2 * t + 1;
+          if (ta >= 0) r0 = p.res + sp + (long long)ta * p.rsT;
+          else if (p.res_t_mode == 1) r0 = p.res + sp;
+          else if (p.res_t_mode == 2) r0 = p.res_cache + (((long long)tc.b * p.Ho + h) * p.Wo + w) * (long long)p.Co + tc.n0;
+          if (tb < p.resT) r1 = p.res + sp + (long long)tb * p.rsT;
+          if (tcn < p.resT) r2 = p.res + sp + (long long)tcn * p.rsT;
         }
+        // residual of the first chunk is fetched before the accumulator is waited for
+        uint4 rcur[4];
+        const bool pre = valid && p.res_mode == 1;
+        if (pre && half < nchunks) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) rcur[g] = *reinterpret_cast<const uint4*>(r0 + half * 32 + g * 8);
+        }
+        if (!waited) {
+          mbar_wait(tfull_bar(as), aphase);
+          tc_fence_after();
+          waited = true;
+        }
+        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * p.MT + mt) * p.BN);
+        for (int ch = half; ch < nchunks; ch += 2) {
+          const int j = ch * 32;
+          uint32_t v[32];
+          tmem_ld32(tbase + (uint32_t)j, v);
+          uint4 rnext[4];
+          if (pre && ch + 2 < nchunks) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) rnext[g] = *reinterpret_cast<const uint4*>(r0 + (j + 64) + g * 8);
+          }
+          tmem_ld_wait();
+          if (valid) {
+            float f[32];
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const float4 bv = *reinterpret_cast<const float4*>(bias_s + j + g * 4);
+              f[g * 4 + 0] = p.rb * (__uint_as_float(v[g * 4 + 0]) + bv.x);
+              f[g * 4 + 1] = p.rb * (__uint_as_float(v[g * 4 + 1]) + bv.y);
+              f[g * 4 + 2] = p.rb * (__uint_as_float(v[g * 4 + 2]) + bv.z);
+              f[g * 4 + 3] = p.rb * (__uint_as_float(v[g * 4 + 3]) + bv.w);
+            }
+            if (p.res_mode == 1) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float rr[8];
+                unpack8(rcur[g], rr);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[g * 8 + i] = fmaf(p.ra, rr[i], f[g * 8 + i]);
+              }
+            } else if (p.res_mode == 3) {
+              const float s3 = p.ra * (1.0f / 3.0f);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                float rr[8];
+                if (r0) { unpack8(*reinterpret_cast<const uint4*>(r0 + j + g * 8), rr);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) acc[i] += rr[i]; }
+                if (r1) { unpack8(*reinterpret_cast<const uint4*>(r1 + j + g * 8), rr);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) acc[i] += rr[i]; }
+                if (r2) { unpack8(*reinterpret_cast<const uint4*>(r2 + j + g * 8), rr);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) acc[i] += rr[i]; }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[g * 8 + i] = fmaf(s3, acc[i], f[g * 8 + i]);
+              }
+            }
+            if (p.out_f32) {
+              float* of = reinterpret_cast<float*>(p.out) + ooff;
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (tc.n0 + j + i < p.Co_real) of[(long long)(tc.n0 + j + i) * p.osC] = f[i];
+            } else {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(orow + j + g * 8) = pack8(f + g * 8);
+            }
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) rcur[g] = rnext[g];
+        }
+      }
+      if (!waited) {  // (MT >= 1 always waits; kept for symmetry)
+        mbar_wait(tfull_bar(as), aphase);
+        tc_fence_after();
       }
       tc_fence_before();
       __syncwarp();
@@ -434,19 +474,20 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-bool choose_tile(const ConvP& p, int& BW, int& BH, int& BT) {
+bool choose_tile(const ConvP& p, int rows, int& BW, int& BH, int& BT, long long* padded_out = nullptr) {
   const bool allow_bt = (p.st == 1) && (p.t_mode == 0);
   long long best = -1;
   auto ceil_to = [](int v, int b) { return (long long)((v + b - 1) / b) * b; };
   for (int bw = 128; bw >= 8; bw >>= 1) {
-    for (int bh = 128 / bw; bh >= 1; bh >>= 1) {
-      const int bt = 128 / (bw * bh);
+    for (int bh = rows / bw; bh >= 1; bh >>= 1) {
+      if (bh > 256) continue;
+      const int bt = rows / (bw * bh);
       if (bt > 1 && !allow_bt) continue;
       if (bt > 16) continue;
       const long long padded = ceil_to(p.Wo, bw) * ceil_to(p.Ho, bh) * ceil_to(p.To, bt);
       // prefer less padding; then square-ish spatial tiles (halo reuse in L2); then BT == 1
       const long long cost = padded * 1024 + (long long)(bw > 16 ? bw - 16 : 16 - bw) * 4 + (bt - 1);
-      if (best < 0 || cost < best) { best = cost; BW = bw; BH = bh; BT = bt; }
+      if (best < 0 || cost < best) { best = cost; BW = bw; BH = bh; BT = bt; if (padded_out) *padded_out = padded; }
     }
   }
   return best >= 0;
@@ -494,9 +535,27 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   if (!enc) { g_tc_err = "cuTensorMapEncodeTiled unavailable"; return cudaErrorNotSupported; }
   TcParams t;
   memset(&t, 0, sizeof(t));
-  if (!choose_tile(p, t.BW, t.BH, t.BT)) { g_tc_err = "no tile shape"; return cudaErrorInvalidValue; }
   const int Co_pad = (p.Co + 31) / 32 * 32;
   t.BN = choose_bn(Co_pad);
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  // two M tiles per CTA tile when the N tile is narrow: one B (weight) tile then feeds 256 output rows, which halves
+  // the weight bytes per FLOP (the N<=128 layers are operand-bandwidth bound otherwise)
+  t.MT = 1;
+  long long pad1 = 0, pad2 = 0;
+  if (!choose_tile(p, 128, t.BW, t.BH, t.BT, &pad1)) { g_tc_err = "no tile shape"; return cudaErrorInvalidValue; }
+  if (t.BN <= 128) {
+    int bw2, bh2, bt2;
+    if (choose_tile(p, 256, bw2, bh2, bt2, &pad2) && pad2 <= pad1 + pad1 / 16 &&
+        (long long)p.B * pad2 / 256 * (Co_pad / t.BN) >= 2LL * num_sms) {
+      t.MT = 2; t.BW = bw2; t.BH = bh2; t.BT = bt2;
+    }
+  }
   t.B = p.B; t.To = p.To; t.Ho = p.Ho; t.Wo = p.Wo; t.Co = p.Co; t.Ti = p.Ti;
   t.tilesW = (p.Wo + t.BW - 1) / t.BW; t.tilesH = (p.Ho + t.BH - 1) / t.BH; t.tilesT = (p.To + t.BT - 1) / t.BT;
   t.num_n_tiles = Co_pad / t.BN;
@@ -510,7 +569,7 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   t.out = out; t.osB = p.osB; t.osT = p.osT; t.osH = p.osH; t.osW = p.osW; t.osC = p.osC;
   t.out_f32 = (tout == DT_F32) ? 1 : 0;
   t.Co_real = p.Co;
-  const size_t stage_bytes = kABytes + (size_t)t.BN * 128;
+  const size_t stage_bytes = (size_t)t.MT * kABytes + (size_t)t.BN * 128;
   const size_t budget = 220 * 1024;
   const size_t fixed = 1024 /*align*/ + 8 * 2 * 8 + 64 + 2 * 256 * 4 + 256;
   int stages = (int)((budget - fixed) / stage_bytes);
@@ -518,7 +577,7 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   if (stages < 2) { g_tc_err = "not enough shared memory for 2 stages"; return cudaErrorInvalidValue; }
   t.stages = stages;
   uint32_t cols = 32;
-  while (cols < (uint32_t)(2 * t.BN)) cols <<= 1;
+  while (cols < (uint32_t)(2 * t.MT * t.BN)) cols <<= 1;
   t.tmem_cols = cols;
   const size_t smem = fixed + (size_t)stages * stage_bytes + 8 * (2 * stages + 4);
 
@@ -562,14 +621,7 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { g_tc_err = "cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r); return cudaErrorInvalidValue; }
   }
-  static int num_sms = 0;
   static bool smem_set = false;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
-  }
   if (!smem_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) { g_tc_err = "cudaFuncSetAttribute(smem)"; return e; }
@@ -578,7 +630,7 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   const unsigned grid = (unsigned)(t.num_tiles < num_sms ? t.num_tiles : num_sms);
   const double Mrows = (double)p.B * p.To * p.Ho * p.Wo;
   char det[96] = "";
-  if (prof_enabled()) snprintf(det, sizeof(det), "k%d%d%d s%d%d %d->%d @%dx%dx%d tile%dx%dx%d bn%d", p.kt, p.kh, p.kw, p.st, p.sh, p.Ci, p.Co, p.To, p.Ho, p.Wo, t.BT, t.BH, t.BW, t.BN);
+  if (prof_enabled()) snprintf(det, sizeof(det), "k%d%d%d s%d%d %d->%d @%dx%dx%d tile%dx%dx%d bn%d mt%d", p.kt, p.kh, p.kw, p.st, p.sh, p.Ci, p.Co, p.To, p.Ho, p.Wo, t.BT, t.BH, t.BW, t.BN, t.MT);
   ProfScope _ps("conv_tc", 2.0 * Mrows * p.kt * p.kh * p.kw * p.Ci * p.Co,
                 2.0 * ((double)p.B * p.Ti * p.Hi * p.Wi * p.Ci) + Mrows * p.Co * (tout == DT_F32 ? 4.0 : 2.0), s, det);
   conv_tc_kernel<<<grid, kThreads, smem, s>>>(maps, t);

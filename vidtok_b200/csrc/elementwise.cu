@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const bf16* __restr
   constexpr int LPR = (C / 8) < 32 ? (C / 8) : 32;  // lanes per row
   constexpr int V = C / (8 * LPR);                  // 16-byte vectors per lane
   constexpr int RPW = 32 / LPR;                     // rows per warp pass
-  constexpr int U = 2;                              // passes in flight
+  constexpr int U = (V == 1) ? 4 : 2;               // passes in flight (64 B per lane outstanding)
   const int lane = threadIdx.x & 31, sub = lane / LPR, l = lane % LPR;
   const long long gw = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const long long nw = (long long)gridDim.x * 8;
@@ -607,7 +607,7 @@ cudaError_t launch_layernorm(DType t, const void* x, const float* gamma, const f
     else if (C == 512) VT_LN_VEC(float, 4);
     else VT_LN_GEN(float);
   } else if (C == 128 || C == 256 || C == 512) {
-    const long long per_block = (C == 128) ? 8 * 2 * 2 : 8 * 2;
+    const long long per_block = (C == 128) ? 8 * 2 * 4 : (C == 256 ? 8 * 4 : 8 * 2);
     long long gb = (rows + per_block - 1) / per_block;
     if (gb > 148 * 8) gb = 148 * 8;
 #define VT_LN_BF(CC)                                                                                                  \

@@ -59,4 +59,8 @@ bool conv_tc_supported(const ConvP& p, DType tout);
 cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int Kpad, void* out, DType tout, cudaStream_t s);
 const char* conv_tc_last_error();
 
+// conv_stem.cu (thread-built im2col A tile + tcgen05 for the Cin=3 stem)
+bool conv_stem_supported(const ConvP& p);
+cudaError_t launch_conv_stem(const ConvP& p, const float* x, const bf16* wpk, bf16* out, cudaStream_t s);
+
 }  // namespace vt

@@ -470,8 +470,11 @@ struct Exec {
       const DType tin = o.ext_in ? DT_F32 : ta;
       const DType tout = o.ext_out ? DT_F32 : ta;
       const bool tc = (prec == VT_PREC_BF16) && !o.force_simt && !o.ext_in && w.w_nk && conv_tc_supported(p, tout);
+      const bool stem = (prec == VT_PREC_BF16) && !o.force_simt && o.ext_in && !o.ext_out && !o.out_view && w.w_stem && conv_stem_supported(p);
       if (tc) {
         if (!cuda(launch_conv_tc(p, (const bf16*)in.p, w.w_nk, w.Kpad, out.p, tout, s), conv_tc_last_error())) return out;
+      } else if (stem) {
+        if (!cuda(launch_conv_stem(p, o.ext_in, w.w_stem, (bf16*)out.p, s), "conv_stem")) return out;
       } else if (!w.w_kn) {
         rc = fail(VT_ERR_INVALID, "phase-collapsed conv rejected by the tcgen05 path: %s", conv_tc_last_error());
         return out;
@@ -934,6 +937,7 @@ void vt_model_destroy(vt_model* m) {
   if (m->pool) cudaFree(m->pool);
   if (m->packed_kn) cudaFree(m->packed_kn);
   if (m->packed_nk) cudaFree(m->packed_nk);
+  if (m->packed_stem) cudaFree(m->packed_stem);
   if (m->kl_scratch) cudaFree(m->kl_scratch);
   delete m;
 }
@@ -1053,6 +1057,14 @@ int32_t vt_model_finalize(vt_model* m, void* stream) {
         // even frames t'=2i read x'[2i-2..2i] = x[i-1],x[i-1],x[i]; odd frames read x[i-1],x[i],x[i]
         VT_CUDA(launch_pack_w_collapsed(w, ph.w_nk, c.Co, c.Co, c.Ci, 3, 3, 3, pt == 0 ? hi : lo, id3, id3, 2, 3, 3, s));
       }
+    }
+  }
+  {
+    ConvW& c = m->enc.conv_in;
+    if (c.Ci * 27 <= 128 && c.Co % 64 == 0 && c.Co <= 256 && c.kt == 3 && c.kh == 3 && c.kw == 3) {
+      if (!m->packed_stem) VT_CUDA(cudaMalloc(&m->packed_stem, (size_t)c.Co * 128 * sizeof(bf16)));
+      c.w_stem = m->packed_stem;
+      VT_CUDA(launch_pack_w_nk_bf16(m->pool + m->params[c.pw].offset, c.w_stem, c.Co, c.Co, c.Ci, 27, 128, s));
     }
   }
   for (NormW* n : m->norms) {

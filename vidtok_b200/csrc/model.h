@@ -27,6 +27,7 @@ struct ConvW {
   bf16* w_nk = nullptr;      // [Co_pad][Kpad] bf16 (tcgen05 B operand), may be null
   int Kpad = 0;
   int Co_pad = 0;            // Cout rounded up to 32 (zero rows)
+  bf16* w_stem = nullptr;    // [Co][128] bf16 (conv_stem.cu), only for the Cin<=4 stem
   const float* bias = nullptr;
   int taps() const { return kt * kh * kw; }
 };
@@ -95,6 +96,7 @@ struct vt_model {
   int64_t pool_elems = 0;
   float* packed_kn = nullptr;   // all [K][Co] fp32 repacks
   vt::bf16* packed_nk = nullptr;
+  vt::bf16* packed_stem = nullptr;
   bool finalized = false;
   vt::StackW enc, dec;
   std::vector<int> spatial_ds, tempo_ds, spatial_us, tempo_us;
