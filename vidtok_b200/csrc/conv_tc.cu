@@ -53,6 +53,7 @@ struct TcParams {
   long long osB, osT, osH, osW, osC;
   int out_f32;               // 1: fp32 output with channel stride osC (external NCDHW heads), only n < Co_real stored
   int Co_real;
+  int w_batched;             // weights differ per batch element (attention: K / V^T of each frame)
 };
 
 struct TcMaps {
@@ -107,10 +108,10 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
@@ -282,7 +283,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             mbar_expect_tx(full_bar(stage), stage_bytes);
             const uint32_t sa = smem_base + stage * stage_bytes;
             tma_load_5d(sa, mapA, full_bar(stage), kc * 64, cw, ch, tv, tc.b);
-            tma_load_2d(sa + a_bytes, &maps.b, full_bar(stage), tap * p.Ci + kc * 64, tc.n0);
+            tma_load_3d(sa + a_bytes, &maps.b, full_bar(stage), tap * p.Ci + kc * 64, tc.n0, p.w_batched ? tc.b : 0);
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -424,9 +425,15 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             }
             if (p.out_f32) {
               float* of = reinterpret_cast<float*>(p.out) + ooff;
+              if (p.osC == 1 && tc.n0 + j + 32 <= p.Co_real) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (tc.n0 + j + i < p.Co_real) of[(long long)(tc.n0 + j + i) * p.osC] = f[i];
+                for (int g = 0; g < 8; ++g)
+                  *reinterpret_cast<float4*>(of + tc.n0 + j + g * 4) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (tc.n0 + j + i < p.Co_real) of[(long long)(tc.n0 + j + i) * p.osC] = f[i];
+              }
             } else {
 #pragma unroll
               for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(orow + j + g * 8) = pack8(f + g * 8);
@@ -530,7 +537,8 @@ bool conv_tc_supported(const ConvP& p, DType tout) {
 }
 
 // w_nk: [Co_pad][Kpad] bf16 with Co_pad = roundup(Co, 32) (rows >= Co are zero).
-cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int Kpad, void* out, DType tout, cudaStream_t s) {
+cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int Kpad, void* out, DType tout, cudaStream_t s,
+                           int w_batches, long long w_batch_stride) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { g_tc_err = "cuTensorMapEncodeTiled unavailable"; return cudaErrorNotSupported; }
   TcParams t;
@@ -569,6 +577,8 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   t.out = out; t.osB = p.osB; t.osT = p.osT; t.osH = p.osH; t.osW = p.osW; t.osC = p.osC;
   t.out_f32 = (tout == DT_F32) ? 1 : 0;
   t.Co_real = p.Co;
+  t.w_batched = w_batches > 1 ? 1 : 0;
+  if (t.w_batched && w_batches != p.B) { g_tc_err = "batched weights need one weight matrix per batch element"; return cudaErrorInvalidValue; }
   const size_t stage_bytes = (size_t)t.MT * kABytes + (size_t)t.BN * 128;
   const size_t budget = 220 * 1024;
   const size_t fixed = 1024 /*align*/ + 8 * 2 * 8 + 64 + 2 * 256 * 4 + 256;
@@ -612,11 +622,12 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
     maps.c = maps.a[0];
   }
   {
-    cuuint64_t dims[2] = {(cuuint64_t)Kpad, (cuuint64_t)Co_pad};
-    cuuint64_t strides[1] = {(cuuint64_t)Kpad * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)t.BN};
-    cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(&maps.b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(w_nk), dims, strides, box, es,
+    const int nb = w_batches > 1 ? w_batches : 1;
+    cuuint64_t dims[3] = {(cuuint64_t)Kpad, (cuuint64_t)Co_pad, (cuuint64_t)nb};
+    cuuint64_t strides[2] = {(cuuint64_t)Kpad * 2, (cuuint64_t)(nb > 1 ? w_batch_stride : (long long)Kpad * Co_pad) * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)t.BN, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(&maps.b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(w_nk), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { g_tc_err = "cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r); return cudaErrorInvalidValue; }

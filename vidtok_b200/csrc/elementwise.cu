@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const bf16* __restr
 #pragma unroll
       for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
       const float rstd = rsqrtf(q * (1.0f / C) + 1e-6f);
+      const float nmr = -mean * rstd;
       if (row < rows) {
 #pragma unroll
         for (int v = 0; v < V; ++v) {
@@ -201,8 +202,9 @@ __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const bf16* __restr
           __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o4);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            float a0 = (f[v][2 * i] - mean) * rstd * g[v][2 * i] + b[v][2 * i];
-            float a1 = (f[v][2 * i + 1] - mean) * rstd * g[v][2 * i + 1] + b[v][2 * i + 1];
+            // ((x - mean) * rstd) * g + b with xhat = fma(x, rstd, -mean*rstd)
+            float a0 = fmaf(fmaf(f[v][2 * i], rstd, nmr), g[v][2 * i], b[v][2 * i]);
+            float a1 = fmaf(fmaf(f[v][2 * i + 1], rstd, nmr), g[v][2 * i + 1], b[v][2 * i + 1]);
             if (SILU) { a0 = silu_f(a0); a1 = silu_f(a1); }
             ho[i] = __floats2bfloat162_rn(a0, a1);
           }
@@ -575,6 +577,17 @@ __global__ void __launch_bounds__(256) cache_update_kernel(const T* __restrict__
   }
 }
 
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int rows, int cols) {
+  __shared__ bf16 tile[32][34];
+  const bf16* xb = x + (long long)blockIdx.z * rows * cols;
+  bf16* yb = y + (long long)blockIdx.z * rows * cols;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) tile[i][tx] = xb[(long long)(r0 + i) * cols + c0 + tx];
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) yb[(long long)(c0 + i) * rows + r0 + tx] = tile[tx][i];
+}
+
 inline int grid_for(long long total, int block = 256) {
   long long g = (total + block - 1) / block;
   const long long cap = 148LL * 16;
@@ -720,6 +733,14 @@ cudaError_t launch_time_interp2x(DType t, const void* x, void* y, int B, int T, 
   if (total == 0) return cudaSuccess;
   if (t == DT_F32) time_interp2x_kernel<float><<<grid_for(total), 256, 0, s>>>((const float*)x, (float*)y, B, T, hwc);
   else time_interp2x_kernel<bf16><<<grid_for(total), 256, 0, s>>>((const bf16*)x, (bf16*)y, B, T, hwc);
+  count_launch();
+  return cudaGetLastError();
+}
+cudaError_t launch_transpose_bf16(const bf16* x, bf16* y, int batch, int rows, int cols, cudaStream_t s) {
+  if (rows % 32 != 0 || cols % 32 != 0) return cudaErrorInvalidValue;
+  ProfScope _ps("transpose", 0.0, 4.0 * batch * rows * cols, s);
+  dim3 grid(cols / 32, rows / 32, batch);
+  transpose_bf16_kernel<<<grid, 256, 0, s>>>(x, y, rows, cols);
   count_launch();
   return cudaGetLastError();
 }

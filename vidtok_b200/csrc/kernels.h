@@ -56,7 +56,10 @@ cudaError_t launch_copy_frames(DType t, const void* src, void* dst, int B, long 
 
 // conv_tc.cu (tcgen05 / TMA implicit GEMM)
 bool conv_tc_supported(const ConvP& p, DType tout);
-cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int Kpad, void* out, DType tout, cudaStream_t s);
+cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int Kpad, void* out, DType tout, cudaStream_t s,
+                           int w_batches = 1, long long w_batch_stride = 0);
+// x [batch][rows][cols] -> y [batch][cols][rows] (bf16), rows and cols multiples of 32
+cudaError_t launch_transpose_bf16(const bf16* x, bf16* y, int batch, int rows, int cols, cudaStream_t s);
 const char* conv_tc_last_error();
 
 // conv_stem.cu (thread-built im2col A tile + tcgen05 for the Cin=3 stem)

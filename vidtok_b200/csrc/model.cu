@@ -577,8 +577,45 @@ struct Exec {
     return out;
   }
   // AttnBlockWrapper: model_3dcausal.py:114-141
+  // tcgen05 path of the attention core: S = scale * Q K^T (fp32), P = softmax(S) (bf16), O = P V.
+  // Both products are the conv_tc GEMM with per-frame "weights": K of the frame for the scores, V^T for the output.
+  bool attention_tc(const Act& q, const Act& k, const Act& v, Act& o) {
+    const int frames = q.B * q.T, tokens = q.H * q.W, C = q.C;
+    if (prec != VT_PREC_BF16 || tokens % 64 != 0 || C % 64 != 0 || tokens % 32 != 0) return false;
+    ConvP ps;
+    memset(&ps, 0, sizeof(ps));
+    ps.B = frames; ps.Ti = 1; ps.Hi = q.H; ps.Wi = q.W; ps.Ci = C;
+    ps.isC = 1; ps.isW = C; ps.isH = (long long)q.W * C; ps.isT = ps.isH * q.H; ps.isB = ps.isT;
+    ps.To = 1; ps.Ho = q.H; ps.Wo = q.W; ps.Co = tokens;
+    ps.osC = 1; ps.osW = tokens; ps.osH = (long long)q.W * tokens; ps.osT = ps.osH * q.H; ps.osB = ps.osT;
+    ps.kt = ps.kh = ps.kw = 1; ps.st = ps.sh = ps.sw = 1; ps.ut = ps.uh = ps.uw = 1;
+    ps.ra = 0.f; ps.rb = 1.0f / sqrtf((float)C);
+    ConvP pv = ps;
+    pv.Ci = tokens; pv.isW = tokens; pv.isH = (long long)q.W * tokens; pv.isT = pv.isH * q.H; pv.isB = pv.isT;
+    pv.Co = C; pv.osW = C; pv.osH = (long long)q.W * C; pv.osT = pv.osH * q.H; pv.osB = pv.osT;
+    pv.rb = 1.0f;
+    if (!dry && (!conv_tc_supported(ps, DT_F32) || !conv_tc_supported(pv, DT_BF16))) return false;
+    o = new_act(q.B, q.T, q.H, q.W, C);
+    float* S = (float*)alloc((size_t)frames * tokens * tokens * sizeof(float));
+    bf16* P = (bf16*)alloc((size_t)frames * tokens * tokens * sizeof(bf16));
+    bf16* Vt = (bf16*)alloc((size_t)frames * tokens * C * sizeof(bf16));
+    if (ok() && !dry) {
+      cuda(launch_conv_tc(ps, (const bf16*)q.p, (const bf16*)k.p, C, S, DT_F32, s, frames, (long long)tokens * C), conv_tc_last_error());
+      cuda(launch_softmax_rows(DT_BF16, S, P, (long long)frames * tokens, tokens, s), "attn softmax");
+      cuda(launch_transpose_bf16((const bf16*)v.p, Vt, frames, tokens, C, s), "attn transpose V");
+      cuda(launch_conv_tc(pv, P, Vt, tokens, o.p, DT_BF16, s, frames, (long long)tokens * C), conv_tc_last_error());
+    }
+    ar.release(Vt);
+    ar.release(P);
+    ar.release(S);
+    return true;
+  }
   Act attention_core(const Act& q, const Act& k, const Act& v) {
     const int frames = q.B * q.T, tokens = q.H * q.W, C = q.C;
+    {
+      Act o_tc;
+      if (attention_tc(q, k, v, o_tc)) return o_tc;
+    }
     Act o = new_act(q.B, q.T, q.H, q.W, C);
     float* S = (float*)alloc((size_t)frames * tokens * tokens * sizeof(float));
     void* P = alloc((size_t)frames * tokens * tokens * dtype_size(ta));
