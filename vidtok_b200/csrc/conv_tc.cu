@@ -54,6 +54,11 @@ struct TcParams {
   int out_f32;               // 1: fp32 output with channel stride osC (external NCDHW heads), only n < Co_real stored
   int Co_real;
   int w_batched;             // weights differ per batch element (attention: K / V^T of each frame)
+  // fused LayerNorm(+SiLU) over the output row (needs BN == Cout): 0 none, 1 out := act(LN(v)), 2 out := v and out2 := act(LN(v))
+  int ln_mode, ln_silu;
+  const float* ln_gamma;
+  const float* ln_beta;
+  void* out2;
 };
 
 struct TcMaps {
@@ -144,6 +149,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
@@ -221,7 +237,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   const uint32_t bias_base = tmem_slot + 16u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
-  float* sbias = reinterpret_cast<float*>(smem_gen + (bias_base - smem_base));
+  float* sbias = reinterpret_cast<float*>(smem_gen + (bias_base - smem_base));   // [2][bias 256 | gamma 256 | beta 256]
+  float* stat_s = sbias + 2 * 768;                                                // [2 groups][128 rows][sum, sumsq]
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&maps.a[0]);
@@ -329,123 +346,177 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
+    // Row ownership: MT == 2 -> warps 4-7 own the rows of M tile 0, warps 8-11 those of M tile 1 (full rows);
+    //                MT == 1 -> the two warps of a TMEM lane quarter alternate 32-column chunks of the same row.
     const int q = warp & 3;            // TMEM lane quarter this warp may read
-    const int half = (warp - 4) >> 2;  // even / odd 32-column chunks
+    const int grp = (warp - 4) >> 2;   // 0 / 1
     const int et = threadIdx.x - 128;
     const int nchunks = p.BN / 32;
+    const int mt = (p.MT == 2) ? grp : 0;
+    const int cb = (p.MT == 2) ? 0 : grp;      // first chunk
+    const int cs = (p.MT == 2) ? 1 : 2;        // chunk step
     uint32_t it = 0;
     for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const TileCoord tc = decode_tile(p, tile);
       const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
-      float* bias_s = sbias + as * 256;
-      for (int i = et; i < p.BN; i += kEpiWarps * 32) bias_s[i] = (p.bias && tc.n0 + i < p.Co_real) ? p.bias[tc.n0 + i] : 0.f;
+      float* bias_s = sbias + as * 768;
+      float* gamma_s = bias_s + 256;
+      float* beta_s = bias_s + 512;
+      for (int i = et; i < p.BN; i += kEpiWarps * 32) {
+        bias_s[i] = (p.bias && tc.n0 + i < p.Co_real) ? p.bias[tc.n0 + i] : 0.f;
+        if (p.ln_mode) { gamma_s[i] = p.ln_gamma[tc.n0 + i]; beta_s[i] = p.ln_beta[tc.n0 + i]; }
+      }
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-      bool waited = false;
-      for (int mt = 0; mt < p.MT; ++mt) {
-        const int row = mt * 128 + q * 32 + lane;
-        const int dw = row % p.BW, dh = (row / p.BW) % p.BH, dt = row / (p.BW * p.BH);
-        const int t = tc.t0 + dt, h = tc.h0 + dh, w = tc.w0 + dw;
-        const bool valid = (t < p.To) && (h < p.Ho) && (w < p.Wo);
-        const long long ooff = (long long)tc.b * p.osB + (long long)t * p.osT + (long long)h * p.osH + (long long)w * p.osW;
-        bf16* orow = reinterpret_cast<bf16*>(p.out) + ooff + tc.n0;
-        const bf16* r0 = nullptr;
-        const bf16* r1 = nullptr;
-        const bf16* r2 = nullptr;
-        if (valid && p.res_mode == 1) {
-          r0 = p.res + (long long)tc.b * p.rsB + (long long)t * p.rsT + (long long)h * p.rsH + (long long)w * p.rsW + tc.n0;
-        } else if (valid && p.res_mode == 3) {
-          // avg-pool of residual frames 2t-1, 2t, 2t+1 (front pad: zero / frame 0 / 1-frame cache)
-          const long long sp = (long long)tc.b * p.rsB + (long long)h * p.rsH + (long long)w * p.rsW + tc.n0;
-          const int ta = 2 * t - 1, tb = 2 * t, tcn = 2 * t + 1;
-          if (ta >= 0) r0 = p.res + sp + (long long)ta * p.rsT;
-          else if (p.res_t_mode == 1) r0 = p.res + sp;
-          else if (p.res_t_mode == 2) r0 = p.res_cache + (((long long)tc.b * p.Ho + h) * p.Wo + w) * (long long)p.Co + tc.n0;
-          if (tb < p.resT) r1 = p.res + sp + (long long)tb * p.rsT;
-          if (tcn < p.resT) r2 = p.res + sp + (long long)tcn * p.rsT;
-        }
-        // residual of the first chunk is fetched before the accumulator is waited for
-        uint4 rcur[4];
-        const bool pre = valid && p.res_mode == 1;
-        if (pre && half < nchunks) {
+
+      const int row = mt * 128 + q * 32 + lane;
+      const int dw = row % p.BW, dh = (row / p.BW) % p.BH, dt = row / (p.BW * p.BH);
+      const int t = tc.t0 + dt, h = tc.h0 + dh, w = tc.w0 + dw;
+      const bool valid = (t < p.To) && (h < p.Ho) && (w < p.Wo);
+      const long long ooff = (long long)tc.b * p.osB + (long long)t * p.osT + (long long)h * p.osH + (long long)w * p.osW;
+      bf16* orow = reinterpret_cast<bf16*>(p.out) + ooff + tc.n0;
+      const bf16* r0 = nullptr;
+      const bf16* r1 = nullptr;
+      const bf16* r2 = nullptr;
+      if (valid && p.res_mode == 1) {
+        r0 = p.res + (long long)tc.b * p.rsB + (long long)t * p.rsT + (long long)h * p.rsH + (long long)w * p.rsW + tc.n0;
+      } else if (valid && p.res_mode == 3) {
+        // avg-pool of residual frames 2t-1, 2t, 2t+1 (front pad: zero / frame 0 / 1-frame cache)
+        const long long sp = (long long)tc.b * p.rsB + (long long)h * p.rsH + (long long)w * p.rsW + tc.n0;
+        const int ta = 2 * t - 1, tb = 2 * t, tcn = 2 * t + 1;
+        if (ta >= 0) r0 = p.res + sp + (long long)ta * p.rsT;
+        else if (p.res_t_mode == 1) r0 = p.res + sp;
+        else if (p.res_t_mode == 2) r0 = p.res_cache + (((long long)tc.b * p.Ho + h) * p.Wo + w) * (long long)p.Co + tc.n0;
+        if (tb < p.resT) r1 = p.res + sp + (long long)tb * p.rsT;
+        if (tcn < p.resT) r2 = p.res + sp + (long long)tcn * p.rsT;
+      }
+      // residual of the first chunk is fetched before the accumulator is waited for
+      uint4 rcur[4];
+      const bool pre = valid && p.res_mode == 1;
+      if (pre && cb < nchunks) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) rcur[g] = *reinterpret_cast<const uint4*>(r0 + half * 32 + g * 8);
+        for (int g = 0; g < 4; ++g) rcur[g] = *reinterpret_cast<const uint4*>(r0 + cb * 32 + g * 8);
+      }
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * p.MT + mt) * p.BN);
+      float lsum = 0.f, lsq = 0.f;
+      // ---- pass A: v = rb*(acc+bias) + ra*R ; plain mode stores it, LayerNorm modes also keep it in TMEM + statistics
+      for (int ch = cb; ch < nchunks; ch += cs) {
+        const int j = ch * 32;
+        uint32_t v[32];
+        tmem_ld32(tbase + (uint32_t)j, v);
+        uint4 rnext[4];
+        if (pre && ch + cs < nchunks) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) rnext[g] = *reinterpret_cast<const uint4*>(r0 + (j + 32 * cs) + g * 8);
         }
-        if (!waited) {
-          mbar_wait(tfull_bar(as), aphase);
-          tc_fence_after();
-          waited = true;
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 bv = *reinterpret_cast<const float4*>(bias_s + j + g * 4);
+          f[g * 4 + 0] = p.rb * (__uint_as_float(v[g * 4 + 0]) + bv.x);
+          f[g * 4 + 1] = p.rb * (__uint_as_float(v[g * 4 + 1]) + bv.y);
+          f[g * 4 + 2] = p.rb * (__uint_as_float(v[g * 4 + 2]) + bv.z);
+          f[g * 4 + 3] = p.rb * (__uint_as_float(v[g * 4 + 3]) + bv.w);
         }
-        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * p.MT + mt) * p.BN);
-        for (int ch = half; ch < nchunks; ch += 2) {
+        if (valid && p.res_mode == 1) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float rr[8];
+            unpack8(rcur[g], rr);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[g * 8 + i] = fmaf(p.ra, rr[i], f[g * 8 + i]);
+          }
+        } else if (valid && p.res_mode == 3) {
+          const float s3 = p.ra * (1.0f / 3.0f);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            float rr[8];
+            if (r0) { unpack8(*reinterpret_cast<const uint4*>(r0 + j + g * 8), rr);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) acc[i] += rr[i]; }
+            if (r1) { unpack8(*reinterpret_cast<const uint4*>(r1 + j + g * 8), rr);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) acc[i] += rr[i]; }
+            if (r2) { unpack8(*reinterpret_cast<const uint4*>(r2 + j + g * 8), rr);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) acc[i] += rr[i]; }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[g * 8 + i] = fmaf(s3, acc[i], f[g * 8 + i]);
+          }
+        }
+        if (p.ln_mode) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            lsum += f[i];
+            lsq = fmaf(f[i], f[i], lsq);
+            v[i] = __float_as_uint(f[i]);
+          }
+          tmem_st32(tbase + (uint32_t)j, v);
+        }
+        if (valid && p.ln_mode != 1) {
+          if (p.out_f32) {
+            float* of = reinterpret_cast<float*>(p.out) + ooff;
+            if (p.osC == 1 && tc.n0 + j + 32 <= p.Co_real) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                *reinterpret_cast<float4*>(of + tc.n0 + j + g * 4) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (tc.n0 + j + i < p.Co_real) of[(long long)(tc.n0 + j + i) * p.osC] = f[i];
+            }
+          } else {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(orow + j + g * 8) = pack8(f + g * 8);
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) rcur[g] = rnext[g];
+      }
+      if (p.ln_mode) {
+        // ---- LayerNorm over the Cout values of this row (model_3dcausal.py:62-80, eps 1e-6), optional SiLU (:26-27)
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        if (p.MT == 1) {  // the other warp of this lane quarter holds the other half of the row
+          float* xs = stat_s + ((grp * 128 + q * 32 + lane) << 1);
+          xs[0] = lsum; xs[1] = lsq;
+          asm volatile("bar.sync 2, %0;" ::"n"(kEpiWarps * 32) : "memory");
+          const float* ys = stat_s + ((((grp ^ 1) * 128) + q * 32 + lane) << 1);
+          lsum += ys[0]; lsq += ys[1];
+        }
+        const float inv_n = 1.0f / (float)p.BN;
+        const float mean = lsum * inv_n;
+        float var = fmaf(-mean, mean, lsq * inv_n);
+        var = var < 0.f ? 0.f : var;
+        const float rstd = rsqrtf(var + 1e-6f);
+        const float nmr = -mean * rstd;
+        bf16* nrow = reinterpret_cast<bf16*>(p.ln_mode == 1 ? p.out : p.out2) + ooff + tc.n0;
+        for (int ch = cb; ch < nchunks; ch += cs) {
           const int j = ch * 32;
           uint32_t v[32];
           tmem_ld32(tbase + (uint32_t)j, v);
-          uint4 rnext[4];
-          if (pre && ch + 2 < nchunks) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) rnext[g] = *reinterpret_cast<const uint4*>(r0 + (j + 64) + g * 8);
-          }
           tmem_ld_wait();
           if (valid) {
             float f[32];
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
-              const float4 bv = *reinterpret_cast<const float4*>(bias_s + j + g * 4);
-              f[g * 4 + 0] = p.rb * (__uint_as_float(v[g * 4 + 0]) + bv.x);
-              f[g * 4 + 1] = p.rb * (__uint_as_float(v[g * 4 + 1]) + bv.y);
-              f[g * 4 + 2] = p.rb * (__uint_as_float(v[g * 4 + 2]) + bv.z);
-              f[g * 4 + 3] = p.rb * (__uint_as_float(v[g * 4 + 3]) + bv.w);
+              const float4 gv = *reinterpret_cast<const float4*>(gamma_s + j + g * 4);
+              const float4 bv = *reinterpret_cast<const float4*>(beta_s + j + g * 4);
+              f[g * 4 + 0] = fmaf(fmaf(__uint_as_float(v[g * 4 + 0]), rstd, nmr), gv.x, bv.x);
+              f[g * 4 + 1] = fmaf(fmaf(__uint_as_float(v[g * 4 + 1]), rstd, nmr), gv.y, bv.y);
+              f[g * 4 + 2] = fmaf(fmaf(__uint_as_float(v[g * 4 + 2]), rstd, nmr), gv.z, bv.z);
+              f[g * 4 + 3] = fmaf(fmaf(__uint_as_float(v[g * 4 + 3]), rstd, nmr), gv.w, bv.w);
             }
-            if (p.res_mode == 1) {
+            if (p.ln_silu) {
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                float rr[8];
-                unpack8(rcur[g], rr);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) f[g * 8 + i] = fmaf(p.ra, rr[i], f[g * 8 + i]);
-              }
-            } else if (p.res_mode == 3) {
-              const float s3 = p.ra * (1.0f / 3.0f);
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                float rr[8];
-                if (r0) { unpack8(*reinterpret_cast<const uint4*>(r0 + j + g * 8), rr);
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) acc[i] += rr[i]; }
-                if (r1) { unpack8(*reinterpret_cast<const uint4*>(r1 + j + g * 8), rr);
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) acc[i] += rr[i]; }
-                if (r2) { unpack8(*reinterpret_cast<const uint4*>(r2 + j + g * 8), rr);
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) acc[i] += rr[i]; }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) f[g * 8 + i] = fmaf(s3, acc[i], f[g * 8 + i]);
-              }
+              for (int i = 0; i < 32; ++i) f[i] = silu_f(f[i]);
             }
-            if (p.out_f32) {
-              float* of = reinterpret_cast<float*>(p.out) + ooff;
-              if (p.osC == 1 && tc.n0 + j + 32 <= p.Co_real) {
 #pragma unroll
-                for (int g = 0; g < 8; ++g)
-                  *reinterpret_cast<float4*>(of + tc.n0 + j + g * 4) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (tc.n0 + j + i < p.Co_real) of[(long long)(tc.n0 + j + i) * p.osC] = f[i];
-              }
-            } else {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(orow + j + g * 8) = pack8(f + g * 8);
-            }
+            for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(nrow + j + g * 8) = pack8(f + g * 8);
           }
-#pragma unroll
-          for (int g = 0; g < 4; ++g) rcur[g] = rnext[g];
         }
-      }
-      if (!waited) {  // (MT >= 1 always waits; kept for symmetry)
-        mbar_wait(tfull_bar(as), aphase);
-        tc_fence_after();
       }
       tc_fence_before();
       __syncwarp();
@@ -512,7 +583,9 @@ int choose_bn(int Co) {
 
 const char* conv_tc_last_error() { return g_tc_err.c_str(); }
 
-bool conv_tc_supported(const ConvP& p, DType tout) {
+bool conv_tc_can_fuse_ln(const ConvP& p) { return p.Co % 32 == 0 && p.Co <= 256 && choose_bn(p.Co) == p.Co; }
+
+bool conv_tc_supported(const ConvP& p, DType tout, bool planning) {
   g_tc_err.clear();
   auto no = [&](const char* why) { g_tc_err = why; return false; };
   if (p.Ci % 64 != 0) return no("Cin % 64 != 0");
@@ -530,15 +603,16 @@ bool conv_tc_supported(const ConvP& p, DType tout) {
   if (p.ut != 1 || p.uh != 1 || p.uw != 1 || p.t_rep != 0) return no("folded upsampling / replicate prefix");
   if (p.res_mode != 0 && p.res_mode != 1 && p.res_mode != 3) return no("residual mode");
   if (p.res_mode != 0 && tout != DT_BF16) return no("residual with fp32 output");
-  if (p.t_mode == 2 && (!p.cache || p.cacheT <= 0)) return no("cache mode without cache");
+  if (p.t_mode == 2 && p.sh != 1) return no("cache mode with spatial stride");
+  if (!planning && p.t_mode == 2 && (!p.cache || p.cacheT <= 0)) return no("cache mode without cache");
   if (p.Wi > 65535 || p.Hi > 65535) return no("extent");
-  if (!get_encode()) return no("cuTensorMapEncodeTiled unavailable");
+  if (!planning && !get_encode()) return no("cuTensorMapEncodeTiled unavailable");
   return true;
 }
 
 // w_nk: [Co_pad][Kpad] bf16 with Co_pad = roundup(Co, 32) (rows >= Co are zero).
 cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int Kpad, void* out, DType tout, cudaStream_t s,
-                           int w_batches, long long w_batch_stride) {
+                           int w_batches, long long w_batch_stride, const TcLnFusion* ln) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { g_tc_err = "cuTensorMapEncodeTiled unavailable"; return cudaErrorNotSupported; }
   TcParams t;
@@ -577,11 +651,15 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   t.out = out; t.osB = p.osB; t.osT = p.osT; t.osH = p.osH; t.osW = p.osW; t.osC = p.osC;
   t.out_f32 = (tout == DT_F32) ? 1 : 0;
   t.Co_real = p.Co;
+  if (ln && ln->mode) {
+    if (t.BN != p.Co || tout != DT_BF16) { g_tc_err = "fused LayerNorm needs one N tile covering Cout and bf16 output"; return cudaErrorInvalidValue; }
+    t.ln_mode = ln->mode; t.ln_silu = ln->silu ? 1 : 0; t.ln_gamma = ln->gamma; t.ln_beta = ln->beta; t.out2 = ln->out2;
+  }
   t.w_batched = w_batches > 1 ? 1 : 0;
   if (t.w_batched && w_batches != p.B) { g_tc_err = "batched weights need one weight matrix per batch element"; return cudaErrorInvalidValue; }
   const size_t stage_bytes = (size_t)t.MT * kABytes + (size_t)t.BN * 128;
   const size_t budget = 220 * 1024;
-  const size_t fixed = 1024 /*align*/ + 8 * 2 * 8 + 64 + 2 * 256 * 4 + 256;
+  const size_t fixed = 1024 /*align*/ + 8 * 2 * 8 + 64 + 2 * 768 * 4 + 2 * 128 * 2 * 4 + 256;
   int stages = (int)((budget - fixed) / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) { g_tc_err = "not enough shared memory for 2 stages"; return cudaErrorInvalidValue; }

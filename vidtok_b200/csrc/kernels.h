@@ -55,9 +55,20 @@ cudaError_t launch_copy_frames(DType t, const void* src, void* dst, int B, long 
                                long long n_per_batch, cudaStream_t s);
 
 // conv_tc.cu (tcgen05 / TMA implicit GEMM)
-bool conv_tc_supported(const ConvP& p, DType tout);
+// LayerNorm(+SiLU) of the output row fused into the conv epilogue (the row is complete in TMEM when Cout <= 256):
+// mode 1: out := act(LN(v));  mode 2: out := v, out2 := act(LN(v))   (out2 uses the strides of out)
+struct TcLnFusion {
+  int mode = 0;
+  bool silu = true;
+  const float* gamma = nullptr;
+  const float* beta = nullptr;
+  void* out2 = nullptr;
+};
+bool conv_tc_can_fuse_ln(const ConvP& p);
+// planning = true: geometry-only answer (workspace dry runs: no device pointers, possibly no driver)
+bool conv_tc_supported(const ConvP& p, DType tout, bool planning = false);
 cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int Kpad, void* out, DType tout, cudaStream_t s,
-                           int w_batches = 1, long long w_batch_stride = 0);
+                           int w_batches = 1, long long w_batch_stride = 0, const TcLnFusion* ln = nullptr);
 // x [batch][rows][cols] -> y [batch][cols][rows] (bf16), rows and cols multiples of 32
 cudaError_t launch_transpose_bf16(const bf16* x, bf16* y, int batch, int rows, int cols, cudaStream_t s);
 const char* conv_tc_last_error();

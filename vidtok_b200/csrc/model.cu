@@ -293,6 +293,14 @@ struct ConvOpt {
   bool force_simt = false;
   void* out_view = nullptr;       // write into an existing channels-last tensor through these element strides
   long long ov_sB = 0, ov_sT = 0, ov_sH = 0, ov_sW = 0;
+  // LayerNorm(+SiLU) fusion requests (BF16 tcgen05 path only; silently not honoured otherwise -> check fused1/fused2)
+  const NormW* ln1 = nullptr;     // replace the output by act(LN(out))           (conv1 -> norm2 of a ResBlock)
+  bool ln1_silu = true;
+  const NormW* ln2 = nullptr;     // additionally produce act(LN(out))            (stream producer -> next block's norm1)
+  bool ln2_silu = true;
+  void* ln2_view = nullptr;       // with out_view: where the normalised copy goes (same strides)
+  mutable bool fused1 = false, fused2 = false;
+  mutable Act ln2_act;            // filled when fused2 and no view was given
 };
 
 struct Exec {
@@ -466,13 +474,31 @@ struct Exec {
         }
       }
     }
+    const DType tin = o.ext_in ? DT_F32 : ta;
+    const DType tout = o.ext_out ? DT_F32 : ta;
+    const bool tc = (prec == VT_PREC_BF16) && !o.force_simt && !o.ext_in && w.Kpad > 0 && conv_tc_supported(p, tout, dry);
+    // LayerNorm fusion into the epilogue: the planning (dry) pass and the real pass must take the same decision
+    TcLnFusion lf;
+    if (tc && tout == DT_BF16 && m->desc.norm_type == VT_NORM_LAYERNORM && conv_tc_can_fuse_ln(p)) {
+      if (o.ln1) {
+        lf.mode = 1; lf.silu = o.ln1_silu; lf.gamma = o.ln1->gamma; lf.beta = o.ln1->beta;
+        o.fused1 = true;
+      } else if (o.ln2) {
+        lf.mode = 2; lf.silu = o.ln2_silu; lf.gamma = o.ln2->gamma; lf.beta = o.ln2->beta;
+        if (o.out_view) {
+          lf.out2 = o.ln2_view;
+        } else {
+          o.ln2_act = new_act(out.B, out.T, out.H, out.W, out.C);
+          lf.out2 = o.ln2_act.p;
+        }
+        o.fused2 = true;
+        if (!ok()) return out;
+      }
+    }
     if (!dry) {
-      const DType tin = o.ext_in ? DT_F32 : ta;
-      const DType tout = o.ext_out ? DT_F32 : ta;
-      const bool tc = (prec == VT_PREC_BF16) && !o.force_simt && !o.ext_in && w.w_nk && conv_tc_supported(p, tout);
       const bool stem = (prec == VT_PREC_BF16) && !o.force_simt && o.ext_in && !o.ext_out && !o.out_view && w.w_stem && conv_stem_supported(p);
       if (tc) {
-        if (!cuda(launch_conv_tc(p, (const bf16*)in.p, w.w_nk, w.Kpad, out.p, tout, s), conv_tc_last_error())) return out;
+        if (!cuda(launch_conv_tc(p, (const bf16*)in.p, w.w_nk, w.Kpad, out.p, tout, s, 1, 0, lf.mode ? &lf : nullptr), conv_tc_last_error())) return out;
       } else if (stem) {
         if (!cuda(launch_conv_stem(p, o.ext_in, w.w_stem, (bf16*)out.p, s), "conv_stem")) return out;
       } else if (!w.w_kn) {
@@ -529,54 +555,56 @@ struct Exec {
     return out;
   }
 
-  // ResnetBlock (2D, per frame): model_3dcausal.py:317-337
-  Act res2d(const ResBlockW& r, Act x) {
-    Act n1 = norm(r.n1, x, true, false);
-    Act h1 = conv(r.c1, n1, ConvOpt());
+  // The residual stream: x plus, when the producing conv's epilogue already made it, n = act(LN_{n_of}(x)).
+  struct Stream {
+    Act x, n;
+    const NormW* n_of = nullptr;
+  };
+  Act take_norm(Stream& st, const NormW& nw, bool silu, bool per_position) {
+    if (st.n.p && st.n_of == &nw) {
+      Act r = st.n;
+      st.n = Act();
+      st.n_of = nullptr;
+      return r;
+    }
+    return norm(nw, st.x, silu, per_position);
+  }
+  void set_stream(Stream& st, Act out, const ConvOpt& o) {
+    if (st.n.p) free_act(st.n);
+    free_act(st.x);
+    st.x = out;
+    st.n = Act();
+    st.n_of = nullptr;
+    if (o.fused2) { st.n = o.ln2_act; st.n_of = o.ln2; }
+  }
+  // ResnetBlock (2D, model_3dcausal.py:317-337), ResnetCausalBlock1D (:473-499; GroupNorm statistics per position, see
+  // the oracle) and ResnetCausalBlock (3D, :400-424) share one shape: LN,SiLU,conv1,LN,SiLU,conv2,+skip.
+  // `next`: the norm the FOLLOWING stage applies to this block's output (fused into conv2's epilogue when possible).
+  void resblock(const ResBlockW& r, Stream& st, int kind /*2,1,3*/, const NormW* next, bool next_silu) {
+    const bool pp = kind == 1;
+    const std::string k1 = r.key + ".conv1", k2 = r.key + ".conv2";
+    Act n1 = take_norm(st, r.n1, true, pp);
+    ConvOpt o1;
+    if (kind != 2) o1.cache_key = k1.c_str();
+    o1.ln1 = &r.n2;
+    Act h1 = conv(r.c1, n1, o1);
     free_act(n1);
-    Act n2 = norm(r.n2, h1, true, false);
-    free_act(h1);
-    Act skip = x;
-    if (r.has_nin) skip = conv(r.nin, x, ConvOpt());
+    Act n2 = h1;
+    if (!o1.fused1) {
+      n2 = norm(r.n2, h1, true, pp);
+      free_act(h1);
+    }
+    Act skip = st.x;
+    if (r.has_nin) skip = conv(r.nin, st.x, ConvOpt());
     ConvOpt o;
     o.res_mode = 1; o.res = &skip;
+    if (kind != 2) o.cache_key = k2.c_str();
+    o.ln2 = next; o.ln2_silu = next_silu;
     Act out = conv(r.c2, n2, o);
     free_act(n2);
     if (r.has_nin) free_act(skip);
-    free_act(x);
-    return out;
+    set_stream(st, out, o);
   }
-  // ResnetCausalBlock1D: model_3dcausal.py:473-499 (GroupNorm statistics per position, see oracle)
-  Act res1d(const ResBlockW& r, Act x) {
-    const std::string k1 = r.key + ".conv1", k2 = r.key + ".conv2";
-    Act n1 = norm(r.n1, x, true, true);
-    ConvOpt o1; o1.cache_key = k1.c_str();
-    Act h1 = conv(r.c1, n1, o1);
-    free_act(n1);
-    Act n2 = norm(r.n2, h1, true, true);
-    free_act(h1);
-    ConvOpt o; o.res_mode = 1; o.res = &x; o.cache_key = k2.c_str();
-    Act out = conv(r.c2, n2, o);
-    free_act(n2);
-    free_act(x);
-    return out;
-  }
-  // ResnetCausalBlock (3D, mid): model_3dcausal.py:400-424
-  Act res3d(const ResBlockW& r, Act x) {
-    const std::string k1 = r.key + ".conv1", k2 = r.key + ".conv2";
-    Act n1 = norm(r.n1, x, true, false);
-    ConvOpt o1; o1.cache_key = k1.c_str();
-    Act h1 = conv(r.c1, n1, o1);
-    free_act(n1);
-    Act n2 = norm(r.n2, h1, true, false);
-    free_act(h1);
-    ConvOpt o; o.res_mode = 1; o.res = &x; o.cache_key = k2.c_str();
-    Act out = conv(r.c2, n2, o);
-    free_act(n2);
-    free_act(x);
-    return out;
-  }
-  // AttnBlockWrapper: model_3dcausal.py:114-141
   // tcgen05 path of the attention core: S = scale * Q K^T (fp32), P = softmax(S) (bf16), O = P V.
   // Both products are the conv_tc GEMM with per-frame "weights": K of the frame for the scores, V^T for the output.
   bool attention_tc(const Act& q, const Act& k, const Act& v, Act& o) {
@@ -630,19 +658,20 @@ struct Exec {
     ar.release(S);
     return o;
   }
-  Act attn(const AttnW& a, Act x) {
-    Act n = norm(a.n, x, false, false);
+  // AttnBlockWrapper: model_3dcausal.py:114-141
+  void attn(const AttnW& a, Stream& st, const NormW* next, bool next_silu) {
+    Act n = take_norm(st, a.n, false, false);
     Act q = conv(a.q, n, ConvOpt());
     Act k = conv(a.k, n, ConvOpt());
     Act v = conv(a.v, n, ConvOpt());
     free_act(n);
     Act o = attention_core(q, k, v);
     free_act(q); free_act(k); free_act(v);
-    ConvOpt op; op.res_mode = 1; op.res = &x;
+    ConvOpt op; op.res_mode = 1; op.res = &st.x;
+    op.ln2 = next; op.ln2_silu = next_silu;
     Act out = conv(a.proj, o, op);
     free_act(o);
-    free_act(x);
-    return out;
+    set_stream(st, out, op);
   }
   Act upsample_mat(const Act& x, int ut, int uh, int uw) {
     Act y = new_act(x.B, x.T * ut, x.H * uh, x.W * uw, x.C);
@@ -651,48 +680,107 @@ struct Exec {
   }
   bool fold_upsample() const { return prec == VT_PREC_EXACT; }
 
+  bool phase_ln_ok(int Co) const {
+    return prec == VT_PREC_BF16 && m->desc.norm_type == VT_NORM_LAYERNORM && Co % 32 == 0 && Co <= 256;
+  }
+  // Downsample: pad (0,1,0,1) + conv3x3 stride 2 (model_3dcausal.py:223-227)
+  void down(const LevelW& lv, Stream& st, const NormW* next, bool next_silu) {
+    ConvOpt o; o.sh = 2; o.sw = 2; o.ph0 = 0; o.ph1 = 1; o.pw0 = 0; o.pw1 = 1;
+    o.ln2 = next; o.ln2_silu = next_silu;
+    Act y = conv(lv.resample, st.x, o);
+    set_stream(st, y, o);
+  }
   // TimeDownsampleResCausal2x: model_3dcausal.py:247-252 / model_3dcausal_v1_1.py:289-302
-  Act time_down(const LevelW& lv, Act x) {
+  void time_down(const LevelW& lv, Stream& st, const NormW* next, bool next_silu) {
     const std::string ck_ = lv.tkey + ".conv";
     ConvOpt o;
-    o.st = 2; o.res_mode = 3; o.res = &x; o.ra = lv.alpha; o.rb = 1.f - lv.alpha; o.cache_key = ck_.c_str();
-    Act out = conv(lv.tconv, x, o);
-    free_act(x);
-    return out;
+    o.st = 2; o.res_mode = 3; o.res = &st.x; o.ra = lv.alpha; o.rb = 1.f - lv.alpha; o.cache_key = ck_.c_str();
+    o.ln2 = next; o.ln2_silu = next_silu;
+    Act out = conv(lv.tconv, st.x, o);
+    set_stream(st, out, o);
+  }
+  // Upsample: nearest 2x (H,W) + conv3x3 (model_3dcausal.py:208-212)
+  void up(const LevelW& lv, Stream& st, const NormW* next, bool next_silu) {
+    Act& h = st.x;
+    if (fold_upsample()) {
+      ConvOpt o; o.uh = 2; o.uw = 2;
+      Act y = conv(lv.resample, h, o);
+      set_stream(st, y, o);
+    } else if (lv.has_up_phase && prec == VT_PREC_BF16) {
+      // four parity classes of the 2x-upsampled output, each a 1x2x2 conv on the low-resolution input
+      Act y = new_act(h.B, h.T, 2 * h.H, 2 * h.W, lv.resample.Co);
+      const bool fuse = next && phase_ln_ok(lv.resample.Co);
+      Act n;
+      if (fuse) n = new_act(h.B, h.T, 2 * h.H, 2 * h.W, lv.resample.Co);
+      const long long C = lv.resample.Co, Wo2 = 2 * h.W, Ho2 = 2 * h.H;
+      ConvOpt last;
+      for (int py = 0; py < 2 && ok(); ++py)
+        for (int px = 0; px < 2 && ok(); ++px) {
+          ConvOpt o;
+          o.ph0 = py == 0 ? 1 : 0; o.ph1 = 1 - o.ph0; o.pw0 = px == 0 ? 1 : 0; o.pw1 = 1 - o.pw0;
+          const size_t off = (size_t)((py * Wo2 + px) * C) * dtype_size(ta);
+          o.out_view = dry ? y.p : (void*)((char*)y.p + off);
+          o.ov_sW = 2 * C; o.ov_sH = 2 * Wo2 * C; o.ov_sT = Ho2 * Wo2 * C; o.ov_sB = o.ov_sT * h.T;
+          if (fuse) { o.ln2 = next; o.ln2_silu = next_silu; o.ln2_view = dry ? n.p : (void*)((char*)n.p + off); }
+          conv(lv.up_ph[py * 2 + px], h, o);
+          if (fuse && ok() && !o.fused2) rc = fail(VT_ERR_INVALID, "upsample phase conv did not fuse its LayerNorm");
+        }
+      set_stream(st, y, last);
+      if (fuse) { st.n = n; st.n_of = next; }
+    } else {
+      Act hu = upsample_mat(h, 1, 2, 2);
+      ConvOpt o; o.ln2 = next; o.ln2_silu = next_silu;
+      Act y = conv(lv.resample, hu, o);
+      free_act(hu);
+      set_stream(st, y, o);
+    }
   }
   // TimeUpsampleResCausal2x: model_3dcausal.py:267-273 / model_3dcausal_v1_1.py:325-343
-  Act time_up(const LevelW& lv, Act x) {
+  void time_up(const LevelW& lv, Stream& st, const NormW* next, bool next_silu) {
+    Act x = st.x;          // consumed here; st.x is re-pointed by set_stream at every exit
+    st.x = Act();
     const bool v11 = m->desc.version == 1;
     const std::string ckey = lv.tkey + ".conv";
     ConvOpt o;
     o.ra = lv.alpha; o.rb = 1.f - lv.alpha; o.cache_key = ckey.c_str();
+    o.ln2 = next; o.ln2_silu = next_silu;
     if (!v11) {
       if (fold_upsample()) {
         o.ut = 2; o.res_mode = 2; o.res = &x;
         Act out = conv(lv.tconv, x, o);
         free_act(x);
-        return out;
+        set_stream(st, out, o);
+        return;
       }
       if (lv.has_tup_phase && prec == VT_PREC_BF16) {
         // even / odd output frames: 2x3x3 convs on the un-upsampled input, mixed with x[t/2] in the epilogue
         Act out = new_act(x.B, 2 * x.T, x.H, x.W, lv.tconv.Co);
+        const bool fuse = next && phase_ln_ok(lv.tconv.Co);
+        Act n;
+        if (fuse) n = new_act(x.B, 2 * x.T, x.H, x.W, lv.tconv.Co);
         const long long fr = (long long)x.H * x.W * lv.tconv.Co;
         for (int pt = 0; pt < 2 && ok(); ++pt) {
           ConvOpt op;
           op.ra = lv.alpha; op.rb = 1.f - lv.alpha; op.res_mode = 1; op.res = &x;
-          op.out_view = dry ? out.p : (void*)((char*)out.p + (size_t)(pt * fr) * dtype_size(ta));
+          const size_t off = (size_t)(pt * fr) * dtype_size(ta);
+          op.out_view = dry ? out.p : (void*)((char*)out.p + off);
           op.ov_sW = lv.tconv.Co; op.ov_sH = (long long)x.W * lv.tconv.Co; op.ov_sT = 2 * fr; op.ov_sB = 2 * fr * x.T;
+          if (fuse) { op.ln2 = next; op.ln2_silu = next_silu; op.ln2_view = dry ? n.p : (void*)((char*)n.p + off); }
           conv(lv.tup_ph[pt], x, op);
+          if (fuse && ok() && !op.fused2) rc = fail(VT_ERR_INVALID, "time-upsample phase conv did not fuse its LayerNorm");
         }
         free_act(x);
-        return out;
+        set_stream(st, out, ConvOpt());
+        if (fuse) { st.n = n; st.n_of = next; }
+        return;
       }
       Act xu = upsample_mat(x, 2, 1, 1);
       free_act(x);
       o.res_mode = 1; o.res = &xu;
       Act out = conv(lv.tconv, xu, o);
       free_act(xu);
-      return out;
+      set_stream(st, out, o);
+      return;
     }
     if (m->desc.interpolation_mode != VT_INTERP_TRILINEAR) {
       Act xu = upsample_mat(x, 2, 1, 1);
@@ -700,7 +788,8 @@ struct Exec {
       o.res_mode = 1; o.res = &xu;
       Act out = conv(lv.tconv, xu, o);
       free_act(xu);
-      return out;
+      set_stream(st, out, o);
+      return;
     }
     // trilinear with cache (model_3dcausal_v1_1.py:329-340)
     const int n = lv.num_temp_upsample;
@@ -711,7 +800,7 @@ struct Exec {
     CacheBuf* cb = nullptr;
     if (persist) {
       cb = get_cache(lv.tkey + "#up", n, (size_t)x.B * n * fe * es);
-      if (!ok()) { free_act(x); return Act(); }
+      if (!ok()) { free_act(x); return; }
     }
     Act xu;
     Act view;
@@ -764,11 +853,49 @@ struct Exec {
     o.res_mode = 1; o.res = &view; o.in_bs = bs; o.res_bs = bs;
     Act out = conv(lv.tconv, view, o);
     if (first) free_act(xu); else free_act(big);
-    return out;
+    set_stream(st, out, o);
   }
 };
 
 // ---- encoder / decoder stacks ----------------------------------------------------------------------
+// The stack is flattened into stages so that each stream-producing conv knows which norm the NEXT stage applies to its
+// output (and can fuse it into its epilogue).
+struct Stage {
+  enum Kind { RES2D, RES1D, RES3D, ATTN, DOWN, TDOWN, UP, TUP, HEAD } kind;
+  const ResBlockW* rb = nullptr;
+  const AttnW* at = nullptr;
+  const LevelW* lv = nullptr;
+  const NormW* head_norm = nullptr;
+  const NormW* first_norm(bool* silu) const {
+    *silu = true;
+    switch (kind) {
+      case RES2D: case RES1D: case RES3D: return &rb->n1;
+      case ATTN: *silu = false; return &at->n;
+      case HEAD: return head_norm;
+      default: return nullptr;
+    }
+  }
+};
+
+static void run_stages(Exec& ex, Exec::Stream& st, const std::vector<Stage>& stages) {
+  for (size_t i = 0; i < stages.size() && ex.ok(); ++i) {
+    const Stage& sg = stages[i];
+    bool nsilu = true;
+    const NormW* next = (i + 1 < stages.size()) ? stages[i + 1].first_norm(&nsilu) : nullptr;
+    switch (sg.kind) {
+      case Stage::RES2D: ex.resblock(*sg.rb, st, 2, next, nsilu); break;
+      case Stage::RES1D: ex.resblock(*sg.rb, st, 1, next, nsilu); break;
+      case Stage::RES3D: ex.resblock(*sg.rb, st, 3, next, nsilu); break;
+      case Stage::ATTN: ex.attn(*sg.at, st, next, nsilu); break;
+      case Stage::DOWN: ex.down(*sg.lv, st, next, nsilu); break;
+      case Stage::TDOWN: ex.time_down(*sg.lv, st, next, nsilu); break;
+      case Stage::UP: ex.up(*sg.lv, st, next, nsilu); break;
+      case Stage::TUP: ex.time_up(*sg.lv, st, next, nsilu); break;
+      case Stage::HEAD: break;
+    }
+  }
+}
+
 // x_ext: fp32 [B,Cin,T,H,W]; h_out: fp32 [B,Cz,Tz,Hz,Wz]
 static void run_encoder(Exec& ex, const float* x_ext, int B, int T, int H, int W, float* h_out) {
   vt_model* m = ex.m;
@@ -779,43 +906,38 @@ static void run_encoder(Exec& ex, const float* x_ext, int B, int T, int H, int W
   if (T % tdf != 0) t_rep = (d.version == 0) ? (tdf - 1) : (tdf - T % tdf);  // model_3dcausal.py:685-689 / _v1_1.py:755-760
   Act xin;
   xin.p = (void*)x_ext; xin.B = B; xin.T = T; xin.H = H; xin.W = W; xin.C = d.in_channels;
-  Act h;
+  Exec::Stream st;
   if (d.version == 1 && ex.ck && ex.ck->persist) {
-    // chunked v1.1: the causal cache of conv_in holds *padded input* frames; materialise the replicate-padded
-    // chunk channels-last so the cache update sees the same tensor the reference caches.
+    // chunked v1.1: the causal cache of conv_in holds *padded input* frames; materialise the replicate-padded chunk
+    // channels-last so the cache update sees the same tensor the reference caches (model_3dcausal_v1_1.py:230-233).
     Act xp = ex.new_act(B, T + t_rep, H, W, d.in_channels);
-    if (ex.ok() && !ex.dry) {
-      // gather NCDHW fp32 -> channels-last activation type with replicate front pad via a 1x1x1 "copy conv" is
-      // overkill; use the conv kernel itself on the external tensor instead: conv_in reads x_ext with t_rep, and
-      // the cache is updated from a channels-last copy made here.
-      ex.cuda(launch_ncdhw_to_cl(ex.ta, x_ext, xp.p, B, d.in_channels, T, H, W, t_rep, ex.s), "ncdhw_to_cl");
-    }
+    if (ex.ok() && !ex.dry) ex.cuda(launch_ncdhw_to_cl(ex.ta, x_ext, xp.p, B, d.in_channels, T, H, W, t_rep, ex.s), "ncdhw_to_cl");
     ConvOpt o; o.cache_key = "encoder.conv_in";
-    h = ex.conv(e.conv_in, xp, o);
+    st.x = ex.conv(e.conv_in, xp, o);
     ex.free_act(xp);
   } else {
     ConvOpt o; o.ext_in = x_ext; o.t_rep = t_rep;
-    h = ex.conv(e.conv_in, xin, o);
+    st.x = ex.conv(e.conv_in, xin, o);
   }
+  std::vector<Stage> stages;
   for (size_t l = 0; l < e.levels.size(); ++l) {
     const LevelW& lv = e.levels[l];
     for (size_t b = 0; b < lv.blk.size(); ++b) {
-      h = ex.res2d(lv.blk[b], h);
-      h = ex.res1d(lv.tblk[b], h);
+      Stage a; a.kind = Stage::RES2D; a.rb = &lv.blk[b]; stages.push_back(a);
+      Stage t; t.kind = Stage::RES1D; t.rb = &lv.tblk[b]; stages.push_back(t);
     }
     if (lv.has_resample) {
-      ConvOpt o; o.sh = 2; o.sw = 2; o.ph0 = 0; o.ph1 = 1; o.pw0 = 0; o.pw1 = 1;  // Downsample: model_3dcausal.py:223-227
-      Act y = ex.conv(lv.resample, h, o);
-      ex.free_act(h);
-      h = y;
-      if (lv.has_tres) h = ex.time_down(lv, h);
+      Stage a; a.kind = Stage::DOWN; a.lv = &lv; stages.push_back(a);
+      if (lv.has_tres) { Stage t; t.kind = Stage::TDOWN; t.lv = &lv; stages.push_back(t); }
     }
   }
-  h = ex.res3d(e.mid1, h);
-  h = ex.attn(e.attn, h);
-  h = ex.res3d(e.mid2, h);
-  Act n = ex.norm(e.norm_out, h, true, false);
-  ex.free_act(h);
+  { Stage a; a.kind = Stage::RES3D; a.rb = &e.mid1; stages.push_back(a); }
+  { Stage a; a.kind = Stage::ATTN; a.at = &e.attn; stages.push_back(a); }
+  { Stage a; a.kind = Stage::RES3D; a.rb = &e.mid2; stages.push_back(a); }
+  { Stage a; a.kind = Stage::HEAD; a.head_norm = &e.norm_out; stages.push_back(a); }
+  run_stages(ex, st, stages);
+  Act n = ex.take_norm(st, e.norm_out, true, false);
+  ex.free_act(st.x);
   ConvOpt o; o.ext_out = h_out; o.cache_key = "encoder.conv_out";
   ex.conv(e.conv_out, n, o);
   ex.free_act(n);
@@ -828,58 +950,36 @@ static void run_decoder(Exec& ex, const float* z_ext, int B, int Tz, int Hz, int
   const StackW& g = m->dec;
   Act zin;
   zin.p = (void*)z_ext; zin.B = B; zin.T = Tz; zin.H = Hz; zin.W = Wz; zin.C = d.z_channels;
-  Act h;
+  Exec::Stream st;
   if (d.version == 1 && ex.ck && ex.ck->persist) {
     Act zp = ex.new_act(B, Tz, Hz, Wz, d.z_channels);
     if (ex.ok() && !ex.dry) ex.cuda(launch_ncdhw_to_cl(ex.ta, z_ext, zp.p, B, d.z_channels, Tz, Hz, Wz, 0, ex.s), "ncdhw_to_cl");
     ConvOpt o; o.cache_key = "decoder.conv_in";
-    h = ex.conv(g.conv_in, zp, o);
+    st.x = ex.conv(g.conv_in, zp, o);
     ex.free_act(zp);
   } else {
     ConvOpt o; o.ext_in = z_ext;
-    h = ex.conv(g.conv_in, zin, o);
+    st.x = ex.conv(g.conv_in, zin, o);
   }
-  h = ex.res3d(g.mid1, h);
-  h = ex.attn(g.attn, h);
-  h = ex.res3d(g.mid2, h);
+  std::vector<Stage> stages;
+  { Stage a; a.kind = Stage::RES3D; a.rb = &g.mid1; stages.push_back(a); }
+  { Stage a; a.kind = Stage::ATTN; a.at = &g.attn; stages.push_back(a); }
+  { Stage a; a.kind = Stage::RES3D; a.rb = &g.mid2; stages.push_back(a); }
   for (int l = (int)g.levels.size() - 1; l >= 0; --l) {
     const LevelW& lv = g.levels[l];
     for (size_t b = 0; b < lv.blk.size(); ++b) {
-      h = ex.res2d(lv.blk[b], h);
-      h = ex.res1d(lv.tblk[b], h);
+      Stage a; a.kind = Stage::RES2D; a.rb = &lv.blk[b]; stages.push_back(a);
+      Stage t; t.kind = Stage::RES1D; t.rb = &lv.tblk[b]; stages.push_back(t);
     }
     if (lv.has_resample) {
-      // Upsample: nearest 2x (H,W) + conv3x3 (model_3dcausal.py:208-212)
-      Act y;
-      if (ex.fold_upsample()) {
-        ConvOpt o; o.uh = 2; o.uw = 2;
-        y = ex.conv(lv.resample, h, o);
-        ex.free_act(h);
-      } else if (lv.has_up_phase && ex.prec == VT_PREC_BF16) {
-        // four parity classes of the 2x-upsampled output, each a 1x2x2 conv on the low-resolution input
-        y = ex.new_act(h.B, h.T, 2 * h.H, 2 * h.W, lv.resample.Co);
-        const long long C = lv.resample.Co, Wo2 = 2 * h.W, Ho2 = 2 * h.H;
-        for (int py = 0; py < 2 && ex.ok(); ++py)
-          for (int px = 0; px < 2 && ex.ok(); ++px) {
-            ConvOpt o;
-            o.ph0 = py == 0 ? 1 : 0; o.ph1 = 1 - o.ph0; o.pw0 = px == 0 ? 1 : 0; o.pw1 = 1 - o.pw0;
-            o.out_view = ex.dry ? y.p : (void*)((char*)y.p + (size_t)((py * Wo2 + px) * C) * dtype_size(ex.ta));
-            o.ov_sW = 2 * C; o.ov_sH = 2 * Wo2 * C; o.ov_sT = Ho2 * Wo2 * C; o.ov_sB = o.ov_sT * h.T;
-            ex.conv(lv.up_ph[py * 2 + px], h, o);
-          }
-        ex.free_act(h);
-      } else {
-        Act hu = ex.upsample_mat(h, 1, 2, 2);
-        ex.free_act(h);
-        y = ex.conv(lv.resample, hu, ConvOpt());
-        ex.free_act(hu);
-      }
-      h = y;
-      if (lv.has_tres) h = ex.time_up(lv, h);   // nested under spatial_us as in model_3dcausal.py:844-853
+      Stage a; a.kind = Stage::UP; a.lv = &lv; stages.push_back(a);
+      if (lv.has_tres) { Stage t; t.kind = Stage::TUP; t.lv = &lv; stages.push_back(t); }  // nested as model_3dcausal.py:844-853
     }
   }
-  Act n = ex.norm(g.norm_out, h, true, false);
-  ex.free_act(h);
+  { Stage a; a.kind = Stage::HEAD; a.head_norm = &g.norm_out; stages.push_back(a); }
+  run_stages(ex, st, stages);
+  Act n = ex.take_norm(st, g.norm_out, true, false);
+  ex.free_act(st.x);
   ConvOpt o; o.ext_out = x_out; o.cache_key = "decoder.conv_out";
   if (d.version == 0) o.to_off = d.time_downsample_factor - 1;  // model_3dcausal.py:883-885
   ex.conv(g.conv_out, n, o);
