@@ -59,12 +59,24 @@ struct TcParams {
   const float* ln_gamma;
   const float* ln_beta;
   void* out2;
+  // residual add through the tensor pipe: BN/64 extra K steps with A = residual tile (TMA) and B = a slice of the
+  // identity matrix, so `+ x` costs no epilogue work at all (res_mode 1 with ra == rb == 1)
+  int res_mma;
+  // coalesced epilogue: bf16 results are staged in shared memory (SWIZZLE_128B rows of 64 channels) and written with
+  // TMA tensor stores of {64, sBW, sBH, sBT} boxes (partial tiles are clipped by the tensor bounds)
+  int tma_store;
+  int sBH, sBT;              // store box of one M tile (sBW == BW)
+  uint32_t stage_off;        // byte offset of the staging buffers [2 groups][16 KB] from the aligned smem base
 };
 
 struct TcMaps {
   CUtensorMap a[4];          // activation maps; [1..3] are the odd-parity views used by stride-2 convolutions
   CUtensorMap c;             // v1.1 causal cache
   CUtensorMap b;             // weights
+  CUtensorMap r;             // residual tensor (output geometry), box = A box
+  CUtensorMap e;             // 256 x 256 bf16 identity
+  CUtensorMap o;             // output store map
+  CUtensorMap o2;            // second output (fused LayerNorm result)
 };
 
 constexpr int kEpiWarps = 8;
@@ -119,6 +131,16 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+      ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -227,7 +249,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   const uint32_t a_bytes = (uint32_t)p.MT * kABytes;
   const uint32_t b_bytes = (uint32_t)p.BN * 128u;
   const uint32_t stage_bytes = a_bytes + b_bytes;
-  const uint32_t bar_base = smem_base + p.stages * stage_bytes;
+  const uint32_t bar_base = smem_base + p.stages * stage_bytes + (p.tma_store ? 2u * 16384u : 0u);
   // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2]; then tmem ptr; then bias[2][256]
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
@@ -245,6 +267,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     prefetch_tmap(&maps.b);
     if (p.sp == 2) { prefetch_tmap(&maps.a[1]); prefetch_tmap(&maps.a[2]); prefetch_tmap(&maps.a[3]); }
     if (p.t_mode == 2) prefetch_tmap(&maps.c);
+    if (p.res_mma) { prefetch_tmap(&maps.r); prefetch_tmap(&maps.e); }
+    if (p.tma_store) { prefetch_tmap(&maps.o); if (p.ln_mode == 2) prefetch_tmap(&maps.o2); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -304,6 +328,17 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
         }
+        if (p.res_mma) {
+          // out += I * residual : A = residual tile of this output box, channels [n0 + 64g, +64); B = identity columns
+          for (int g = 0; g < p.BN / 64; ++g) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_expect_tx(full_bar(stage), stage_bytes);
+            const uint32_t sa = smem_base + stage * stage_bytes;
+            tma_load_5d(sa, &maps.r, full_bar(stage), tc.n0 + g * 64, tc.w0, tc.h0, tc.t0, tc.b);
+            tma_load_3d(sa + a_bytes, &maps.e, full_bar(stage), g * 64, 0, 0);
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -341,20 +376,42 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
         }
+        if (p.res_mma) {
+          for (int g = 0; g < p.BN / 64; ++g) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t sa = smem_base + stage * stage_bytes;
+            const uint64_t bdesc = make_sdesc(sa + a_bytes);
+            for (int mt = 0; mt < p.MT; ++mt) {
+              const uint64_t adesc = make_sdesc(sa + mt * kABytes);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16(tmem_d + (uint32_t)(mt * p.BN), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, 1u);
+            }
+            umma_commit(empty_bar(stage));
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+        }
         umma_commit(tfull_bar(as));
       }
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    // Row ownership: MT == 2 -> warps 4-7 own the rows of M tile 0, warps 8-11 those of M tile 1 (full rows);
-    //                MT == 1 -> the two warps of a TMEM lane quarter alternate 32-column chunks of the same row.
+    // Two groups of four warps (one warp per TMEM lane quarter).  MT == 2: group g owns the rows of M tile g;
+    // MT == 1: the groups alternate 64-channel slices of the same 128 rows.
     const int q = warp & 3;            // TMEM lane quarter this warp may read
     const int grp = (warp - 4) >> 2;   // 0 / 1
     const int et = threadIdx.x - 128;
+    const bool leader = (et & 127) == 0;
     const int nchunks = p.BN / 32;
     const int mt = (p.MT == 2) ? grp : 0;
-    const int cb = (p.MT == 2) ? 0 : grp;      // first chunk
-    const int cs = (p.MT == 2) ? 1 : 2;        // chunk step
+    const int sb = (p.MT == 2) ? 0 : grp;      // first 64-channel slice
+    const int ss = (p.MT == 2) ? 1 : 2;        // slice step
+    const int rr = q * 32 + lane;              // row inside the M tile
+    uint8_t* stg_gen = smem_gen + p.stage_off + grp * 16384;
+    const uint32_t stg = smem_base + p.stage_off + grp * 16384;
+    uint8_t* my_stg = stg_gen + rr * 128;
+    const int swz = rr & 7;
     uint32_t it = 0;
     for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const TileCoord tc = decode_tile(p, tile);
@@ -368,16 +425,21 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       }
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
 
-      const int row = mt * 128 + q * 32 + lane;
+      const int row = mt * 128 + rr;
       const int dw = row % p.BW, dh = (row / p.BW) % p.BH, dt = row / (p.BW * p.BH);
       const int t = tc.t0 + dt, h = tc.h0 + dh, w = tc.w0 + dw;
       const bool valid = (t < p.To) && (h < p.Ho) && (w < p.Wo);
       const long long ooff = (long long)tc.b * p.osB + (long long)t * p.osT + (long long)h * p.osH + (long long)w * p.osW;
       bf16* orow = reinterpret_cast<bf16*>(p.out) + ooff + tc.n0;
+      // origin of this M tile's store box
+      const int sw0 = tc.w0;
+      const int sh0 = tc.h0 + ((p.MT == 2 && p.BT == p.sBT) ? mt * p.sBH : 0);
+      const int st0 = tc.t0 + ((p.MT == 2 && p.BT != p.sBT) ? mt * p.sBT : 0);
       const bf16* r0 = nullptr;
       const bf16* r1 = nullptr;
       const bf16* r2 = nullptr;
-      if (valid && p.res_mode == 1) {
+      const bool res_direct = (p.res_mode == 1 && !p.res_mma);
+      if (valid && res_direct) {
         r0 = p.res + (long long)tc.b * p.rsB + (long long)t * p.rsT + (long long)h * p.rsH + (long long)w * p.rsW + tc.n0;
       } else if (valid && p.res_mode == 3) {
         // avg-pool of residual frames 2t-1, 2t, 2t+1 (front pad: zero / frame 0 / 1-frame cache)
@@ -389,101 +451,110 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         if (tb < p.resT) r1 = p.res + sp + (long long)tb * p.rsT;
         if (tcn < p.resT) r2 = p.res + sp + (long long)tcn * p.rsT;
       }
-      // residual of the first chunk is fetched before the accumulator is waited for
-      uint4 rcur[4];
-      const bool pre = valid && p.res_mode == 1;
-      if (pre && cb < nchunks) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) rcur[g] = *reinterpret_cast<const uint4*>(r0 + cb * 32 + g * 8);
-      }
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * p.MT + mt) * p.BN);
       float lsum = 0.f, lsq = 0.f;
+      const bool store_a = (p.ln_mode != 1);
       // ---- pass A: v = rb*(acc+bias) + ra*R ; plain mode stores it, LayerNorm modes also keep it in TMEM + statistics
-      for (int ch = cb; ch < nchunks; ch += cs) {
-        const int j = ch * 32;
-        uint32_t v[32];
-        tmem_ld32(tbase + (uint32_t)j, v);
-        uint4 rnext[4];
-        if (pre && ch + cs < nchunks) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) rnext[g] = *reinterpret_cast<const uint4*>(r0 + (j + 32 * cs) + g * 8);
+      for (int sl = sb; sl * 2 < nchunks; sl += ss) {
+        if (p.tma_store && store_a) {
+          if (leader) tma_store_wait_read();
+          asm volatile("bar.sync %0, 128;" ::"r"(3 + grp) : "memory");
         }
-        tmem_ld_wait();
-        float f[32];
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          const int ch = 2 * sl + c;
+          if (ch >= nchunks) break;
+          const int j = ch * 32;
+          uint32_t v[32];
+          tmem_ld32(tbase + (uint32_t)j, v);
+          tmem_ld_wait();
+          float f[32];
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const float4 bv = *reinterpret_cast<const float4*>(bias_s + j + g * 4);
-          f[g * 4 + 0] = p.rb * (__uint_as_float(v[g * 4 + 0]) + bv.x);
-          f[g * 4 + 1] = p.rb * (__uint_as_float(v[g * 4 + 1]) + bv.y);
-          f[g * 4 + 2] = p.rb * (__uint_as_float(v[g * 4 + 2]) + bv.z);
-          f[g * 4 + 3] = p.rb * (__uint_as_float(v[g * 4 + 3]) + bv.w);
-        }
-        if (valid && p.res_mode == 1) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float rr[8];
-            unpack8(rcur[g], rr);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[g * 8 + i] = fmaf(p.ra, rr[i], f[g * 8 + i]);
+          for (int g = 0; g < 8; ++g) {
+            const float4 bv = *reinterpret_cast<const float4*>(bias_s + j + g * 4);
+            f[g * 4 + 0] = p.rb * (__uint_as_float(v[g * 4 + 0]) + bv.x);
+            f[g * 4 + 1] = p.rb * (__uint_as_float(v[g * 4 + 1]) + bv.y);
+            f[g * 4 + 2] = p.rb * (__uint_as_float(v[g * 4 + 2]) + bv.z);
+            f[g * 4 + 3] = p.rb * (__uint_as_float(v[g * 4 + 3]) + bv.w);
           }
-        } else if (valid && p.res_mode == 3) {
-          const float s3 = p.ra * (1.0f / 3.0f);
+          if (valid && res_direct) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            float rr[8];
-            if (r0) { unpack8(*reinterpret_cast<const uint4*>(r0 + j + g * 8), rr);
+            for (int g = 0; g < 4; ++g) {
+              float rv[8];
+              unpack8(*reinterpret_cast<const uint4*>(r0 + j + g * 8), rv);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) acc[i] += rr[i]; }
-            if (r1) { unpack8(*reinterpret_cast<const uint4*>(r1 + j + g * 8), rr);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) acc[i] += rr[i]; }
-            if (r2) { unpack8(*reinterpret_cast<const uint4*>(r2 + j + g * 8), rr);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) acc[i] += rr[i]; }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[g * 8 + i] = fmaf(s3, acc[i], f[g * 8 + i]);
-          }
-        }
-        if (p.ln_mode) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            lsum += f[i];
-            lsq = fmaf(f[i], f[i], lsq);
-            v[i] = __float_as_uint(f[i]);
-          }
-          tmem_st32(tbase + (uint32_t)j, v);
-        }
-        if (valid && p.ln_mode != 1) {
-          if (p.out_f32) {
-            float* of = reinterpret_cast<float*>(p.out) + ooff;
-            if (p.osC == 1 && tc.n0 + j + 32 <= p.Co_real) {
-#pragma unroll
-              for (int g = 0; g < 8; ++g)
-                *reinterpret_cast<float4*>(of + tc.n0 + j + g * 4) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (tc.n0 + j + i < p.Co_real) of[(long long)(tc.n0 + j + i) * p.osC] = f[i];
+              for (int i = 0; i < 8; ++i) f[g * 8 + i] = fmaf(p.ra, rv[i], f[g * 8 + i]);
             }
-          } else {
+          } else if (valid && p.res_mode == 3) {
+            const float s3 = p.ra * (1.0f / 3.0f);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(orow + j + g * 8) = pack8(f + g * 8);
+            for (int g = 0; g < 4; ++g) {
+              float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+              float rv[8];
+              if (r0) { unpack8(*reinterpret_cast<const uint4*>(r0 + j + g * 8), rv);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] += rv[i]; }
+              if (r1) { unpack8(*reinterpret_cast<const uint4*>(r1 + j + g * 8), rv);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] += rv[i]; }
+              if (r2) { unpack8(*reinterpret_cast<const uint4*>(r2 + j + g * 8), rv);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] += rv[i]; }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[g * 8 + i] = fmaf(s3, acc[i], f[g * 8 + i]);
+            }
+          }
+          if (p.ln_mode) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              lsum += f[i];
+              lsq = fmaf(f[i], f[i], lsq);
+              v[i] = __float_as_uint(f[i]);
+            }
+            tmem_st32(tbase + (uint32_t)j, v);
+          }
+          if (store_a) {
+            if (p.tma_store) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(my_stg + (((c * 4 + g) ^ swz) << 4)) = pack8(f + g * 8);
+            } else if (valid) {
+              if (p.out_f32) {
+                float* of = reinterpret_cast<float*>(p.out) + ooff;
+                if (p.osC == 1 && tc.n0 + j + 32 <= p.Co_real) {
+#pragma unroll
+                  for (int g = 0; g < 8; ++g)
+                    *reinterpret_cast<float4*>(of + tc.n0 + j + g * 4) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i)
+                    if (tc.n0 + j + i < p.Co_real) of[(long long)(tc.n0 + j + i) * p.osC] = f[i];
+                }
+              } else {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(orow + j + g * 8) = pack8(f + g * 8);
+              }
+            }
           }
         }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) rcur[g] = rnext[g];
+        if (p.tma_store && store_a) {
+          fence_async_smem();
+          asm volatile("bar.sync %0, 128;" ::"r"(3 + grp) : "memory");
+          if (leader) {
+            tma_store_5d(&maps.o, stg, tc.n0 + sl * 64, sw0, sh0, st0, tc.b);
+            tma_store_commit();
+          }
+        }
       }
       if (p.ln_mode) {
         // ---- LayerNorm over the Cout values of this row (model_3dcausal.py:62-80, eps 1e-6), optional SiLU (:26-27)
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        if (p.MT == 1) {  // the other warp of this lane quarter holds the other half of the row
-          float* xs = stat_s + ((grp * 128 + q * 32 + lane) << 1);
+        if (p.MT == 1) {  // the other group holds the other slices of the row
+          float* xs = stat_s + ((grp * 128 + rr) << 1);
           xs[0] = lsum; xs[1] = lsq;
           asm volatile("bar.sync 2, %0;" ::"n"(kEpiWarps * 32) : "memory");
-          const float* ys = stat_s + ((((grp ^ 1) * 128) + q * 32 + lane) << 1);
+          const float* ys = stat_s + ((((grp ^ 1) * 128) + rr) << 1);
           lsum += ys[0]; lsq += ys[1];
         }
         const float inv_n = 1.0f / (float)p.BN;
@@ -493,12 +564,20 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         const float rstd = rsqrtf(var + 1e-6f);
         const float nmr = -mean * rstd;
         bf16* nrow = reinterpret_cast<bf16*>(p.ln_mode == 1 ? p.out : p.out2) + ooff + tc.n0;
-        for (int ch = cb; ch < nchunks; ch += cs) {
-          const int j = ch * 32;
-          uint32_t v[32];
-          tmem_ld32(tbase + (uint32_t)j, v);
-          tmem_ld_wait();
-          if (valid) {
+        const CUtensorMap* nmap = (p.ln_mode == 1) ? &maps.o : &maps.o2;
+        for (int sl = sb; sl * 2 < nchunks; sl += ss) {
+          if (p.tma_store) {
+            if (leader) tma_store_wait_read();
+            asm volatile("bar.sync %0, 128;" ::"r"(3 + grp) : "memory");
+          }
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            const int ch = 2 * sl + c;
+            if (ch >= nchunks) break;
+            const int j = ch * 32;
+            uint32_t v[32];
+            tmem_ld32(tbase + (uint32_t)j, v);
+            tmem_ld_wait();
             float f[32];
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
@@ -513,8 +592,21 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] = silu_f(f[i]);
             }
+            if (p.tma_store) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(nrow + j + g * 8) = pack8(f + g * 8);
+              for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(my_stg + (((c * 4 + g) ^ swz) << 4)) = pack8(f + g * 8);
+            } else if (valid) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(nrow + j + g * 8) = pack8(f + g * 8);
+            }
+          }
+          if (p.tma_store) {
+            fence_async_smem();
+            asm volatile("bar.sync %0, 128;" ::"r"(3 + grp) : "memory");
+            if (leader) {
+              tma_store_5d(nmap, stg, tc.n0 + sl * 64, sw0, sh0, st0, tc.b);
+              tma_store_commit();
+            }
           }
         }
       }
@@ -522,6 +614,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));
     }
+    if (p.tma_store && leader) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -530,6 +623,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
+}
+
+__global__ void fill_identity_kernel(bf16* e) {
+  const int r = blockIdx.x, c = threadIdx.x;
+  e[r * 256 + c] = __float2bfloat16_rn(r == c ? 1.0f : 0.0f);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -657,17 +755,35 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   }
   t.w_batched = w_batches > 1 ? 1 : 0;
   if (t.w_batched && w_batches != p.B) { g_tc_err = "batched weights need one weight matrix per batch element"; return cudaErrorInvalidValue; }
+  // epilogue strategy
+  t.tma_store = (tout == DT_BF16 && p.osC == 1 && t.BN % 64 == 0 && p.osW % 8 == 0 && p.osH % 8 == 0 && p.osT % 8 == 0 && p.osB % 8 == 0 &&
+                 (((uintptr_t)out) & 15) == 0) ? 1 : 0;
+  {
+    // the staging buffers cost a pipeline stage; long-K layers hide the direct-store epilogue behind their main loop
+    int ntaps_eff = p.kt * p.kh * p.kw;
+    if (ntaps_eff * t.num_kc >= 48) t.tma_store = 0;
+  }
+  t.sBH = t.BH; t.sBT = t.BT;
+  if (t.MT == 2) {
+    if (t.BT >= 2) t.sBT = t.BT / 2; else t.sBH = t.BH / 2;
+    if (t.BW * t.sBH * t.sBT != 128) t.tma_store = 0;
+  }
+  t.res_mma = (p.res_mode == 1 && p.ra == 1.0f && p.rb == 1.0f && t.BN % 64 == 0 && p.Co % 64 == 0 && p.rsW % 8 == 0 && p.rsH % 8 == 0 &&
+               p.rsT % 8 == 0 && p.rsB % 8 == 0 && (((uintptr_t)p.res) & 15) == 0) ? 1 : 0;
   const size_t stage_bytes = (size_t)t.MT * kABytes + (size_t)t.BN * 128;
-  const size_t budget = 220 * 1024;
+  const size_t budget = 222 * 1024;
+  const size_t staging = t.tma_store ? 2 * 16384 : 0;
   const size_t fixed = 1024 /*align*/ + 8 * 2 * 8 + 64 + 2 * 768 * 4 + 2 * 128 * 2 * 4 + 256;
-  int stages = (int)((budget - fixed) / stage_bytes);
+  int stages = (int)((budget - fixed - staging) / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) { g_tc_err = "not enough shared memory for 2 stages"; return cudaErrorInvalidValue; }
   t.stages = stages;
+  // smem layout from the 1024-aligned base: [stages x (A | B)] [staging 2 x 16 KB] [barriers | tmem slot | bias/gamma/beta | stats]
+  t.stage_off = (uint32_t)(stages * stage_bytes);
   uint32_t cols = 32;
   while (cols < (uint32_t)(2 * t.MT * t.BN)) cols <<= 1;
   t.tmem_cols = cols;
-  const size_t smem = fixed + (size_t)stages * stage_bytes + 8 * (2 * stages + 4);
+  const size_t smem = fixed + staging + (size_t)stages * stage_bytes + 8 * (2 * stages + 4);
 
   TcMaps maps;
   // activation view: element (c, w, h, t, b) at base + c + w*sw_ + h*sh_ + t*isT + b*bs  (elements)
@@ -709,6 +825,39 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { g_tc_err = "cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r); return cudaErrorInvalidValue; }
+  }
+  // output / residual maps (output geometry) and the identity used by the residual-through-MMA K steps
+  auto encode_out = [&](CUtensorMap* m, const void* base, int Tn, long long sW, long long sH, long long sT, long long sB, int bw, int bh, int bt) -> bool {
+    cuuint64_t dims[5] = {(cuuint64_t)p.Co, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)Tn, (cuuint64_t)p.B};
+    cuuint64_t strides[4] = {(cuuint64_t)sW * 2, (cuuint64_t)sH * 2, (cuuint64_t)sT * 2, (cuuint64_t)sB * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bt, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { g_tc_err = "cuTensorMapEncodeTiled(output/residual) failed: " + std::to_string((int)r); return false; }
+    return true;
+  };
+  maps.r = maps.a[0]; maps.e = maps.b; maps.o = maps.a[0]; maps.o2 = maps.a[0];
+  if (t.tma_store) {
+    if (!encode_out(&maps.o, out, p.To, p.osW, p.osH, p.osT, p.osB, t.BW, t.sBH, t.sBT)) return cudaErrorInvalidValue;
+    if (t.ln_mode == 2 && !encode_out(&maps.o2, t.out2, p.To, p.osW, p.osH, p.osT, p.osB, t.BW, t.sBH, t.sBT)) return cudaErrorInvalidValue;
+  }
+  if (t.res_mma) {
+    static bf16* ident = nullptr;   // 256 x 256 identity, built once per process on this stream
+    if (!ident) {
+      cudaError_t e = cudaMalloc(&ident, 256 * 256 * sizeof(bf16));
+      if (e != cudaSuccess) { g_tc_err = "cudaMalloc(identity)"; return e; }
+      fill_identity_kernel<<<256, 256, 0, s>>>(ident);
+    }
+    if (!encode_out(&maps.r, p.res, p.resT, p.rsW, p.rsH, p.rsT, p.rsB, t.BW, t.BH, t.BT)) return cudaErrorInvalidValue;
+    cuuint64_t dims[3] = {256, 256, 1};
+    cuuint64_t strides[2] = {512, 256 * 512};
+    cuuint32_t box[3] = {64, (cuuint32_t)t.BN, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(&maps.e, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ident, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { g_tc_err = "cuTensorMapEncodeTiled(identity) failed: " + std::to_string((int)r); return cudaErrorInvalidValue; }
   }
   static bool smem_set = false;
   if (!smem_set) {
