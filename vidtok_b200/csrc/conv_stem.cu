@@ -78,9 +78,11 @@ __global__ void __launch_bounds__(256, 1) conv_stem_kernel(const StemParams p, c
   const uint32_t offP = offB + (uint32_t)p.Co * 256u;
   const uint32_t patch_floats = (uint32_t)p.Ci * 3 * PH * PW;
   const uint32_t offBias = offP + ((patch_floats * 4 + 15) & ~15u);
-  const uint32_t offBar = offBias + 256 * 4;
+  const uint32_t offLut = offBias + 256 * 4;   // im2col k -> patch offset (or -1)
+  const uint32_t offBar = offLut + 128 * 4;
   float* patch = reinterpret_cast<float*>(gen + offP);
   float* sbias = reinterpret_cast<float*>(gen + offBias);
+  int* lut = reinterpret_cast<int*>(gen + offLut);
   const uint32_t bar0 = base + offBar, bar1 = bar0 + 8, tmem_slot = bar0 + 16;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K = p.Ci * 27;
@@ -94,6 +96,15 @@ __global__ void __launch_bounds__(256, 1) conv_stem_kernel(const StemParams p, c
     *reinterpret_cast<uint4*>(gen + offB + kc * (p.Co * 128) + row * 128 + ((u ^ (row & 7)) << 4)) = v;
   }
   for (int i = tid; i < p.Co; i += 256) sbias[i] = p.bias ? p.bias[i] : 0.f;
+  if (tid < 128) {
+    int off = -1;
+    if (tid < K) {
+      const int ci = tid % p.Ci, tap = tid / p.Ci;
+      const int c = tap % 3, bb = (tap / 3) % 3, a = tap / 9;
+      off = ((ci * 3 + a) * PH + bb) * PW + c;
+    }
+    lut[tid] = off;
+  }
   if (tid == 0) {
     mbar_init(bar0, 1);
     mbar_init(bar1, 1);
@@ -148,20 +159,15 @@ __global__ void __launch_bounds__(256, 1) conv_stem_kernel(const StemParams p, c
     __syncthreads();
     const int row = tid & 127, half = tid >> 7;
     const int dh = row / BW, dw = row % BW;
+    const float* prow = patch + dh * PW + dw;
     uint8_t* arow = gen + offA + buf * kATile + row * 128;
     const int u_begin = half == 0 ? 0 : (units + 1) / 2, u_end = half == 0 ? (units + 1) / 2 : units;
     for (int u = u_begin; u < u_end; ++u) {
       float f[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const int k = u * 8 + e;
-        float v = 0.f;
-        if (k < K) {
-          const int ci = k % p.Ci, tap = k / p.Ci;
-          const int c = tap % 3, bb = (tap / 3) % 3, a = tap / 9;
-          v = patch[((ci * 3 + a) * PH + dh + bb) * PW + dw + c];
-        }
-        f[e] = v;
+        const int off = lut[u * 8 + e];
+        f[e] = off >= 0 ? prow[off] : 0.f;
       }
       uint4 pk;
       __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
@@ -270,7 +276,7 @@ cudaError_t launch_conv_stem(const ConvP& p, const float* x, const bf16* wpk, bf
   uint32_t cols = 32;
   while (cols < (uint32_t)(2 * p.Co)) cols <<= 1;
   t.tmem_cols = cols;
-  const size_t smem = 1024 + 2 * kATile + (size_t)p.Co * 256 + (((size_t)p.Ci * 3 * PH * PW * 4 + 15) & ~(size_t)15) + 256 * 4 + 64;
+  const size_t smem = 1024 + 2 * kATile + (size_t)p.Co * 256 + (((size_t)p.Ci * 3 * PH * PW * 4 + 15) & ~(size_t)15) + 256 * 4 + 128 * 4 + 64;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(conv_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));

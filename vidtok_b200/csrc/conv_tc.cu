@@ -17,6 +17,7 @@
 #include <cuda.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -28,6 +29,15 @@ namespace vt {
 namespace {
 
 thread_local std::string g_tc_err;
+// VT_TC_PAIR=0 disables cta_group::2, VT_TC_PAIR=2 forces it whenever the geometry allows (tests on small shapes)
+int g_pair_mode = -1;
+int pair_mode() {
+  if (g_pair_mode < 0) {
+    const char* e = getenv("VT_TC_PAIR");
+    g_pair_mode = e ? atoi(e) : 1;
+  }
+  return g_pair_mode;
+}
 
 struct TcParams {
   int B, To, Ho, Wo, Co, Ti;
@@ -67,6 +77,10 @@ struct TcParams {
   int tma_store;
   int sBH, sBT;              // store box of one M tile (sBW == BW)
   uint32_t stage_off;        // byte offset of the staging buffers [2 groups][16 KB] from the aligned smem base
+  // cta_group::2: two CTAs of a cluster (one TPC) work on one 2*MT*128-row tile; each loads its own rows of A and half of
+  // the B (weight) rows, the leader issues M=256 MMAs that read both halves -> weight bytes per FLOP are halved again
+  int pair;
+  int tileBH, tileBT;        // box of the whole (pair) tile; BH/BT above are the per-CTA box
 };
 
 struct TcMaps {
@@ -141,6 +155,49 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(rank) : "memory");
+}
+// 2-CTA TMA loads: data lands in this CTA's shared memory, the transaction bytes are credited to the LEADER's barrier
+// (peer bit of the barrier address cleared, cute::Sm100MmaPeerBitMask)
+__device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                                int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -191,8 +248,8 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t addr) {
          ((uint64_t)2 << 61);
 }
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
-__device__ __forceinline__ uint32_t make_idesc(int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc(int N, int M = 128) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
@@ -214,7 +271,7 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 struct TileCoord {
   int b, t0, h0, w0, n0;
 };
-__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, long long tile) {
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, long long tile, int rank) {
   TileCoord c;
   const int nt = (int)(tile % p.num_n_tiles);
   long long m = tile / p.num_n_tiles;
@@ -222,7 +279,11 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, long long ti
   const int th = (int)(m % p.tilesH); m /= p.tilesH;
   const int tt = (int)(m % p.tilesT);
   c.b = (int)(m / p.tilesT);
-  c.t0 = tt * p.BT; c.h0 = th * p.BH; c.w0 = tw * p.BW; c.n0 = nt * p.BN;
+  // origin of THIS CTA's box inside the (pair) tile: the second CTA takes the upper half in t (if the tile spans
+  // several frames) or in h
+  c.t0 = tt * p.tileBT + ((p.pair && p.tileBT != p.BT) ? rank * p.BT : 0);
+  c.h0 = th * p.tileBH + ((p.pair && p.tileBT == p.BT) ? rank * p.BH : 0);
+  c.w0 = tw * p.BW; c.n0 = nt * p.BN;
   return c;
 }
 // time coordinate of a tap for a tile; returns false when the whole box is causal zero padding (tap skipped)
@@ -246,8 +307,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = p.pair ? (int)cluster_ctarank() : 0;     // 0 = leader of the CTA pair
+  const long long tile0 = p.pair ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
+  const long long tile_step = p.pair ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
   const uint32_t a_bytes = (uint32_t)p.MT * kABytes;
-  const uint32_t b_bytes = (uint32_t)p.BN * 128u;
+  const int bn_local = p.pair ? p.BN / 2 : p.BN;           // weight rows this CTA stages
+  const uint32_t b_bytes = (uint32_t)bn_local * 128u;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   const uint32_t bar_base = smem_base + p.stages * stage_bytes + (p.tma_store ? 2u * 16384u : 0u);
   // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2]; then tmem ptr; then bias[2][256]
@@ -271,22 +336,29 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     if (p.tma_store) { prefetch_tmap(&maps.o); if (p.ln_mode == 2) prefetch_tmap(&maps.o2); }
   }
   if (warp == 1 && lane == 0) {
+    // pair mode: the leader's full barrier collects its own expect_tx arrival plus the peer's remote arrival (and the
+    // transaction bytes of both CTAs' TMA loads); the leader's tmem_empty barrier collects both CTAs' epilogue warps
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), p.pair ? 2 : 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), kEpiWarps);
+      mbar_init(tempty_bar(s), p.pair ? 2 * kEpiWarps : kEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (p.pair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (p.pair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -297,8 +369,15 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(p, tile);
+      // pair mode: expect_tx (both CTAs' bytes) is posted by the leader only; the peer announces its loads with a
+      // remote arrive on the leader's barrier; both wait on their OWN empty barrier (multicast commit frees both).
+      auto post = [&](int stg_) {
+        if (!p.pair) mbar_expect_tx(full_bar(stg_), stage_bytes);
+        else if (rank == 0) mbar_expect_tx(full_bar(stg_), 2u * stage_bytes);
+        else mbar_arrive_remote(full_bar(stg_), 0);
+      };
+      for (long long tile = tile0; tile < p.num_tiles; tile += tile_step) {
+        const TileCoord tc = decode_tile(p, tile, rank);
         for (int tap = 0; tap < ntaps; ++tap) {
           const int c = tap % p.kw, bb = (tap / p.kw) % p.kh, a = tap / (p.kw * p.kh);
           int tv;
@@ -321,10 +400,15 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           if (from_cache) mapA = &maps.c;
           for (int kc = 0; kc < p.num_kc; ++kc) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            mbar_expect_tx(full_bar(stage), stage_bytes);
+            post(stage);
             const uint32_t sa = smem_base + stage * stage_bytes;
-            tma_load_5d(sa, mapA, full_bar(stage), kc * 64, cw, ch, tv, tc.b);
-            tma_load_3d(sa + a_bytes, &maps.b, full_bar(stage), tap * p.Ci + kc * 64, tc.n0, p.w_batched ? tc.b : 0);
+            if (p.pair) {
+              tma_load_5d_2sm(sa, mapA, full_bar(stage), kc * 64, cw, ch, tv, tc.b);
+              tma_load_3d_2sm(sa + a_bytes, &maps.b, full_bar(stage), tap * p.Ci + kc * 64, tc.n0 + rank * bn_local, p.w_batched ? tc.b : 0);
+            } else {
+              tma_load_5d(sa, mapA, full_bar(stage), kc * 64, cw, ch, tv, tc.b);
+              tma_load_3d(sa + a_bytes, &maps.b, full_bar(stage), tap * p.Ci + kc * 64, tc.n0, p.w_batched ? tc.b : 0);
+            }
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -332,10 +416,15 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           // out += I * residual : A = residual tile of this output box, channels [n0 + 64g, +64); B = identity columns
           for (int g = 0; g < p.BN / 64; ++g) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            mbar_expect_tx(full_bar(stage), stage_bytes);
+            post(stage);
             const uint32_t sa = smem_base + stage * stage_bytes;
-            tma_load_5d(sa, &maps.r, full_bar(stage), tc.n0 + g * 64, tc.w0, tc.h0, tc.t0, tc.b);
-            tma_load_3d(sa + a_bytes, &maps.e, full_bar(stage), g * 64, 0, 0);
+            if (p.pair) {
+              tma_load_5d_2sm(sa, &maps.r, full_bar(stage), tc.n0 + g * 64, tc.w0, tc.h0, tc.t0, tc.b);
+              tma_load_3d_2sm(sa + a_bytes, &maps.e, full_bar(stage), g * 64, rank * bn_local, 0);
+            } else {
+              tma_load_5d(sa, &maps.r, full_bar(stage), tc.n0 + g * 64, tc.w0, tc.h0, tc.t0, tc.b);
+              tma_load_3d(sa + a_bytes, &maps.e, full_bar(stage), g * 64, 0, 0);
+            }
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -343,13 +432,17 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(p.BN);
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc(p.BN, p.pair ? 256 : 128);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t it = 0;
-      for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        const TileCoord tc = decode_tile(p, tile);
+      auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t acc) {
+        if (p.pair) umma_f16_2sm(d, ad, bd, idesc, acc); else umma_f16(d, ad, bd, idesc, acc);
+      };
+      auto commit = [&](uint32_t bar) { if (p.pair) umma_commit_2sm(bar); else umma_commit(bar); };
+      for (long long tile = tile0; tile < p.num_tiles; tile += tile_step, ++it) {
+        const TileCoord tc = decode_tile(p, tile, rank);
         const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
         mbar_wait(tempty_bar(as), aphase ^ 1u);
         tc_fence_after();
@@ -369,10 +462,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
               const uint64_t adesc = make_sdesc(sa + mt * kABytes);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                umma_f16(tmem_d + (uint32_t)(mt * p.BN), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accum | (uint32_t)k);
+                mma(tmem_d + (uint32_t)(mt * p.BN), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), accum | (uint32_t)k);
             }
             accum = 1;
-            umma_commit(empty_bar(stage));
+            commit(empty_bar(stage));
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -386,13 +479,13 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
               const uint64_t adesc = make_sdesc(sa + mt * kABytes);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                umma_f16(tmem_d + (uint32_t)(mt * p.BN), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, 1u);
+                mma(tmem_d + (uint32_t)(mt * p.BN), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), 1u);
             }
-            umma_commit(empty_bar(stage));
+            commit(empty_bar(stage));
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
         }
-        umma_commit(tfull_bar(as));
+        commit(tfull_bar(as));
       }
     }
   } else if (warp >= 4) {
@@ -413,8 +506,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     uint8_t* my_stg = stg_gen + rr * 128;
     const int swz = rr & 7;
     uint32_t it = 0;
-    for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const TileCoord tc = decode_tile(p, tile);
+    for (long long tile = tile0; tile < p.num_tiles; tile += tile_step, ++it) {
+      const TileCoord tc = decode_tile(p, tile, rank);
       const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
       float* bias_s = sbias + as * 768;
       float* gamma_s = bias_s + 256;
@@ -612,16 +705,19 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (lane == 0) {
+        if (p.pair) mbar_arrive_remote(tempty_bar(as), 0); else mbar_arrive(tempty_bar(as));
+      }
     }
     if (p.tma_store && leader) tma_store_wait_all();
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (p.pair) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    if (p.pair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
 }
 
@@ -680,6 +776,7 @@ int choose_bn(int Co) {
 }  // namespace
 
 const char* conv_tc_last_error() { return g_tc_err.c_str(); }
+void conv_tc_set_pair(bool on) { g_pair_mode = on ? 1 : 0; }
 
 bool conv_tc_can_fuse_ln(const ConvP& p) { return p.Co % 32 == 0 && p.Co <= 256 && choose_bn(p.Co) == p.Co; }
 
@@ -736,8 +833,25 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
       t.MT = 2; t.BW = bw2; t.BH = bh2; t.BT = bt2;
     }
   }
+  // CTA pairs (cta_group::2): the tile doubles again, each CTA keeps its own MT*128 rows and half of the weight rows
+  t.pair = 0;
+  t.tileBH = t.BH; t.tileBT = t.BT;
+  if (w_batches <= 1 && pair_mode() != 0) {
+    int bwp, bhp, btp;
+    long long padp = 0;
+    const int rows = 256 * t.MT;
+    const long long pad_single = (t.MT == 2) ? pad2 : pad1;
+    if (choose_tile(p, rows, bwp, bhp, btp, &padp) && padp <= pad_single + pad_single / 16 &&
+        (pair_mode() == 2 || (long long)p.B * padp / rows * (Co_pad / t.BN) >= (long long)(num_sms / 2) * 2)) {
+      int cbh = bhp, cbt = btp;
+      if (btp >= 2) cbt = btp / 2; else cbh = bhp / 2;
+      if (cbh >= 1 && bwp * cbh * cbt == 128 * t.MT) {
+        t.pair = 1; t.BW = bwp; t.BH = cbh; t.BT = cbt; t.tileBH = bhp; t.tileBT = btp;
+      }
+    }
+  }
   t.B = p.B; t.To = p.To; t.Ho = p.Ho; t.Wo = p.Wo; t.Co = p.Co; t.Ti = p.Ti;
-  t.tilesW = (p.Wo + t.BW - 1) / t.BW; t.tilesH = (p.Ho + t.BH - 1) / t.BH; t.tilesT = (p.To + t.BT - 1) / t.BT;
+  t.tilesW = (p.Wo + t.BW - 1) / t.BW; t.tilesH = (p.Ho + t.tileBH - 1) / t.tileBH; t.tilesT = (p.To + t.tileBT - 1) / t.tileBT;
   t.num_n_tiles = Co_pad / t.BN;
   t.num_tiles = (long long)p.B * t.tilesT * t.tilesH * t.tilesW * t.num_n_tiles;
   t.kt = p.kt; t.kh = p.kh; t.kw = p.kw; t.Ci = p.Ci; t.num_kc = p.Ci / 64;
@@ -770,7 +884,8 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   }
   t.res_mma = (p.res_mode == 1 && p.ra == 1.0f && p.rb == 1.0f && t.BN % 64 == 0 && p.Co % 64 == 0 && p.rsW % 8 == 0 && p.rsH % 8 == 0 &&
                p.rsT % 8 == 0 && p.rsB % 8 == 0 && (((uintptr_t)p.res) & 15) == 0) ? 1 : 0;
-  const size_t stage_bytes = (size_t)t.MT * kABytes + (size_t)t.BN * 128;
+  const int bn_local = t.pair ? t.BN / 2 : t.BN;
+  const size_t stage_bytes = (size_t)t.MT * kABytes + (size_t)bn_local * 128;
   const size_t budget = 222 * 1024;
   const size_t staging = t.tma_store ? 2 * 16384 : 0;
   const size_t fixed = 1024 /*align*/ + 8 * 2 * 8 + 64 + 2 * 768 * 4 + 2 * 128 * 2 * 4 + 256;
@@ -819,7 +934,7 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
     const int nb = w_batches > 1 ? w_batches : 1;
     cuuint64_t dims[3] = {(cuuint64_t)Kpad, (cuuint64_t)Co_pad, (cuuint64_t)nb};
     cuuint64_t strides[2] = {(cuuint64_t)Kpad * 2, (cuuint64_t)(nb > 1 ? w_batch_stride : (long long)Kpad * Co_pad) * 2};
-    cuuint32_t box[3] = {64, (cuuint32_t)t.BN, 1};
+    cuuint32_t box[3] = {64, (cuuint32_t)bn_local, 1};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = enc(&maps.b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(w_nk), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -853,7 +968,7 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
     if (!encode_out(&maps.r, p.res, p.resT, p.rsW, p.rsH, p.rsT, p.rsB, t.BW, t.BH, t.BT)) return cudaErrorInvalidValue;
     cuuint64_t dims[3] = {256, 256, 1};
     cuuint64_t strides[2] = {512, 256 * 512};
-    cuuint32_t box[3] = {64, (cuuint32_t)t.BN, 1};
+    cuuint32_t box[3] = {64, (cuuint32_t)bn_local, 1};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = enc(&maps.e, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ident, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -865,12 +980,32 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
     if (e != cudaSuccess) { g_tc_err = "cudaFuncSetAttribute(smem)"; return e; }
     smem_set = true;
   }
-  const unsigned grid = (unsigned)(t.num_tiles < num_sms ? t.num_tiles : num_sms);
+  unsigned grid = (unsigned)(t.num_tiles < num_sms ? t.num_tiles : num_sms);
+  if (t.pair) {
+    const long long pairs = num_sms / 2;
+    grid = 2u * (unsigned)(t.num_tiles < pairs ? t.num_tiles : pairs);
+  }
   const double Mrows = (double)p.B * p.To * p.Ho * p.Wo;
   char det[96] = "";
-  if (prof_enabled()) snprintf(det, sizeof(det), "k%d%d%d s%d%d %d->%d @%dx%dx%d tile%dx%dx%d bn%d mt%d", p.kt, p.kh, p.kw, p.st, p.sh, p.Ci, p.Co, p.To, p.Ho, p.Wo, t.BT, t.BH, t.BW, t.BN, t.MT);
+  if (prof_enabled()) snprintf(det, sizeof(det), "k%d%d%d s%d%d %d->%d @%dx%dx%d tile%dx%dx%d bn%d mt%d%s", p.kt, p.kh, p.kw, p.st, p.sh, p.Ci, p.Co, p.To, p.Ho, p.Wo, t.tileBT, t.tileBH, t.BW, t.BN, t.MT, t.pair ? " pair" : "");
   ProfScope _ps("conv_tc", 2.0 * Mrows * p.kt * p.kh * p.kw * p.Ci * p.Co,
                 2.0 * ((double)p.B * p.Ti * p.Hi * p.Wi * p.Ci) + Mrows * p.Co * (tout == DT_F32 ? 4.0 : 2.0), s, det);
+  if (t.pair) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel, maps, t);
+    count_launch();
+    return e != cudaSuccess ? e : cudaGetLastError();
+  }
   conv_tc_kernel<<<grid, kThreads, smem, s>>>(maps, t);
   count_launch();
   return cudaGetLastError();
