@@ -302,16 +302,18 @@ __device__ __forceinline__ bool tap_time(const TcParams& p, int t0, int a, int& 
 
 // Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle, 4..11 = epilogue (two warps per TMEM
 // lane quarter, alternating 32-column chunks).
+template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rank = p.pair ? (int)cluster_ctarank() : 0;     // 0 = leader of the CTA pair
-  const long long tile0 = p.pair ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
-  const long long tile_step = p.pair ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
+  int rank = 0;
+  if constexpr (kPair) rank = (int)cluster_ctarank();     // 0 = leader of the CTA pair
+  const long long tile0 = kPair ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
+  const long long tile_step = kPair ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
   const uint32_t a_bytes = (uint32_t)p.MT * kABytes;
-  const int bn_local = p.pair ? p.BN / 2 : p.BN;           // weight rows this CTA stages
+  const int bn_local = kPair ? p.BN / 2 : p.BN;           // weight rows this CTA stages
   const uint32_t b_bytes = (uint32_t)bn_local * 128u;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   const uint32_t bar_base = smem_base + p.stages * stage_bytes + (p.tma_store ? 2u * 16384u : 0u);
@@ -339,17 +341,17 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     // pair mode: the leader's full barrier collects its own expect_tx arrival plus the peer's remote arrival (and the
     // transaction bytes of both CTAs' TMA loads); the leader's tmem_empty barrier collects both CTAs' epilogue warps
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(full_bar(s), p.pair ? 2 : 1);
+      mbar_init(full_bar(s), kPair ? 2 : 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), p.pair ? 2 * kEpiWarps : kEpiWarps);
+      mbar_init(tempty_bar(s), kPair ? 2 * kEpiWarps : kEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    if (p.pair) {
+    if constexpr (kPair) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     } else {
@@ -358,7 +360,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     }
   }
   tc_fence_before();
-  if (p.pair) cluster_sync_all(); else __syncthreads();
+  if constexpr (kPair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -372,9 +374,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       // pair mode: expect_tx (both CTAs' bytes) is posted by the leader only; the peer announces its loads with a
       // remote arrive on the leader's barrier; both wait on their OWN empty barrier (multicast commit frees both).
       auto post = [&](int stg_) {
-        if (!p.pair) mbar_expect_tx(full_bar(stg_), stage_bytes);
-        else if (rank == 0) mbar_expect_tx(full_bar(stg_), 2u * stage_bytes);
-        else mbar_arrive_remote(full_bar(stg_), 0);
+        if constexpr (!kPair) {
+          mbar_expect_tx(full_bar(stg_), stage_bytes);
+        } else {
+          if (rank == 0) mbar_expect_tx(full_bar(stg_), 2u * stage_bytes);
+          else mbar_arrive_remote(full_bar(stg_), 0);
+        }
       };
       for (long long tile = tile0; tile < p.num_tiles; tile += tile_step) {
         const TileCoord tc = decode_tile(p, tile, rank);
@@ -402,7 +407,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             post(stage);
             const uint32_t sa = smem_base + stage * stage_bytes;
-            if (p.pair) {
+            if constexpr (kPair) {
               tma_load_5d_2sm(sa, mapA, full_bar(stage), kc * 64, cw, ch, tv, tc.b);
               tma_load_3d_2sm(sa + a_bytes, &maps.b, full_bar(stage), tap * p.Ci + kc * 64, tc.n0 + rank * bn_local, p.w_batched ? tc.b : 0);
             } else {
@@ -418,7 +423,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             post(stage);
             const uint32_t sa = smem_base + stage * stage_bytes;
-            if (p.pair) {
+            if constexpr (kPair) {
               tma_load_5d_2sm(sa, &maps.r, full_bar(stage), tc.n0 + g * 64, tc.w0, tc.h0, tc.t0, tc.b);
               tma_load_3d_2sm(sa + a_bytes, &maps.e, full_bar(stage), g * 64, rank * bn_local, 0);
             } else {
@@ -433,14 +438,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0 && rank == 0) {
-      const uint32_t idesc = make_idesc(p.BN, p.pair ? 256 : 128);
+      const uint32_t idesc = make_idesc(p.BN, kPair ? 256 : 128);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t it = 0;
       auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t acc) {
-        if (p.pair) umma_f16_2sm(d, ad, bd, idesc, acc); else umma_f16(d, ad, bd, idesc, acc);
+        if constexpr (kPair) umma_f16_2sm(d, ad, bd, idesc, acc); else umma_f16(d, ad, bd, idesc, acc);
       };
-      auto commit = [&](uint32_t bar) { if (p.pair) umma_commit_2sm(bar); else umma_commit(bar); };
+      auto commit = [&](uint32_t bar) { if constexpr (kPair) umma_commit_2sm(bar); else umma_commit(bar); };
       for (long long tile = tile0; tile < p.num_tiles; tile += tile_step, ++it) {
         const TileCoord tc = decode_tile(p, tile, rank);
         const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
@@ -706,17 +711,17 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (p.pair) mbar_arrive_remote(tempty_bar(as), 0); else mbar_arrive(tempty_bar(as));
+        if constexpr (kPair) mbar_arrive_remote(tempty_bar(as), 0); else mbar_arrive(tempty_bar(as));
       }
     }
     if (p.tma_store && leader) tma_store_wait_all();
   }
 
   tc_fence_before();
-  if (p.pair) cluster_sync_all(); else __syncthreads();
+  if constexpr (kPair) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    if (p.pair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    if constexpr (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
     else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
 }
@@ -777,6 +782,28 @@ int choose_bn(int Co) {
 
 const char* conv_tc_last_error() { return g_tc_err.c_str(); }
 void conv_tc_set_pair(bool on) { g_pair_mode = on ? 1 : 0; }
+
+// diagnostics: how many 2-CTA clusters of conv_tc_kernel can be co-resident with `smem` dynamic bytes per CTA
+int conv_tc_cluster_query(int smem, char* msg, int cap) {
+  cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(148);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = -1;
+  cudaError_t e2 = cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<true>, &cfg);
+  cudaFuncAttributes fa;
+  cudaFuncGetAttributes(&fa, conv_tc_kernel<true>);
+  snprintf(msg, cap, "setattr=%s occ=%s clusters=%d regs=%d static_smem=%zu maxdyn=%d", cudaGetErrorString(e), cudaGetErrorString(e2), n,
+           fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes);
+  return n;
+}
 
 bool conv_tc_can_fuse_ln(const ConvP& p) { return p.Co % 32 == 0 && p.Co <= 256 && choose_bn(p.Co) == p.Co; }
 
@@ -976,7 +1003,8 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   }
   static bool smem_set = false;
   if (!smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) { g_tc_err = "cudaFuncSetAttribute(smem)"; return e; }
     smem_set = true;
   }
@@ -1002,11 +1030,11 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel, maps, t);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, maps, t);
     count_launch();
     return e != cudaSuccess ? e : cudaGetLastError();
   }
-  conv_tc_kernel<<<grid, kThreads, smem, s>>>(maps, t);
+  conv_tc_kernel<false><<<grid, kThreads, smem, s>>>(maps, t);
   count_launch();
   return cudaGetLastError();
 }

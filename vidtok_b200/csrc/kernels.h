@@ -73,6 +73,7 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
 cudaError_t launch_transpose_bf16(const bf16* x, bf16* y, int batch, int rows, int cols, cudaStream_t s);
 const char* conv_tc_last_error();
 void conv_tc_set_pair(bool on);
+int conv_tc_cluster_query(int smem, char* msg, int cap);
 
 // conv_stem.cu (thread-built im2col A tile + tcgen05 for the Cin=3 stem)
 bool conv_stem_supported(const ConvP& p);
