@@ -29,12 +29,14 @@ namespace vt {
 namespace {
 
 thread_local std::string g_tc_err;
-// VT_TC_PAIR=0 disables cta_group::2, VT_TC_PAIR=2 forces it whenever the geometry allows (tests on small shapes)
+// cta_group::2 (CTA pairs) is implemented and parity-green but measured SLOWER than the single-CTA kernel on B200
+// (k333 256->256 @4x128x128: 850 vs 1609 TFLOP/s, profiles/notes_r1.md), so it is opt-in:
+// VT_TC_PAIR=1 enables it for large layers, VT_TC_PAIR=2 forces it whenever the geometry allows (tests).
 int g_pair_mode = -1;
 int pair_mode() {
   if (g_pair_mode < 0) {
     const char* e = getenv("VT_TC_PAIR");
-    g_pair_mode = e ? atoi(e) : 1;
+    g_pair_mode = e ? atoi(e) : 0;
   }
   return g_pair_mode;
 }
