@@ -168,7 +168,7 @@ __device__ __forceinline__ void cluster_sync_all() {
 // arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
   asm volatile(
-      "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(bar), "r"(rank) : "memory");
 }
 // 2-CTA TMA loads: data lands in this CTA's shared memory, the transaction bytes are credited to the LEADER's barrier
@@ -340,10 +340,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     if (p.tma_store) { prefetch_tmap(&maps.o); if (p.ln_mode == 2) prefetch_tmap(&maps.o2); }
   }
   if (warp == 1 && lane == 0) {
-    // pair mode: the leader's full barrier collects its own expect_tx arrival plus the peer's remote arrival (and the
-    // transaction bytes of both CTAs' TMA loads); the leader's tmem_empty barrier collects both CTAs' epilogue warps
+    // pair mode: the leader's full barrier collects the transaction bytes of both CTAs' TMA loads; the leader's tmem_empty
+    // barrier collects both CTAs' epilogue warps
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(full_bar(s), kPair ? 2 : 1);
+      mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -379,8 +379,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         if constexpr (!kPair) {
           mbar_expect_tx(full_bar(stg_), stage_bytes);
         } else {
+          // only the leader arrives (with the bytes of BOTH CTAs); the peer's TMA loads credit the leader's barrier directly.
+          // The peer cannot run ahead of the phase: it waits on its own empty barrier, which the leader's MMA commit signals
+          // only after the previous use of the stage was consumed.
           if (rank == 0) mbar_expect_tx(full_bar(stg_), 2u * stage_bytes);
-          else mbar_arrive_remote(full_bar(stg_), 0);
         }
       };
       for (long long tile = tile0; tile < p.num_tiles; tile += tile_step) {
