@@ -29,14 +29,13 @@ namespace vt {
 namespace {
 
 thread_local std::string g_tc_err;
-// cta_group::2 (CTA pairs) is implemented and parity-green but measured SLOWER than the single-CTA kernel on B200
-// (k333 256->256 @4x128x128: 850 vs 1609 TFLOP/s, profiles/notes_r1.md), so it is opt-in:
-// VT_TC_PAIR=1 enables it for large layers, VT_TC_PAIR=2 forces it whenever the geometry allows (tests).
-int g_pair_mode = -1;
+// cta_group::2 (CTA pairs): +5 % on N = 256 layers with long K loops, neutral elsewhere (profiles/notes_r1.md).
+// VT_TC_PAIR: unset = default policy, 0 = off, 1 = every layer with enough tiles, 2 = forced whenever the geometry allows.
+int g_pair_mode = -2;   // -2 unread, -1 default policy, 0 off, 1 all large layers, 2 forced
 int pair_mode() {
-  if (g_pair_mode < 0) {
+  if (g_pair_mode == -2) {
     const char* e = getenv("VT_TC_PAIR");
-    g_pair_mode = e ? atoi(e) : 0;
+    g_pair_mode = e ? atoi(e) : -1;
   }
   return g_pair_mode;
 }
@@ -272,6 +271,7 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 
 struct TileCoord {
   int b, t0, h0, w0, n0;
+  int tt0;   // first frame of the whole (pair) tile: tap skipping must be decided identically by both CTAs of a pair
 };
 __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, long long tile, int rank) {
   TileCoord c;
@@ -283,16 +283,18 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, long long ti
   c.b = (int)(m / p.tilesT);
   // origin of THIS CTA's box inside the (pair) tile: the second CTA takes the upper half in t (if the tile spans
   // several frames) or in h
-  c.t0 = tt * p.tileBT + ((p.pair && p.tileBT != p.BT) ? rank * p.BT : 0);
+  c.tt0 = tt * p.tileBT;
+  c.t0 = c.tt0 + ((p.pair && p.tileBT != p.BT) ? rank * p.BT : 0);
   c.h0 = th * p.tileBH + ((p.pair && p.tileBT == p.BT) ? rank * p.BH : 0);
   c.w0 = tw * p.BW; c.n0 = nt * p.BN;
   return c;
 }
 // time coordinate of a tap for a tile; returns false when the whole box is causal zero padding (tap skipped)
-__device__ __forceinline__ bool tap_time(const TcParams& p, int t0, int a, int& tv, bool& from_cache) {
-  tv = (t0 + p.to_off) * p.st + a - p.pt;
+__device__ __forceinline__ bool tap_time(const TcParams& p, const TileCoord& tc, int a, int& tv, bool& from_cache) {
+  tv = (tc.t0 + p.to_off) * p.st + a - p.pt;
   from_cache = false;
-  if (tv + p.BT <= 0) {
+  const int tv_tile = (tc.tt0 + p.to_off) * p.st + a - p.pt;
+  if (tv_tile + p.tileBT <= 0) {
     if (p.t_mode == 0) return false;
     if (p.t_mode == 1) { tv = 0; return true; }
     from_cache = true;
@@ -391,7 +393,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           const int c = tap % p.kw, bb = (tap / p.kw) % p.kh, a = tap / (p.kw * p.kh);
           int tv;
           bool from_cache;
-          if (!tap_time(p, tc.t0, a, tv, from_cache)) continue;
+          if (!tap_time(p, tc, a, tv, from_cache)) continue;
           // input coordinates of the box origin.  Stride 2: tap (bb,c) reads rows 2*h + (bb-ph), i.e. row h + ((bb-ph)>>1)
           // of the parity-((bb-ph)&1) view (a tensor map over every second row/column, see launch_conv_tc).
           const int dh = bb - p.ph, dw2 = c - p.pw;
@@ -461,7 +463,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           const int a = tap / (p.kw * p.kh);
           int tv;
           bool from_cache;
-          if (!tap_time(p, tc.t0, a, tv, from_cache)) continue;
+          if (!tap_time(p, tc, a, tv, from_cache)) continue;
           for (int kc = 0; kc < p.num_kc; ++kc) {
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
@@ -867,7 +869,10 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   // CTA pairs (cta_group::2): the tile doubles again, each CTA keeps its own MT*128 rows and half of the weight rows
   t.pair = 0;
   t.tileBH = t.BH; t.tileBT = t.BT;
-  if (w_batches <= 1 && pair_mode() != 0) {
+  // default policy (VT_TC_PAIR unset): pairs only where they were measured to help -- N = 256 tiles with long K loops
+  const bool pair_wanted = pair_mode() == 2 || pair_mode() == 1 ||
+                           (pair_mode() < 0 && t.BN == 256 && p.kt * p.kh * p.kw * (p.Ci / 64) >= 36);
+  if (w_batches <= 1 && pair_wanted) {
     int bwp, bhp, btp;
     long long padp = 0;
     const int rows = 256 * t.MT;
