@@ -869,9 +869,9 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   // CTA pairs (cta_group::2): the tile doubles again, each CTA keeps its own MT*128 rows and half of the weight rows
   t.pair = 0;
   t.tileBH = t.BH; t.tileBT = t.BT;
-  // default policy (VT_TC_PAIR unset): pairs only where they were measured to help -- N = 256 tiles with long K loops
-  const bool pair_wanted = pair_mode() == 2 || pair_mode() == 1 ||
-                           (pair_mode() < 0 && t.BN == 256 && p.kt * p.kh * p.kw * (p.Ci / 64) >= 36);
+  // default policy (VT_TC_PAIR unset): pairs where they were measured to help -- the N = 256 tiles (+3..12 % in the model
+  // step); the N <= 128 level-0 layers are not weight-traffic bound and gain nothing
+  const bool pair_wanted = pair_mode() == 2 || pair_mode() == 1 || (pair_mode() < 0 && t.BN == 256);
   if (w_batches <= 1 && pair_wanted) {
     int bwp, bhp, btp;
     long long padp = 0;
