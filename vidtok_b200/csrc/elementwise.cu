@@ -588,6 +588,58 @@ __global__ void __launch_bounds__(256) transpose_bf16_kernel(const bf16* __restr
   for (int i = ty; i < 32; i += 8) yb[(long long)(c0 + i) * rows + r0 + tx] = tile[tx][i];
 }
 
+// ---- decoder head as "tap planes": conv_out (Cin -> 3, 3x3x3) is first evaluated as ONE 1x1x1 GEMM producing, for
+// every input position, the 27 x 4 per-tap partial outputs P[pos][tap*4 + co] (tcgen05, input read once instead of 27
+// times), then this kernel gathers the 27 shifted partials of each output position (causal zero padding in t, zero padding
+// in h/w, model_3dcausal.py:162-197) and writes the fp32 [B,C,T,H,W] reconstruction, dropping the first to_off frames
+// (model_3dcausal.py:883-885).
+__global__ void __launch_bounds__(256) tap_planes_gather_kernel(const bf16* __restrict__ P, const float* __restrict__ bias,
+                                                                float* __restrict__ out, int B, int Ti, int H, int W, int NP,
+                                                                int Co, int to_off) {
+  const int To = Ti - to_off;
+  const long long total = (long long)B * To * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    long long r = i / W;
+    const int h = (int)(r % H); r /= H;
+    const int to = (int)(r % To);
+    const int b = (int)(r / To);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int ti = to + to_off + a - 2;
+      if (ti < 0) continue;
+#pragma unroll
+      for (int bb = 0; bb < 3; ++bb) {
+        const int hh = h + bb - 1;
+        if ((unsigned)hh >= (unsigned)H) continue;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int ww = w + c - 1;
+          if ((unsigned)ww >= (unsigned)W) continue;
+          const uint2 v = *reinterpret_cast<const uint2*>(P + ((((long long)b * Ti + ti) * H + hh) * W + ww) * NP + ((a * 3 + bb) * 3 + c) * 4);
+          const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&v.x);
+          const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
+          acc[0] += __low2float(lo); acc[1] += __high2float(lo); acc[2] += __low2float(hi); acc[3] += __high2float(hi);
+        }
+      }
+    }
+    const long long plane = (long long)To * H * W;
+    const long long o = (long long)b * Co * plane + ((long long)to * H + h) * W + w;
+    for (int co = 0; co < Co; ++co) out[o + co * plane] = acc[co] + bias[co];
+  }
+}
+__global__ void pack_w_tap_planes_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Co, int Ci, int NP) {
+  const long long total = (long long)NP * Ci;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Ci), n = (int)(i / Ci);
+    const int tap = n / 4, co = n % 4;
+    float v = 0.f;
+    if (tap < 27 && co < Co) v = w[((long long)co * Ci + ci) * 27 + tap];
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
 inline int grid_for(long long total, int block = 256) {
   long long g = (total + block - 1) / block;
   const long long cap = 148LL * 16;
@@ -733,6 +785,22 @@ cudaError_t launch_time_interp2x(DType t, const void* x, void* y, int B, int T, 
   if (total == 0) return cudaSuccess;
   if (t == DT_F32) time_interp2x_kernel<float><<<grid_for(total), 256, 0, s>>>((const float*)x, (float*)y, B, T, hwc);
   else time_interp2x_kernel<bf16><<<grid_for(total), 256, 0, s>>>((const bf16*)x, (bf16*)y, B, T, hwc);
+  count_launch();
+  return cudaGetLastError();
+}
+cudaError_t launch_tap_planes_gather(const bf16* P, const float* bias, float* out, int B, int Ti, int H, int W, int NP, int Co,
+                                     int to_off, cudaStream_t s) {
+  const long long total = (long long)B * (Ti - to_off) * H * W;
+  if (total <= 0) return cudaSuccess;
+  ProfScope _ps("tap_planes_gather", 2.0 * 27 * Co * total, (double)B * Ti * H * W * NP * 2.0 + (double)total * Co * 4.0, s);
+  long long g = (total + 255) / 256;
+  if (g > 148LL * 32) g = 148LL * 32;
+  tap_planes_gather_kernel<<<(unsigned)g, 256, 0, s>>>(P, bias, out, B, Ti, H, W, NP, Co, to_off);
+  count_launch();
+  return cudaGetLastError();
+}
+cudaError_t launch_pack_w_tap_planes(const float* w, bf16* out, int Co, int Ci, int NP, cudaStream_t s) {
+  pack_w_tap_planes_kernel<<<grid_for((long long)NP * Ci), 256, 0, s>>>(w, out, Co, Ci, NP);
   count_launch();
   return cudaGetLastError();
 }

@@ -69,6 +69,10 @@ bool conv_tc_can_fuse_ln(const ConvP& p);
 bool conv_tc_supported(const ConvP& p, DType tout, bool planning = false);
 cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int Kpad, void* out, DType tout, cudaStream_t s,
                            int w_batches = 1, long long w_batch_stride = 0, const TcLnFusion* ln = nullptr);
+// decoder head through per-tap partial outputs (see elementwise.cu)
+cudaError_t launch_tap_planes_gather(const bf16* P, const float* bias, float* out, int B, int Ti, int H, int W, int NP, int Co,
+                                     int to_off, cudaStream_t s);
+cudaError_t launch_pack_w_tap_planes(const float* w, bf16* out, int Co, int Ci, int NP, cudaStream_t s);
 // x [batch][rows][cols] -> y [batch][cols][rows] (bf16), rows and cols multiples of 32
 cudaError_t launch_transpose_bf16(const bf16* x, bf16* y, int batch, int rows, int cols, cudaStream_t s);
 const char* conv_tc_last_error();

@@ -981,6 +981,16 @@ static void run_decoder(Exec& ex, const float* z_ext, int B, int Tz, int Hz, int
   run_stages(ex, st, stages);
   Act n = ex.take_norm(st, g.norm_out, true, false);
   ex.free_act(st.x);
+  if (ex.prec == VT_PREC_BF16 && m->head_planes.Kpad > 0 && n.W % 8 == 0) {
+    // 27 x 4 per-tap partial outputs by one GEMM over the input, then a gather-add of the shifted partials
+    Act P = ex.conv(m->head_planes, n, ConvOpt());
+    ex.free_act(n);
+    if (ex.ok() && !ex.dry)
+      ex.cuda(launch_tap_planes_gather((const bf16*)P.p, g.conv_out.bias, x_out, P.B, P.T, P.H, P.W, 128, g.conv_out.Co,
+                                       d.time_downsample_factor - 1, ex.s), "tap_planes_gather");
+    ex.free_act(P);
+    return;
+  }
   ConvOpt o; o.ext_out = x_out; o.cache_key = "decoder.conv_out";
   if (d.version == 0) o.to_off = d.time_downsample_factor - 1;  // model_3dcausal.py:883-885
   ex.conv(g.conv_out, n, o);
@@ -1077,6 +1087,7 @@ void vt_model_destroy(vt_model* m) {
   if (m->packed_kn) cudaFree(m->packed_kn);
   if (m->packed_nk) cudaFree(m->packed_nk);
   if (m->packed_stem) cudaFree(m->packed_stem);
+  if (m->packed_planes) cudaFree(m->packed_planes);
   if (m->kl_scratch) cudaFree(m->kl_scratch);
   delete m;
 }
@@ -1204,6 +1215,18 @@ int32_t vt_model_finalize(vt_model* m, void* stream) {
       if (!m->packed_stem) VT_CUDA(cudaMalloc(&m->packed_stem, (size_t)c.Co * 128 * sizeof(bf16)));
       c.w_stem = m->packed_stem;
       VT_CUDA(launch_pack_w_nk_bf16(m->pool + m->params[c.pw].offset, c.w_stem, c.Co, c.Co, c.Ci, 27, 128, s));
+    }
+  }
+  {
+    // decoder head as tap planes (v1.0 only: zero causal padding, no chunk caches)
+    const ConvW& c = m->dec.conv_out;
+    m->head_planes = ConvW();
+    if (m->desc.version == 0 && c.kt == 3 && c.kh == 3 && c.kw == 3 && c.Co <= 4 && c.Ci % 64 == 0) {
+      if (!m->packed_planes) VT_CUDA(cudaMalloc(&m->packed_planes, (size_t)128 * c.Ci * sizeof(bf16)));
+      VT_CUDA(launch_pack_w_tap_planes(m->pool + m->params[c.pw].offset, m->packed_planes, c.Co, c.Ci, 128, s));
+      ConvW& hp = m->head_planes;
+      hp.Co = 128; hp.Ci = c.Ci; hp.kt = hp.kh = hp.kw = 1; hp.Co_pad = 128; hp.Kpad = c.Ci; hp.w_nk = m->packed_planes;
+      hp.bias = nullptr;
     }
   }
   for (NormW* n : m->norms) {

@@ -97,6 +97,8 @@ struct vt_model {
   float* packed_kn = nullptr;   // all [K][Co] fp32 repacks
   vt::bf16* packed_nk = nullptr;
   vt::bf16* packed_stem = nullptr;
+  vt::bf16* packed_planes = nullptr;   // decoder conv_out as 27x4 tap planes: [128][Cin] bf16
+  vt::ConvW head_planes;               // 1x1x1 pseudo-conv Cin -> 128 using packed_planes
   bool finalized = false;
   vt::StackW enc, dec;
   std::vector<int> spatial_ds, tempo_ds, spatial_us, tempo_us;
