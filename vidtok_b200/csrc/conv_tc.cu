@@ -859,7 +859,9 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   t.MT = 1;
   long long pad1 = 0, pad2 = 0;
   if (!choose_tile(p, 128, t.BW, t.BH, t.BT, &pad1)) { g_tc_err = "no tile shape"; return cudaErrorInvalidValue; }
-  if (t.BN <= 128) {
+  static int mt_cap = -1;   // VT_TC_MT=1: experiment knob, forces one M tile per CTA
+  if (mt_cap < 0) { const char* e = getenv("VT_TC_MT"); mt_cap = e ? atoi(e) : 2; }
+  if (t.BN <= 128 && mt_cap >= 2) {
     int bw2, bh2, bt2;
     if (choose_tile(p, 256, bw2, bh2, bt2, &pad2) && pad2 <= pad1 + pad1 / 16 &&
         (long long)p.B * pad2 / 256 * (Co_pad / t.BN) >= 2LL * num_sms) {
@@ -927,6 +929,11 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   const size_t fixed = 1024 /*align*/ + 8 * 2 * 8 + 64 + 2 * 768 * 4 + 2 * 128 * 2 * 4 + 256;
   int stages = (int)((budget - fixed - staging) / stage_bytes);
   if (stages > 8) stages = 8;
+  {
+    static int cap = -1;   // VT_TC_STAGES: experiment knob (pipeline-depth sensitivity)
+    if (cap < 0) { const char* e = getenv("VT_TC_STAGES"); cap = e ? atoi(e) : 0; }
+    if (cap >= 2 && stages > cap) stages = cap;
+  }
   if (stages < 2) { g_tc_err = "not enough shared memory for 2 stages"; return cudaErrorInvalidValue; }
   t.stages = stages;
   // smem layout from the 1024-aligned base: [stages x (A | B)] [staging 2 x 16 KB] [barriers | tmem slot | bias/gamma/beta | stats]
