@@ -272,6 +272,15 @@ def run_b200_arm(args):
 
     # ---- per-kernel attribution of one step (CUDA events around every launch, on the launch stream)
     peaks = load_peaks()
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_conv_tc_r1.json")
+    if os.path.exists(tpath):  # dram__bytes_read+write per launch from the committed `ncu --set full` capture
+        try:
+            cap = json.load(open(tpath))
+            vals = [l["dram_read_bytes"] + l["dram_write_bytes"] for l in cap["launches"] if l.get("dram_read_bytes") is not None]
+            traffic = {"bytes_per_launch_avg": sum(vals) / len(vals), "launches_captured": len(vals), "source": "profiles/ncu_conv_tc_r1.json"}
+        except Exception:
+            traffic = None
     roof = None
     prof = {}
     if rank == 0:
@@ -288,7 +297,7 @@ def run_b200_arm(args):
             bound = "tensor" if d["flops"] > 0 and dom.startswith("conv") else "hbm"
             peak = peaks["tflops"] if bound == "tensor" else peaks["hbm_gbs"]
             roof = {"kernel": dom, "bound": bound, "achieved": ach, "peak": peak, "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
-                    "frac": ach / peak, "traffic": None, "launches_per_step": d["launches"],
+                    "frac": ach / peak, "traffic": traffic, "launches_per_step": d["launches"],
                     "avg_launch_ms": d["ms"] / max(d["launches"], 1), "share_of_step": d["ms"] / tot_ms,
                     "algorithmic_flops_per_step": d["flops"], "peak_source": peaks["source"],
                     "whole_path": {"achieved": FLOPS_PER_CLIP * world * B * args.steps / (ms / 1e3) / 1e12 / world, "unit": "TFLOP/s per GPU",

@@ -66,3 +66,19 @@ if os.path.exists(rep):
                     f.write(f"| {w} | {r[idx[w]]} | {units[idx[w]]} |\n")
             f.write("\n")
     print("wrote", f"profiles/ncu_conv_tc_{tag}.md")
+    # machine-readable digest for bench.py's roofline.traffic
+    import json
+    def fval(r, name):
+        try:
+            v = float(r[idx[name]].replace(",", ""))
+        except Exception:
+            return None
+        u = units[idx[name]]
+        return v * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(u, 1.0)
+    launches = []
+    for r in rows[2:]:
+        rd, wr, ms = fval(r, "dram__bytes_read.sum"), fval(r, "dram__bytes_write.sum"), fval(r, "gpu__time_duration.sum")
+        tp = fval(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed")
+        launches.append({"ms": ms, "dram_read_bytes": rd, "dram_write_bytes": wr, "tensor_pipe_active_pct": tp})
+    json.dump({"kernel": "conv_tc_kernel", "capture": f"ncu --set full -k regex:conv_tc_kernel over tools/ncu_target.py 8 1 (round {tag})", "launches": launches},
+              open(os.path.join(out_dir, f"ncu_conv_tc_{tag}.json"), "w"), indent=1)

@@ -1002,12 +1002,16 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
     if (t.ln_mode == 2 && !encode_out(&maps.o2, t.out2, p.To, p.osW, p.osH, p.osT, p.osB, t.BW, t.sBH, t.sBT)) return cudaErrorInvalidValue;
   }
   if (t.res_mma) {
-    static bf16* ident = nullptr;   // 256 x 256 identity, built once per process on this stream
-    if (!ident) {
-      cudaError_t e = cudaMalloc(&ident, 256 * 256 * sizeof(bf16));
+    static bf16* ident_dev[64] = {nullptr};   // 256 x 256 identity, built once per device on the launching stream
+    int devid = 0;
+    cudaGetDevice(&devid);
+    if (devid < 0 || devid >= 64) { g_tc_err = "device index out of range"; return cudaErrorInvalidValue; }
+    if (!ident_dev[devid]) {
+      cudaError_t e = cudaMalloc(&ident_dev[devid], 256 * 256 * sizeof(bf16));
       if (e != cudaSuccess) { g_tc_err = "cudaMalloc(identity)"; return e; }
-      fill_identity_kernel<<<256, 256, 0, s>>>(ident);
+      fill_identity_kernel<<<256, 256, 0, s>>>(ident_dev[devid]);
     }
+    bf16* ident = ident_dev[devid];
     if (!encode_out(&maps.r, p.res, p.resT, p.rsW, p.rsH, p.rsT, p.rsB, t.BW, t.BH, t.BT)) return cudaErrorInvalidValue;
     cuuint64_t dims[3] = {256, 256, 1};
     cuuint64_t strides[2] = {512, 256 * 512};
