@@ -82,7 +82,7 @@ struct TcParams {
   // the B (weight) rows, the leader issues M=256 MMAs that read both halves -> weight bytes per FLOP are halved again
   int pair;
   int tileBH, tileBT;        // box of the whole (pair) tile; BH/BT above are the per-CTA box
-  int split;                 // experiment (VT_TC_SPLIT=1): issue one TMA load per M tile and two per weight tile
+
 };
 
 struct TcMaps {
@@ -417,14 +417,6 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             if constexpr (kPair) {
               tma_load_5d_2sm(sa, mapA, full_bar(stage), kc * 64, cw, ch, tv, tc.b);
               tma_load_3d_2sm(sa + a_bytes, &maps.b, full_bar(stage), tap * p.Ci + kc * 64, tc.n0 + rank * bn_local, p.w_batched ? tc.b : 0);
-            } else if (p.split) {
-              // smaller boxes = more independent TMA operations in flight (the per-M-tile box is the store box sBH x sBT)
-              for (int mt = 0; mt < p.MT; ++mt)
-                tma_load_5d(sa + mt * kABytes, mapA, full_bar(stage), kc * 64, cw,
-                            ch + ((p.MT == 2 && p.BT == p.sBT) ? mt * p.sBH : 0), tv + ((p.MT == 2 && p.BT != p.sBT) ? mt * p.sBT : 0), tc.b);
-              const int hb = p.BN / 2;
-              tma_load_3d(sa + a_bytes, &maps.b, full_bar(stage), tap * p.Ci + kc * 64, tc.n0, p.w_batched ? tc.b : 0);
-              tma_load_3d(sa + a_bytes + hb * 128, &maps.b, full_bar(stage), tap * p.Ci + kc * 64, tc.n0 + hb, p.w_batched ? tc.b : 0);
             } else {
               tma_load_5d(sa, mapA, full_bar(stage), kc * 64, cw, ch, tv, tc.b);
               tma_load_3d(sa + a_bytes, &maps.b, full_bar(stage), tap * p.Ci + kc * 64, tc.n0, p.w_batched ? tc.b : 0);
@@ -931,12 +923,6 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   }
   t.res_mma = (p.res_mode == 1 && p.ra == 1.0f && p.rb == 1.0f && t.BN % 64 == 0 && p.Co % 64 == 0 && p.rsW % 8 == 0 && p.rsH % 8 == 0 &&
                p.rsT % 8 == 0 && p.rsB % 8 == 0 && (((uintptr_t)p.res) & 15) == 0) ? 1 : 0;
-  {
-    static int split = -1;
-    if (split < 0) { const char* e = getenv("VT_TC_SPLIT"); split = e ? atoi(e) : 0; }
-    // (stride-2 convs use parity views whose box arithmetic differs; keep them on the single-box path)
-    t.split = (split && !t.pair && p.sh == 1 && p.t_mode != 2 && t.BN % 32 == 0 && t.BW * t.sBH * t.sBT == 128) ? 1 : 0;
-  }
   const int bn_local = t.pair ? t.BN / 2 : t.BN;
   const size_t stage_bytes = (size_t)t.MT * kABytes + (size_t)bn_local * 128;
   const size_t budget = 222 * 1024;
@@ -963,7 +949,7 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   auto encode_act = [&](CUtensorMap* m, const bf16* base, int Wn, int Hn, long long sw_, long long sh_, int Tn, long long st_, long long bs) -> bool {
     cuuint64_t dims[5] = {(cuuint64_t)p.Ci, (cuuint64_t)Wn, (cuuint64_t)Hn, (cuuint64_t)Tn, (cuuint64_t)p.B};
     cuuint64_t strides[4] = {(cuuint64_t)sw_ * 2, (cuuint64_t)sh_ * 2, (cuuint64_t)st_ * 2, (cuuint64_t)bs * 2};
-    cuuint32_t box[5] = {64, (cuuint32_t)t.BW, (cuuint32_t)(t.split ? t.sBH : t.BH), (cuuint32_t)(t.split ? t.sBT : t.BT), 1};
+    cuuint32_t box[5] = {64, (cuuint32_t)t.BW, (cuuint32_t)t.BH, (cuuint32_t)t.BT, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<bf16*>(base), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -992,7 +978,7 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
     const int nb = w_batches > 1 ? w_batches : 1;
     cuuint64_t dims[3] = {(cuuint64_t)Kpad, (cuuint64_t)Co_pad, (cuuint64_t)nb};
     cuuint64_t strides[2] = {(cuuint64_t)Kpad * 2, (cuuint64_t)(nb > 1 ? w_batch_stride : (long long)Kpad * Co_pad) * 2};
-    cuuint32_t box[3] = {64, (cuuint32_t)(t.split ? bn_local / 2 : bn_local), 1};
+    cuuint32_t box[3] = {64, (cuuint32_t)bn_local, 1};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = enc(&maps.b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(w_nk), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -495,10 +495,12 @@ __global__ void pack_w_nk_bf16_kernel(const float* __restrict__ w, bf16* __restr
 template <typename T>
 __global__ void __launch_bounds__(256) time_interp2x_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int Tn,
                                                             long long hwc) {
-  const long long total = (long long)B * 2 * Tn * hwc;
+  // 4 elements per thread (hwc is a multiple of 4: channels-last with C % 4 == 0)
+  const long long q = hwc / 4;
+  const long long total = (long long)B * 2 * Tn * q;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long e = i % hwc;
-    const long long r = i / hwc;
+    const long long e = (i % q) * 4;
+    const long long r = i / q;
     const int j = (int)(r % (2 * Tn));
     const long long b = r / (2 * Tn);
     float src = 0.5f * ((float)j + 0.5f) - 0.5f;
@@ -506,9 +508,12 @@ __global__ void __launch_bounds__(256) time_interp2x_kernel(const T* __restrict_
     const int i0 = (int)src;
     const int i1 = i0 + ((i0 < Tn - 1) ? 1 : 0);
     const float l1 = src - (float)i0, l0 = 1.0f - l1;
-    const float a = to_f(x[(b * Tn + i0) * hwc + e]);
-    const float c = to_f(x[(b * Tn + i1) * hwc + e]);
-    y[i] = from_f<T>(__fadd_rn(__fmul_rn(l0, a), __fmul_rn(l1, c)));
+    float a[4], c[4], o[4];
+    load4(x + (b * Tn + i0) * hwc + e, a);
+    load4(x + (b * Tn + i1) * hwc + e, c);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = __fadd_rn(__fmul_rn(l0, a[k]), __fmul_rn(l1, c[k]));
+    store4(y + (b * 2 * Tn + j) * hwc + e, o);
   }
 }
 template <typename T>
@@ -781,7 +786,8 @@ cudaError_t launch_pack_w_nk_bf16(const float* w, bf16* out, int Co, int Co_pad,
 }
 cudaError_t launch_time_interp2x(DType t, const void* x, void* y, int B, int T, long long hwc, cudaStream_t s) {
   ProfScope _ps("time_interp2x", 0.0, 3.0 * B * T * hwc * (double)dtype_size(t), s);
-  const long long total = (long long)B * 2 * T * hwc;
+  if (hwc % 4 != 0) return cudaErrorInvalidValue;
+  const long long total = (long long)B * 2 * T * (hwc / 4);
   if (total == 0) return cudaSuccess;
   if (t == DT_F32) time_interp2x_kernel<float><<<grid_for(total), 256, 0, s>>>((const float*)x, (float*)y, B, T, hwc);
   else time_interp2x_kernel<bf16><<<grid_for(total), 256, 0, s>>>((const bf16*)x, (bf16*)y, B, T, hwc);

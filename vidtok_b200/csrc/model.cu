@@ -272,7 +272,10 @@ struct vt_chunk_state {
   ~vt_chunk_state() {
     for (auto& kv : caches)
       for (int i = 0; i < 2; ++i)
-        if (kv.second.buf[i]) cudaFree(kv.second.buf[i]);
+        if (kv.second.buf[i]) {
+          if (m && persist) m->cache_pool.insert({kv.second.bytes, kv.second.buf[i]});
+          else cudaFree(kv.second.buf[i]);
+        }
   }
 };
 
@@ -384,9 +387,15 @@ struct Exec {
     if (c.bytes != bytes) {
       if (dry) { c.bytes = bytes; c.T = T; return &c; }
       for (int i = 0; i < 2; ++i) {
-        if (c.buf[i]) cudaFree(c.buf[i]);
+        if (c.buf[i]) m->cache_pool.insert({c.bytes, c.buf[i]});
         c.buf[i] = nullptr;
-        if (!cuda(cudaMalloc(&c.buf[i], bytes), "cudaMalloc(causal cache)")) return nullptr;
+        auto it = m->cache_pool.find(bytes);
+        if (it != m->cache_pool.end()) {
+          c.buf[i] = it->second;
+          m->cache_pool.erase(it);
+        } else if (!cuda(cudaMalloc(&c.buf[i], bytes), "cudaMalloc(causal cache)")) {
+          return nullptr;
+        }
       }
       c.bytes = bytes; c.T = T; c.valid = false; c.cur = 0;
     }
@@ -1089,6 +1098,7 @@ void vt_model_destroy(vt_model* m) {
   if (m->packed_stem) cudaFree(m->packed_stem);
   if (m->packed_planes) cudaFree(m->packed_planes);
   if (m->kl_scratch) cudaFree(m->kl_scratch);
+  for (auto& kv : m->cache_pool) cudaFree(kv.second);
   delete m;
 }
 

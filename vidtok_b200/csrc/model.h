@@ -105,4 +105,7 @@ struct vt_model {
   double* kl_scratch = nullptr;
   std::vector<vt::ConvW*> convs;   // every conv of both stacks (for packing)
   std::vector<vt::NormW*> norms;
+  // device buffers of finished chunk states, reused by the next video (cudaMalloc/cudaFree per cache per video would
+  // dominate the tiled path: ~100 caches per direction)
+  std::multimap<size_t, void*> cache_pool;
 };
