@@ -19,6 +19,7 @@ struct StemParams {
   int B, Ci, T, H, W;
   int To;          // output frames = t_rep + T
   int t_rep, t_mode;
+  const float* cache;   // t_mode 2: [B,Ci,2,H,W] fp32, the last two padded input frames of the previous chunk
   int Co;
   const float* bias;
   bf16* out;       // [B,To,H,W,Co]
@@ -145,7 +146,10 @@ __global__ void __launch_bounds__(256, 1) conv_stem_kernel(const StemParams p, c
       int tv = t + a - 2;  // virtual time axis: [t_rep copies of frame 0][T frames]
       float v = 0.f;
       bool ok = hv >= 0 && hv < p.H && wv >= 0 && wv < p.W;
-      if (tv < 0) {
+      if (tv < 0 && p.t_mode == 2) {
+        if (ok) v = p.cache[((((long long)b * p.Ci + ci) * 2 + (2 + tv)) * p.H + hv) * p.W + wv];
+        ok = false;
+      } else if (tv < 0) {
         if (p.t_mode == 0) ok = false;
         tv = 0;
       }
@@ -253,11 +257,38 @@ __global__ void __launch_bounds__(256, 1) conv_stem_kernel(const StemParams p, c
 
 }  // namespace
 
+namespace {
+// new_cache[b][ci][j] = padded_input[L-2+j], padded_input = [t_rep copies of x[:,:,0]][x], L = t_rep + T >= 2
+__global__ void __launch_bounds__(256) stem_cache_update_kernel(const float* __restrict__ x, float* __restrict__ cache, int B, int Ci,
+                                                                int T, int t_rep, long long hw) {
+  const long long total = (long long)B * Ci * 2 * hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i % hw;
+    long long r = i / hw;
+    const int j = (int)(r % 2);
+    r /= 2;  // r = b*Ci + ci
+    int idx = t_rep + T - 2 + j - t_rep;
+    idx = idx < 0 ? 0 : idx;
+    cache[i] = x[(r * T + idx) * hw + e];
+  }
+}
+}  // namespace
+
+cudaError_t launch_stem_cache_update(const float* x, float* cache, int B, int Ci, int T, int t_rep, int H, int W, cudaStream_t s) {
+  if (t_rep + T < 2) return cudaErrorInvalidValue;
+  const long long total = (long long)B * Ci * 2 * H * W;
+  long long g = (total + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  stem_cache_update_kernel<<<(unsigned)g, 256, 0, s>>>(x, cache, B, Ci, T, t_rep, (long long)H * W);
+  count_launch();
+  return cudaGetLastError();
+}
+
 bool conv_stem_supported(const ConvP& p) {
   if (p.kt != 3 || p.kh != 3 || p.kw != 3 || p.st != 1 || p.sh != 1 || p.sw != 1) return false;
   if (p.ut != 1 || p.uh != 1 || p.uw != 1 || p.to_off != 0 || p.res_mode != 0) return false;
   if (p.Ci * 27 > 128 || p.Co % 64 != 0 || p.Co > 256) return false;
-  if (p.t_mode == 2) return false;
+  if (p.t_mode == 2 && (!p.cache || p.cacheT != 2)) return false;
   if (p.pt != 2 || p.ph != 1 || p.pw != 1) return false;
   if (p.Ho != p.Hi || p.Wo != p.Wi || p.To != p.t_rep + p.Ti) return false;
   // external NCDHW fp32 input, dense channels-last bf16 output
@@ -269,6 +300,7 @@ bool conv_stem_supported(const ConvP& p) {
 // wpk: [Co][128] bf16, k = tap*Ci + ci, zero padded (launch_pack_w_nk_bf16 with Kpad = 128)
 cudaError_t launch_conv_stem(const ConvP& p, const float* x, const bf16* wpk, bf16* out, cudaStream_t s) {
   StemParams t;
+  t.cache = (const float*)p.cache;
   t.x = x; t.B = p.B; t.Ci = p.Ci; t.T = p.Ti; t.H = p.Hi; t.W = p.Wi; t.To = p.To; t.t_rep = p.t_rep; t.t_mode = p.t_mode;
   t.Co = p.Co; t.bias = p.bias; t.out = out;
   t.tilesW = (p.Wi + BW - 1) / BW; t.tilesH = (p.Hi + BH - 1) / BH;

@@ -82,5 +82,6 @@ int conv_tc_cluster_query(int smem, char* msg, int cap);
 // conv_stem.cu (thread-built im2col A tile + tcgen05 for the Cin=3 stem)
 bool conv_stem_supported(const ConvP& p);
 cudaError_t launch_conv_stem(const ConvP& p, const float* x, const bf16* wpk, bf16* out, cudaStream_t s);
+cudaError_t launch_stem_cache_update(const float* x, float* cache, int B, int Ci, int T, int t_rep, int H, int W, cudaStream_t s);
 
 }  // namespace vt

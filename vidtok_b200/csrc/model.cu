@@ -917,7 +917,33 @@ static void run_encoder(Exec& ex, const float* x_ext, int B, int T, int H, int W
   Act xin;
   xin.p = (void*)x_ext; xin.B = B; xin.T = T; xin.H = H; xin.W = W; xin.C = d.in_channels;
   Exec::Stream st;
-  if (d.version == 1 && ex.ck && ex.ck->persist) {
+  if (d.version == 1 && ex.ck && ex.ck->persist && ex.prec == VT_PREC_BF16 && e.conv_in.w_stem && T + t_rep >= 2 &&
+      e.conv_in.Ci * 27 <= 128) {
+    // chunked v1.1 on the stem kernel: the causal cache (last two padded input frames, model_3dcausal_v1_1.py:230-233)
+    // is kept in the caller's layout (fp32 [B,C,2,H,W]) and read by the kernel's patch loader
+    CacheBuf* cb = ex.get_cache("encoder.conv_in#stem", 2, (size_t)B * d.in_channels * 2 * H * W * sizeof(float));
+    st.x = ex.new_act(B, T + t_rep, H, W, e.conv_in.Co);
+    if (ex.ok() && !ex.dry) {
+      if (!ex.ck->first && !cb->valid) { ex.rc = fail(VT_ERR_NOT_READY, "stem cache empty on a non-first chunk"); return; }
+      ConvP p;
+      memset(&p, 0, sizeof(p));
+      p.B = B; p.Ti = T; p.Hi = H; p.Wi = W; p.Ci = d.in_channels;
+      p.isW = 1; p.isH = W; p.isT = (long long)H * W; p.isC = p.isT * T; p.isB = p.isC * p.Ci;
+      p.To = T + t_rep; p.Ho = H; p.Wo = W; p.Co = e.conv_in.Co;
+      p.osC = 1; p.osW = p.Co; p.osH = (long long)W * p.Co; p.osT = p.osH * H; p.osB = p.osT * p.To;
+      p.kt = p.kh = p.kw = 3; p.st = p.sh = p.sw = 1; p.ut = p.uh = p.uw = 1;
+      p.pt = 2; p.ph = 1; p.pw = 1; p.t_rep = t_rep;
+      p.t_mode = ex.ck->first ? 1 : 2;
+      p.cache = cb->buf[cb->cur]; p.cacheT = 2;
+      p.bias = e.conv_in.bias;
+      if (!conv_stem_supported(p)) { ex.rc = fail(VT_ERR_INVALID, "stem kernel rejected the chunk geometry"); return; }
+      ex.cuda(launch_conv_stem(p, x_ext, e.conv_in.w_stem, (bf16*)st.x.p, ex.s), "conv_stem");
+      const int nxt = cb->cur ^ 1;
+      ex.cuda(launch_stem_cache_update(x_ext, (float*)cb->buf[nxt], B, d.in_channels, T, t_rep, H, W, ex.s), "stem cache");
+      cb->cur = nxt;
+      cb->valid = true;
+    }
+  } else if (d.version == 1 && ex.ck && ex.ck->persist) {
     // chunked v1.1: the causal cache of conv_in holds *padded input* frames; materialise the replicate-padded chunk
     // channels-last so the cache update sees the same tensor the reference caches (model_3dcausal_v1_1.py:230-233).
     Act xp = ex.new_act(B, T + t_rep, H, W, d.in_channels);
