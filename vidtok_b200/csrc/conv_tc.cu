@@ -29,8 +29,8 @@ namespace vt {
 namespace {
 
 thread_local std::string g_tc_err;
-// cta_group::2 (CTA pairs): +5 % on N = 256 layers with long K loops, neutral elsewhere (profiles/notes_r1.md).
-// VT_TC_PAIR: unset = default policy, 0 = off, 1 = every layer with enough tiles, 2 = forced whenever the geometry allows.
+// cta_group::2 (CTA pairs) halve the weight bytes each CTA stages and reads per FLOP (profiles/notes_r1.md).
+// VT_TC_PAIR: unset / 1 = every layer with enough tiles, 0 = off, 2 = forced whenever the geometry allows, 3 = N = 256 tiles only.
 int g_pair_mode = -2;   // -2 unread, -1 default policy, 0 off, 1 all large layers, 2 forced
 int pair_mode() {
   if (g_pair_mode == -2) {
@@ -82,6 +82,13 @@ struct TcParams {
   // the B (weight) rows, the leader issues M=256 MMAs that read both halves -> weight bytes per FLOP are halved again
   int pair;
   int tileBH, tileBT;        // box of the whole (pair) tile; BH/BT above are the per-CTA box
+  // halo mode (stride-1 spatial kernels): ONE TMA box per (time tap, 64-channel chunk) brings the input window of the
+  // whole CTA tile plus its spatial halo ({64, hP, BH + kh - 1} rows of 128 B) into shared memory; the kh*kw spatial taps
+  // are then UMMA descriptors that start (bb * hP + c) rows into that window, so the activation bytes pulled from L2
+  // drop by ~kh*kw.  The CTA tile is 16 rows x (8 * MT) columns: an 8-row UMMA core group = 8 consecutive columns,
+  // group stride (SBO) = hP rows, and hP % 8 == 0 keeps the swizzle phase of every group equal (= descriptor base offset).
+  int halo, hP, a_stages;
+  uint32_t halo_bytes;
 
 };
 
@@ -190,14 +197,18 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
-__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+__device__ __forceinline__ void umma_f16_2sm_lohi(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                                  uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t"
       "}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accum)
       : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
@@ -208,15 +219,31 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+__device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                              uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
       "}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accum)
       : "memory");
+}
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -243,12 +270,11 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
-// start>>4 [0,14) | LBO>>4 = 1 [16,30) | SBO>>4 = 64 (8 rows x 128 B) [32,46) | version = 1 [46,48) | layout = 2 [61,64)
-__device__ __forceinline__ uint64_t make_sdesc(uint32_t addr) {
-  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)64 << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)2 << 61);
-}
+// Shared-memory matrix descriptors (cute::UMMA::SmemDescriptor), K-major SWIZZLE_128B, are built as two 32-bit words:
+//   lo = start >> 4 [0,14) | LBO >> 4 = 1 [16,30)        hi = SBO >> 4 [0,14) | version = 1 [14,16) | layout = 2 [29,32)
+// SBO = byte distance between 8-row groups: 1024 for a dense tile, hP * 128 for a tile inside a halo window.  The 128-byte
+// swizzle is a function of the absolute shared-memory address, so a tile may start at any 128-byte row of a window that
+// TMA wrote with the same swizzle (descriptor base offset stays 0; verified on B200, tests/test_gpu_ops.py tc_halo_*).
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
 __device__ __forceinline__ uint32_t make_idesc(int N, int M = 128) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -320,14 +346,18 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   const uint32_t a_bytes = (uint32_t)p.MT * kABytes;
   const int bn_local = kPair ? p.BN / 2 : p.BN;           // weight rows this CTA stages
   const uint32_t b_bytes = (uint32_t)bn_local * 128u;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
-  const uint32_t bar_base = smem_base + p.stages * stage_bytes + (p.tma_store ? 2u * 16384u : 0u);
-  // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2]; then tmem ptr; then bias[2][256]
+  const uint32_t stage_bytes = p.halo ? b_bytes : a_bytes + b_bytes;   // halo mode: the stage ring holds B tiles only
+  const uint32_t ring_base = smem_base + (p.halo ? (uint32_t)p.a_stages * p.halo_bytes : 0u);
+  const uint32_t bar_base = ring_base + p.stages * stage_bytes + (p.tma_store ? 2u * 16384u : 0u);
+  // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2], fullA[a_stages], emptyA[a_stages];
+  // then tmem ptr; then bias[2][256]
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * p.stages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * p.stages + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 4);
+  auto fullA_bar = [&](int s) { return bar_base + 8u * (2 * p.stages + 4 + s); };
+  auto emptyA_bar = [&](int s) { return bar_base + 8u * (2 * p.stages + 4 + p.a_stages + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 4 + 2 * p.a_stages);
   const uint32_t bias_base = tmem_slot + 16u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
@@ -353,6 +383,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), kPair ? 2 * kEpiWarps : kEpiWarps);
     }
+    for (int s = 0; s < p.a_stages; ++s) {
+      mbar_init(fullA_bar(s), 1);
+      mbar_init(emptyA_bar(s), 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -369,135 +403,204 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int ntaps = p.kt * p.kh * p.kw;
+  // Producer and MMA issuer run with the WHOLE warp converged and elect one lane only around the asynchronous
+  // instructions: all addresses / coordinates are then warp-uniform values the compiler keeps on the uniform datapath,
+  // so a K step costs a few dozen issue slots.  (A single-lane `if (lane == 0)` loop makes every UTCHMMA / UTMALDG a
+  // vote + broadcast sequence; the issuing thread, not the tensor pipe, was the limit: profiles/notes_r1.md.)
+  const int nsp = p.kh * p.kw;
+  const int num_kc = p.num_kc, nstages = p.stages;
+  const bool halo = p.halo != 0;
+  const int res_steps = p.res_mma ? p.BN / 64 : 0;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      // pair mode: expect_tx (both CTAs' bytes) is posted by the leader only; the peer announces its loads with a
-      // remote arrive on the leader's barrier; both wait on their OWN empty barrier (multicast commit frees both).
-      auto post = [&](int stg_) {
-        if constexpr (!kPair) {
-          mbar_expect_tx(full_bar(stg_), stage_bytes);
+    const bool el = elect_one();
+    int stage = 0, sA = 0;
+    uint32_t phase = 0, phA = 0;
+    // B (or A|B) stage: wait for the slot, post the expected bytes (pair mode: the leader posts both CTAs' bytes, the
+    // peer's loads credit the leader's barrier directly; the peer cannot run ahead of the phase because it waits on its
+    // own empty barrier, which the leader's multicast commit signals)
+    auto acquire = [&]() {
+      mbar_wait(empty_bar(stage), phase ^ 1u);
+      if (el) {
+        if constexpr (!kPair) mbar_expect_tx(full_bar(stage), stage_bytes);
+        else if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * stage_bytes);
+      }
+    };
+    auto advance = [&]() { if (++stage == nstages) { stage = 0; phase ^= 1u; } };
+    auto load_b = [&](uint32_t dst, const CUtensorMap* m, int c0, int c1, int c2) {
+      if constexpr (kPair) tma_load_3d_2sm(dst, m, full_bar(stage), c0, c1, c2);
+      else tma_load_3d(dst, m, full_bar(stage), c0, c1, c2);
+    };
+    auto load_a = [&](uint32_t dst, uint32_t bar, const CUtensorMap* m, int c0, int cw, int ch, int ct, int cb) {
+      if constexpr (kPair) tma_load_5d_2sm(dst, m, bar, c0, cw, ch, ct, cb);
+      else tma_load_5d(dst, m, bar, c0, cw, ch, ct, cb);
+    };
+    // halo window of one (time tap, 64-channel chunk)
+    auto load_window = [&](const CUtensorMap* m, int c0, int cw, int ch, int ct, int cb) {
+      mbar_wait(emptyA_bar(sA), phA ^ 1u);
+      if (el) {
+        if constexpr (!kPair) mbar_expect_tx(fullA_bar(sA), p.halo_bytes);
+        else if (rank == 0) mbar_expect_tx(fullA_bar(sA), 2u * p.halo_bytes);
+        load_a(smem_base + (uint32_t)sA * p.halo_bytes, fullA_bar(sA), m, c0, cw, ch, ct, cb);
+      }
+      if (++sA == p.a_stages) { sA = 0; phA ^= 1u; }
+    };
+    const int n_off = kPair ? rank * bn_local : 0;
+    for (long long tile = tile0; tile < p.num_tiles; tile += tile_step) {
+      const TileCoord tc = decode_tile(p, tile, rank);
+      const int wb = p.w_batched ? tc.b : 0;
+      for (int a = 0; a < p.kt; ++a) {
+        int tv;
+        bool from_cache;
+        if (!tap_time(p, tc, a, tv, from_cache)) continue;
+        if (halo) {
+          const CUtensorMap* mapA = from_cache ? &maps.c : &maps.a[0];
+          for (int kc = 0; kc < num_kc; ++kc) {
+            load_window(mapA, kc * 64, tc.w0 - p.pw, tc.h0 - p.ph, tv, tc.b);
+            int kcol = a * nsp * p.Ci + kc * 64;
+            for (int sp = 0; sp < nsp; ++sp, kcol += p.Ci) {
+              acquire();
+              if (el) load_b(ring_base + stage * stage_bytes, &maps.b, kcol, tc.n0 + n_off, wb);
+              advance();
+            }
+          }
         } else {
-          // only the leader arrives (with the bytes of BOTH CTAs); the peer's TMA loads credit the leader's barrier directly.
-          // The peer cannot run ahead of the phase: it waits on its own empty barrier, which the leader's MMA commit signals
-          // only after the previous use of the stage was consumed.
-          if (rank == 0) mbar_expect_tx(full_bar(stg_), 2u * stage_bytes);
-        }
-      };
-      for (long long tile = tile0; tile < p.num_tiles; tile += tile_step) {
-        const TileCoord tc = decode_tile(p, tile, rank);
-        for (int tap = 0; tap < ntaps; ++tap) {
-          const int c = tap % p.kw, bb = (tap / p.kw) % p.kh, a = tap / (p.kw * p.kh);
-          int tv;
-          bool from_cache;
-          if (!tap_time(p, tc, a, tv, from_cache)) continue;
-          // input coordinates of the box origin.  Stride 2: tap (bb,c) reads rows 2*h + (bb-ph), i.e. row h + ((bb-ph)>>1)
-          // of the parity-((bb-ph)&1) view (a tensor map over every second row/column, see launch_conv_tc).
-          const int dh = bb - p.ph, dw2 = c - p.pw;
-          int ch, cw;
-          const CUtensorMap* mapA;
-          if (p.sp == 2) {
-            mapA = &maps.a[(dh & 1) * 2 + (dw2 & 1)];
-            ch = tc.h0 + (dh >> 1);
-            cw = tc.w0 + (dw2 >> 1);
-          } else {
-            mapA = &maps.a[0];
-            ch = tc.h0 + dh;
-            cw = tc.w0 + dw2;
-          }
-          if (from_cache) mapA = &maps.c;
-          for (int kc = 0; kc < p.num_kc; ++kc) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            post(stage);
-            const uint32_t sa = smem_base + stage * stage_bytes;
-            if constexpr (kPair) {
-              tma_load_5d_2sm(sa, mapA, full_bar(stage), kc * 64, cw, ch, tv, tc.b);
-              tma_load_3d_2sm(sa + a_bytes, &maps.b, full_bar(stage), tap * p.Ci + kc * 64, tc.n0 + rank * bn_local, p.w_batched ? tc.b : 0);
-            } else {
-              tma_load_5d(sa, mapA, full_bar(stage), kc * 64, cw, ch, tv, tc.b);
-              tma_load_3d(sa + a_bytes, &maps.b, full_bar(stage), tap * p.Ci + kc * 64, tc.n0, p.w_batched ? tc.b : 0);
+          int kcol = a * nsp * p.Ci;
+          for (int bb = 0; bb < p.kh; ++bb) {
+            for (int c = 0; c < p.kw; ++c, kcol += p.Ci) {
+              // input coordinates of the box origin.  Stride 2: tap (bb,c) reads rows 2*h + (bb-ph), i.e. row
+              // h + ((bb-ph)>>1) of the parity-((bb-ph)&1) view (a tensor map over every second row/column)
+              const int dh = bb - p.ph, dw2 = c - p.pw;
+              int ch, cw;
+              const CUtensorMap* mapA;
+              if (p.sp == 2) {
+                mapA = &maps.a[(dh & 1) * 2 + (dw2 & 1)];
+                ch = tc.h0 + (dh >> 1);
+                cw = tc.w0 + (dw2 >> 1);
+              } else {
+                mapA = &maps.a[0];
+                ch = tc.h0 + dh;
+                cw = tc.w0 + dw2;
+              }
+              if (from_cache) mapA = &maps.c;
+              for (int kc = 0; kc < num_kc; ++kc) {
+                acquire();
+                if (el) {
+                  const uint32_t sa = smem_base + stage * stage_bytes;
+                  load_a(sa, full_bar(stage), mapA, kc * 64, cw, ch, tv, tc.b);
+                  load_b(sa + a_bytes, &maps.b, kcol + kc * 64, tc.n0 + n_off, wb);
+                }
+                advance();
+              }
             }
-            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
         }
-        if (p.res_mma) {
-          // out += I * residual : A = residual tile of this output box, channels [n0 + 64g, +64); B = identity columns
-          for (int g = 0; g < p.BN / 64; ++g) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            post(stage);
+      }
+      // out += I * residual : A = residual tile of this output box, channels [n0 + 64g, +64); B = identity columns
+      for (int g = 0; g < res_steps; ++g) {
+        if (halo) {
+          load_window(&maps.r, tc.n0 + g * 64, tc.w0 - p.pw, tc.h0 - p.ph, tc.t0, tc.b);
+          acquire();
+          if (el) load_b(ring_base + stage * stage_bytes, &maps.e, g * 64, n_off, 0);
+        } else {
+          acquire();
+          if (el) {
             const uint32_t sa = smem_base + stage * stage_bytes;
-            if constexpr (kPair) {
-              tma_load_5d_2sm(sa, &maps.r, full_bar(stage), tc.n0 + g * 64, tc.w0, tc.h0, tc.t0, tc.b);
-              tma_load_3d_2sm(sa + a_bytes, &maps.e, full_bar(stage), g * 64, rank * bn_local, 0);
-            } else {
-              tma_load_5d(sa, &maps.r, full_bar(stage), tc.n0 + g * 64, tc.w0, tc.h0, tc.t0, tc.b);
-              tma_load_3d(sa + a_bytes, &maps.e, full_bar(stage), g * 64, 0, 0);
-            }
-            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            load_a(sa, full_bar(stage), &maps.r, tc.n0 + g * 64, tc.w0, tc.h0, tc.t0, tc.b);
+            load_b(sa + a_bytes, &maps.e, g * 64, n_off, 0);
           }
         }
+        advance();
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
+      const bool el = elect_one();
       const uint32_t idesc = make_idesc(p.BN, kPair ? 256 : 128);
-      int stage = 0;
-      uint32_t phase = 0;
+      const int MT = p.MT;
+      const uint32_t BNu = (uint32_t)p.BN;
+      // descriptor words: lo = start >> 4 | LBO(1) << 16 ; hi = SBO >> 4 | version 1 << 14 | SWIZZLE_128B (2) << 29
+      const uint32_t hi_b = 64u | (1u << 14) | (2u << 29);
+      const uint32_t hi_a = halo ? (((uint32_t)p.hP * 8u) | (1u << 14) | (2u << 29)) : hi_b;
+      const uint32_t mt_step = halo ? 64u : (uint32_t)(kABytes >> 4);   // next M tile: 8 window rows / 16 KB
+      const uint32_t b_addr0 = halo ? ring_base : smem_base + a_bytes;
+      int stage = 0, sA = 0;
+      uint32_t phase = 0, phA = 0;
       uint32_t it = 0;
-      auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t acc) {
-        if constexpr (kPair) umma_f16_2sm(d, ad, bd, idesc, acc); else umma_f16(d, ad, bd, idesc, acc);
+      uint32_t tmem_d = 0;
+      auto mma = [&](uint32_t d, uint32_t alo, uint32_t blo, uint32_t acc) {
+        if constexpr (kPair) umma_f16_2sm_lohi(d, alo, hi_a, blo, hi_b, idesc, acc);
+        else umma_f16_lohi(d, alo, hi_a, blo, hi_b, idesc, acc);
       };
-      auto commit = [&](uint32_t bar) { if constexpr (kPair) umma_commit_2sm(bar); else umma_commit(bar); };
+      // one K step (64 channels): A tile(s) at descriptor word a_lo against the B tile of the current stage
+      auto kstep = [&](uint32_t a_lo, uint32_t acc) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        if (el) {
+          const uint32_t b_lo = (((b_addr0 + stage * stage_bytes) & 0x3FFFFu) >> 4) | 0x10000u;
+          mma(tmem_d, a_lo, b_lo, acc);
+          mma(tmem_d, a_lo + 2u, b_lo + 2u, 1u);
+          mma(tmem_d, a_lo + 4u, b_lo + 4u, 1u);
+          mma(tmem_d, a_lo + 6u, b_lo + 6u, 1u);
+          if (MT == 2) {
+            const uint32_t a1 = a_lo + mt_step, d1 = tmem_d + BNu;
+            mma(d1, a1, b_lo, acc);
+            mma(d1, a1 + 2u, b_lo + 2u, 1u);
+            mma(d1, a1 + 4u, b_lo + 4u, 1u);
+            mma(d1, a1 + 6u, b_lo + 6u, 1u);
+          }
+          if constexpr (kPair) umma_commit_2sm(empty_bar(stage)); else umma_commit(empty_bar(stage));
+        }
+        if (++stage == nstages) { stage = 0; phase ^= 1u; }
+      };
+      auto stage_a_lo = [&]() { return (((smem_base + stage * stage_bytes) & 0x3FFFFu) >> 4) | 0x10000u; };
+      auto window_lo = [&](int row0) {
+        return (((smem_base + (uint32_t)sA * p.halo_bytes + (uint32_t)row0 * 128u) & 0x3FFFFu) >> 4) | 0x10000u;
+      };
+      auto release_window = [&]() {
+        if (el) { if constexpr (kPair) umma_commit_2sm(emptyA_bar(sA)); else umma_commit(emptyA_bar(sA)); }
+        if (++sA == p.a_stages) { sA = 0; phA ^= 1u; }
+      };
       for (long long tile = tile0; tile < p.num_tiles; tile += tile_step, ++it) {
         const TileCoord tc = decode_tile(p, tile, rank);
         const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
         mbar_wait(tempty_bar(as), aphase ^ 1u);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * (uint32_t)(p.MT * p.BN);
+        tmem_d = tmem_base + as * (uint32_t)(MT * p.BN);
         uint32_t accum = 0;
-        for (int tap = 0; tap < ntaps; ++tap) {
-          const int a = tap / (p.kw * p.kh);
+        for (int a = 0; a < p.kt; ++a) {
           int tv;
           bool from_cache;
           if (!tap_time(p, tc, a, tv, from_cache)) continue;
-          for (int kc = 0; kc < p.num_kc; ++kc) {
-            mbar_wait(full_bar(stage), phase);
-            tc_fence_after();
-            const uint32_t sa = smem_base + stage * stage_bytes;
-            const uint64_t bdesc = make_sdesc(sa + a_bytes);
-            for (int mt = 0; mt < p.MT; ++mt) {
-              const uint64_t adesc = make_sdesc(sa + mt * kABytes);
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                mma(tmem_d + (uint32_t)(mt * p.BN), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), accum | (uint32_t)k);
+          if (halo) {
+            for (int kc = 0; kc < num_kc; ++kc) {
+              mbar_wait(fullA_bar(sA), phA);
+              for (int bb = 0; bb < p.kh; ++bb)
+                for (int c = 0; c < p.kw; ++c) {
+                  kstep(window_lo(bb * p.hP + c), accum);
+                  accum = 1;
+                }
+              release_window();
             }
-            accum = 1;
-            commit(empty_bar(stage));
-            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          } else {
+            for (int s = nsp * num_kc; s > 0; --s) {
+              kstep(stage_a_lo(), accum);
+              accum = 1;
+            }
           }
         }
-        if (p.res_mma) {
-          for (int g = 0; g < p.BN / 64; ++g) {
-            mbar_wait(full_bar(stage), phase);
-            tc_fence_after();
-            const uint32_t sa = smem_base + stage * stage_bytes;
-            const uint64_t bdesc = make_sdesc(sa + a_bytes);
-            for (int mt = 0; mt < p.MT; ++mt) {
-              const uint64_t adesc = make_sdesc(sa + mt * kABytes);
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                mma(tmem_d + (uint32_t)(mt * p.BN), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), 1u);
-            }
-            commit(empty_bar(stage));
-            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        for (int g = 0; g < res_steps; ++g) {
+          if (halo) {
+            mbar_wait(fullA_bar(sA), phA);
+            kstep(window_lo(p.ph * p.hP + p.pw), 1u);
+            release_window();
+          } else {
+            kstep(stage_a_lo(), 1u);
           }
         }
-        commit(tfull_bar(as));
+        if (el) { if constexpr (kPair) umma_commit_2sm(tfull_bar(as)); else umma_commit(tfull_bar(as)); }
       }
     }
   } else if (warp >= 4) {
@@ -531,15 +634,18 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
 
       const int row = mt * 128 + rr;
-      const int dw = row % p.BW, dh = (row / p.BW) % p.BH, dt = row / (p.BW * p.BH);
+      // halo mode: M tile mt covers columns [8 mt, 8 mt + 8) of the 16-row CTA tile
+      const int dw = p.halo ? 8 * mt + (rr & 7) : row % p.BW;
+      const int dh = p.halo ? (rr >> 3) : (row / p.BW) % p.BH;
+      const int dt = p.halo ? 0 : row / (p.BW * p.BH);
       const int t = tc.t0 + dt, h = tc.h0 + dh, w = tc.w0 + dw;
       const bool valid = (t < p.To) && (h < p.Ho) && (w < p.Wo);
       const long long ooff = (long long)tc.b * p.osB + (long long)t * p.osT + (long long)h * p.osH + (long long)w * p.osW;
       bf16* orow = reinterpret_cast<bf16*>(p.out) + ooff + tc.n0;
       // origin of this M tile's store box
-      const int sw0 = tc.w0;
-      const int sh0 = tc.h0 + ((p.MT == 2 && p.BT == p.sBT) ? mt * p.sBH : 0);
-      const int st0 = tc.t0 + ((p.MT == 2 && p.BT != p.sBT) ? mt * p.sBT : 0);
+      const int sw0 = tc.w0 + (p.halo ? 8 * mt : 0);
+      const int sh0 = tc.h0 + ((!p.halo && p.MT == 2 && p.BT == p.sBT) ? mt * p.sBH : 0);
+      const int st0 = tc.t0 + ((!p.halo && p.MT == 2 && p.BT != p.sBT) ? mt * p.sBT : 0);
       const bf16* r0 = nullptr;
       const bf16* r1 = nullptr;
       const bf16* r2 = nullptr;
@@ -872,9 +978,9 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   // CTA pairs (cta_group::2): the tile doubles again, each CTA keeps its own MT*128 rows and half of the weight rows
   t.pair = 0;
   t.tileBH = t.BH; t.tileBT = t.BT;
-  // default policy (VT_TC_PAIR unset): pairs where they were measured to help -- the N = 256 tiles (+3..12 % in the model
-  // step); the N <= 128 level-0 layers are not weight-traffic bound and gain nothing
-  const bool pair_wanted = pair_mode() == 2 || pair_mode() == 1 || (pair_mode() < 0 && t.BN == 256);
+  // default policy (VT_TC_PAIR unset): pairs wherever there are enough tiles (N = 128, k133: 1247 -> 1336 TF/s, with the
+  // halo window 1343 -> 1599; profiles/notes_r1.md)
+  const bool pair_wanted = pair_mode() == 2 || pair_mode() == 1 || pair_mode() < 0 || (pair_mode() == 3 && t.BN == 256);
   if (w_batches <= 1 && pair_wanted) {
     int bwp, bhp, btp;
     long long padp = 0;
@@ -887,6 +993,28 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
       if (cbh >= 1 && bwp * cbh * cbt == 128 * t.MT) {
         t.pair = 1; t.BW = bwp; t.BH = cbh; t.BT = cbt; t.tileBH = bhp; t.tileBT = btp;
       }
+    }
+  }
+  // halo mode: spatial taps reuse one shared-memory window (see TcParams::halo)
+  {
+    static int halo_env = -1;   // VT_TC_HALO=0 switches the halo windows off (experiment knob)
+    if (halo_env < 0) { const char* e = getenv("VT_TC_HALO"); halo_env = e ? atoi(e) : 1; }
+    const bool geom = p.sh == 1 && p.sw == 1 && p.kh * p.kw > 1 && p.kh <= 3 && p.kw <= 3 && p.Ho == p.Hi && p.Wo == p.Wi &&
+                      w_batches <= 1 && p.Wo % 8 == 0 && p.Ho % 16 == 0;
+    if (halo_env && geom) {
+      const long long pos = (long long)p.B * p.To * p.Ho * p.Wo;
+      const long long ntl = Co_pad / t.BN;
+      int mt = 1;
+      if (t.BN <= 128 && mt_cap >= 2 && p.Wo % 16 == 0 && pos / 256 * ntl >= 2LL * num_sms) mt = 2;
+      int pr = 0;
+      if (pair_wanted && p.Ho % 32 == 0 && (pair_mode() == 2 || pos / (256 * mt) * ntl >= (long long)(num_sms / 2) * 2)) pr = 1;
+      t.halo = 1;
+      t.MT = mt; t.pair = pr;
+      t.BW = 8 * mt; t.BH = 16; t.BT = 1;
+      t.tileBH = pr ? 32 : 16; t.tileBT = 1;
+      t.hP = 8 * mt + 8;
+      t.halo_bytes = (uint32_t)((16 + p.kh - 1) * t.hP * 128);
+      t.a_stages = 2;
     }
   }
   t.B = p.B; t.To = p.To; t.Ho = p.Ho; t.Wo = p.Wo; t.Co = p.Co; t.Ti = p.Ti;
@@ -917,18 +1045,19 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
     if (ntaps_eff * t.num_kc >= 48) t.tma_store = 0;
   }
   t.sBH = t.BH; t.sBT = t.BT;
-  if (t.MT == 2) {
+  if (t.MT == 2 && !t.halo) {
     if (t.BT >= 2) t.sBT = t.BT / 2; else t.sBH = t.BH / 2;
     if (t.BW * t.sBH * t.sBT != 128) t.tma_store = 0;
   }
   t.res_mma = (p.res_mode == 1 && p.ra == 1.0f && p.rb == 1.0f && t.BN % 64 == 0 && p.Co % 64 == 0 && p.rsW % 8 == 0 && p.rsH % 8 == 0 &&
                p.rsT % 8 == 0 && p.rsB % 8 == 0 && (((uintptr_t)p.res) & 15) == 0) ? 1 : 0;
   const int bn_local = t.pair ? t.BN / 2 : t.BN;
-  const size_t stage_bytes = (size_t)t.MT * kABytes + (size_t)bn_local * 128;
+  const size_t stage_bytes = (t.halo ? 0 : (size_t)t.MT * kABytes) + (size_t)bn_local * 128;
   const size_t budget = 222 * 1024;
   const size_t staging = t.tma_store ? 2 * 16384 : 0;
   const size_t fixed = 1024 /*align*/ + 8 * 2 * 8 + 64 + 2 * 768 * 4 + 2 * 128 * 2 * 4 + 256;
-  int stages = (int)((budget - fixed - staging) / stage_bytes);
+  const size_t a_ring = (size_t)t.a_stages * t.halo_bytes;
+  int stages = (int)((budget - fixed - staging - a_ring) / stage_bytes);
   if (stages > 8) stages = 8;
   {
     static int cap = -1;   // VT_TC_STAGES: experiment knob (pipeline-depth sensitivity)
@@ -938,11 +1067,11 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   if (stages < 2) { g_tc_err = "not enough shared memory for 2 stages"; return cudaErrorInvalidValue; }
   t.stages = stages;
   // smem layout from the 1024-aligned base: [stages x (A | B)] [staging 2 x 16 KB] [barriers | tmem slot | bias/gamma/beta | stats]
-  t.stage_off = (uint32_t)(stages * stage_bytes);
+  t.stage_off = (uint32_t)(a_ring + stages * stage_bytes);
   uint32_t cols = 32;
   while (cols < (uint32_t)(2 * t.MT * t.BN)) cols <<= 1;
   t.tmem_cols = cols;
-  const size_t smem = fixed + staging + (size_t)stages * stage_bytes + 8 * (2 * stages + 4);
+  const size_t smem = fixed + staging + a_ring + (size_t)stages * stage_bytes + 8 * (2 * stages + 4 + 2 * t.a_stages);
 
   TcMaps maps;
   // activation view: element (c, w, h, t, b) at base + c + w*sw_ + h*sh_ + t*isT + b*bs  (elements)
@@ -950,6 +1079,7 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
     cuuint64_t dims[5] = {(cuuint64_t)p.Ci, (cuuint64_t)Wn, (cuuint64_t)Hn, (cuuint64_t)Tn, (cuuint64_t)p.B};
     cuuint64_t strides[4] = {(cuuint64_t)sw_ * 2, (cuuint64_t)sh_ * 2, (cuuint64_t)st_ * 2, (cuuint64_t)bs * 2};
     cuuint32_t box[5] = {64, (cuuint32_t)t.BW, (cuuint32_t)t.BH, (cuuint32_t)t.BT, 1};
+    if (t.halo) { box[1] = (cuuint32_t)t.hP; box[2] = (cuuint32_t)(16 + p.kh - 1); }
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<bf16*>(base), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -999,8 +1129,9 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   };
   maps.r = maps.a[0]; maps.e = maps.b; maps.o = maps.a[0]; maps.o2 = maps.a[0];
   if (t.tma_store) {
-    if (!encode_out(&maps.o, out, p.To, p.osW, p.osH, p.osT, p.osB, t.BW, t.sBH, t.sBT)) return cudaErrorInvalidValue;
-    if (t.ln_mode == 2 && !encode_out(&maps.o2, t.out2, p.To, p.osW, p.osH, p.osT, p.osB, t.BW, t.sBH, t.sBT)) return cudaErrorInvalidValue;
+    const int sbw = t.halo ? 8 : t.BW;
+    if (!encode_out(&maps.o, out, p.To, p.osW, p.osH, p.osT, p.osB, sbw, t.sBH, t.sBT)) return cudaErrorInvalidValue;
+    if (t.ln_mode == 2 && !encode_out(&maps.o2, t.out2, p.To, p.osW, p.osH, p.osT, p.osB, sbw, t.sBH, t.sBT)) return cudaErrorInvalidValue;
   }
   if (t.res_mma) {
     static bf16* ident_dev[64] = {nullptr};   // 256 x 256 identity, built once per device on the launching stream
@@ -1013,7 +1144,7 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
       fill_identity_kernel<<<256, 256, 0, s>>>(ident_dev[devid]);
     }
     bf16* ident = ident_dev[devid];
-    if (!encode_out(&maps.r, p.res, p.resT, p.rsW, p.rsH, p.rsT, p.rsB, t.BW, t.BH, t.BT)) return cudaErrorInvalidValue;
+    if (!encode_out(&maps.r, p.res, p.resT, p.rsW, p.rsH, p.rsT, p.rsB, t.halo ? t.hP : t.BW, t.halo ? 16 + p.kh - 1 : t.BH, t.BT)) return cudaErrorInvalidValue;
     cuuint64_t dims[3] = {256, 256, 1};
     cuuint64_t strides[2] = {512, 256 * 512};
     cuuint32_t box[3] = {64, (cuuint32_t)bn_local, 1};
@@ -1036,7 +1167,7 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   }
   const double Mrows = (double)p.B * p.To * p.Ho * p.Wo;
   char det[96] = "";
-  if (prof_enabled()) snprintf(det, sizeof(det), "k%d%d%d s%d%d %d->%d @%dx%dx%d tile%dx%dx%d bn%d mt%d%s", p.kt, p.kh, p.kw, p.st, p.sh, p.Ci, p.Co, p.To, p.Ho, p.Wo, t.tileBT, t.tileBH, t.BW, t.BN, t.MT, t.pair ? " pair" : "");
+  if (prof_enabled()) snprintf(det, sizeof(det), "k%d%d%d s%d%d %d->%d @%dx%dx%d tile%dx%dx%d bn%d mt%d%s", p.kt, p.kh, p.kw, p.st, p.sh, p.Ci, p.Co, p.To, p.Ho, p.Wo, t.tileBT, t.tileBH, t.BW, t.BN, t.MT, t.pair ? (t.halo ? " pair halo" : " pair") : (t.halo ? " halo" : ""));
   ProfScope _ps("conv_tc", 2.0 * Mrows * p.kt * p.kh * p.kw * p.Ci * p.Co,
                 2.0 * ((double)p.B * p.Ti * p.Hi * p.Wi * p.Ci) + Mrows * p.Co * (tout == DT_F32 ? 4.0 : 2.0), s, det);
   if (t.pair) {
