@@ -10,6 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 from vidtok_b200 import _native as N  # noqa: E402
+if os.environ.get("VT_AB_LIB"):   # same-run A/B against another build of the library (development only)
+    N.LIB_PATH = os.environ["VT_AB_LIB"]
 from vidtok_b200.compat_util import instantiate_from_config  # noqa: E402
 from vidtok_b200.synth import synth_clip, synth_state_dict  # noqa: E402
 

@@ -12,8 +12,8 @@
 // Both land in shared memory in the canonical K-major SWIZZLE_128B layout and feed
 // tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) issued by one thread; accumulators live in TMEM.
 // Warp roles (persistent CTA, one per SM): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator,
-// warps 4-7 = epilogue (tcgen05.ld -> bias / residual / mix -> bf16 -> 16-byte global stores), overlapping the
-// next tile's main loop through the second TMEM accumulator stage.
+// warps 3-10 = epilogue (tcgen05.ld -> bias / residual / mix / LayerNorm -> bf16 -> per-warp swizzled staging -> TMA
+// store), overlapping the next tile's main loop through the second TMEM accumulator stage.
 #include <cuda.h>
 
 #include <cstdio>
@@ -73,11 +73,12 @@ struct TcParams {
   // residual add through the tensor pipe: BN/64 extra K steps with A = residual tile (TMA) and B = a slice of the
   // identity matrix, so `+ x` costs no epilogue work at all (res_mode 1 with ra == rb == 1)
   int res_mma;
-  // coalesced epilogue: bf16 results are staged in shared memory (SWIZZLE_128B rows of 64 channels) and written with
-  // TMA tensor stores of {64, sBW, sBH, sBT} boxes (partial tiles are clipped by the tensor bounds)
+  // coalesced epilogue: every epilogue warp stages its 32 rows x 64 channels of bf16 results in shared memory
+  // (SWIZZLE_128B rows) and writes them with its own TMA tensor store of a {64, qw, qh, qt} box (partial tiles are
+  // clipped by the tensor bounds)
   int tma_store;
-  int sBH, sBT;              // store box of one M tile (sBW == BW)
-  uint32_t stage_off;        // byte offset of the staging buffers [2 groups][16 KB] from the aligned smem base
+  int stg_bufs;              // staging buffers per warp (4 KB each): 2 when shared memory allows, else 1
+  uint32_t stage_off;        // byte offset of the staging buffers [8 warps][stg_bufs][4 KB] from the aligned smem base
   // cta_group::2: two CTAs of a cluster (one TPC) work on one 2*MT*128-row tile; each loads its own rows of A and half of
   // the B (weight) rows, the leader issues M=256 MMAs that read both halves -> weight bytes per FLOP are halved again
   int pair;
@@ -103,7 +104,8 @@ struct TcMaps {
 };
 
 constexpr int kEpiWarps = 8;
-constexpr int kThreads = 128 + kEpiWarps * 32;
+constexpr int kEpiWarp0 = 3;            // first epilogue warp (any 8 consecutive warps cover every TMEM lane quarter twice)
+constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;
 constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
 
 // ---------------------------------------------------------------------------------------------------
@@ -162,6 +164,7 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t sr
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -257,17 +260,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
-        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
-        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
-        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
-      : "memory");
-}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptors (cute::UMMA::SmemDescriptor), K-major SWIZZLE_128B, are built as two 32-bit words:
@@ -288,13 +280,21 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
     f[2 * i + 1] = __high2float(h[i]);
   }
 }
-__device__ __forceinline__ uint4 pack8(const float* f) {
-  uint4 u;
-  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-  return u;
+// bf16 pair <-> fp32 through plain 32-bit registers (pointer punning would push the packed row into local memory)
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
+// packed fp32 pairs (sm_100 FADD2 / FMUL2 / FFMA2): two lanes per issue slot in the epilogue arithmetic
+__device__ __forceinline__ uint64_t pk2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ float tanh_approx(float x) { float t; asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x)); return t; }
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
 struct TileCoord {
   int b, t0, h0, w0, n0;
@@ -331,7 +331,7 @@ __device__ __forceinline__ bool tap_time(const TcParams& p, const TileCoord& tc,
   return true;
 }
 
-// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle, 4..11 = epilogue (two warps per TMEM
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3..10 = epilogue (two warps per TMEM
 // lane quarter, alternating 32-column chunks).
 template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -348,7 +348,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   const uint32_t b_bytes = (uint32_t)bn_local * 128u;
   const uint32_t stage_bytes = p.halo ? b_bytes : a_bytes + b_bytes;   // halo mode: the stage ring holds B tiles only
   const uint32_t ring_base = smem_base + (p.halo ? (uint32_t)p.a_stages * p.halo_bytes : 0u);
-  const uint32_t bar_base = ring_base + p.stages * stage_bytes + (p.tma_store ? 2u * 16384u : 0u);
+  const uint32_t bar_base = ring_base + p.stages * stage_bytes + (p.tma_store ? (uint32_t)(kEpiWarps * p.stg_bufs) * 4096u : 0u);
   // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2], fullA[a_stages], emptyA[a_stages];
   // then tmem ptr; then bias[2][256]
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -603,35 +603,55 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         if (el) { if constexpr (kPair) umma_commit_2sm(tfull_bar(as)); else umma_commit(tfull_bar(as)); }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= kEpiWarp0) {
     // ===================== epilogue =====================
     // Two groups of four warps (one warp per TMEM lane quarter).  MT == 2: group g owns the rows of M tile g;
-    // MT == 1: the groups alternate 64-channel slices of the same 128 rows.
+    // MT == 1: the groups alternate 64-channel slices of the same 128 rows.  A thread owns one output row and at most
+    // 128 of its channels.  Every WARP stages its 32 rows x 64 channels in its own swizzled buffer and issues its own TMA
+    // store (no block-level barrier on the store path); LayerNorm keeps the bf16-packed row in registers between the
+    // statistics pass and the normalisation pass, so the accumulator is read once and released before the second pass.
     const int q = warp & 3;            // TMEM lane quarter this warp may read
-    const int grp = (warp - 4) >> 2;   // 0 / 1
-    const int et = threadIdx.x - 128;
-    const bool leader = (et & 127) == 0;
+    const int grp = (warp - kEpiWarp0) >> 2;   // 0 / 1
+    const int et = threadIdx.x - kEpiWarp0 * 32;
     const int nchunks = p.BN / 32;
     const int mt = (p.MT == 2) ? grp : 0;
     const int sb = (p.MT == 2) ? 0 : grp;      // first 64-channel slice
     const int ss = (p.MT == 2) ? 1 : 2;        // slice step
     const int rr = q * 32 + lane;              // row inside the M tile
-    uint8_t* stg_gen = smem_gen + p.stage_off + grp * 16384;
-    const uint32_t stg = smem_base + p.stage_off + grp * 16384;
-    uint8_t* my_stg = stg_gen + rr * 128;
-    const int swz = rr & 7;
+    const uint32_t stg_bytes = (uint32_t)p.stg_bufs * 4096u;
+    const uint32_t wstg = smem_base + p.stage_off + (uint32_t)(warp - kEpiWarp0) * stg_bytes;
+    uint8_t* wstg_gen = smem_gen + p.stage_off + (uint32_t)(warp - kEpiWarp0) * stg_bytes;
+    const int swz = lane & 7;
+    uint32_t nstore = 0;                       // TMA stores issued by this warp (selects the staging buffer)
+    // origin of this warp's 32 rows inside the CTA tile (the store box is {64, qw, qh, qt})
+    int qw0, qh0, qt0;
+    if (p.halo) { qw0 = 8 * mt; qh0 = 4 * q; qt0 = 0; }
+    else { const int row0 = mt * 128 + q * 32; qw0 = row0 % p.BW; qh0 = (row0 / p.BW) % p.BH; qt0 = row0 / (p.BW * p.BH); }
+    const bool res_direct = (p.res_mode == 1 && !p.res_mma);
+    const bool store_a = (p.ln_mode != 1);
+    const float inv_n = 1.0f / (float)p.BN;
     uint32_t it = 0;
+    int last_n0 = -1;
+    uint32_t cbuf = 1;                         // bias / gamma / beta buffer in use (toggled whenever n0 changes)
     for (long long tile = tile0; tile < p.num_tiles; tile += tile_step, ++it) {
       const TileCoord tc = decode_tile(p, tile, rank);
       const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
-      float* bias_s = sbias + as * 768;
-      float* gamma_s = bias_s + 256;
-      float* beta_s = bias_s + 512;
-      for (int i = et; i < p.BN; i += kEpiWarps * 32) {
-        bias_s[i] = (p.bias && tc.n0 + i < p.Co_real) ? p.bias[tc.n0 + i] : 0.f;
-        if (p.ln_mode) { gamma_s[i] = p.ln_gamma[tc.n0 + i]; beta_s[i] = p.ln_beta[tc.n0 + i]; }
+      if (tc.n0 != last_n0) {
+        // all epilogue warps walk the same tile sequence, so this branch is uniform across them; a warp can only be one
+        // barrier behind, which is why two buffers are enough
+        last_n0 = tc.n0;
+        cbuf ^= 1u;
+        float* b_ = sbias + cbuf * 768;
+        for (int i = et; i < p.BN; i += kEpiWarps * 32) {
+          b_[i] = (p.bias && tc.n0 + i < p.Co_real) ? p.bias[tc.n0 + i] : 0.f;
+          // with SiLU the normalisation produces y/2 directly (silu(y) = h + h*tanh(h), h = y/2)
+          if (p.ln_mode) { const float sc = p.ln_silu ? 0.5f : 1.0f; b_[256 + i] = sc * p.ln_gamma[tc.n0 + i]; b_[512 + i] = sc * p.ln_beta[tc.n0 + i]; }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+      const float* bias_s = sbias + cbuf * 768;
+      const float* gamma_s = bias_s + 256;
+      const float* beta_s = bias_s + 512;
 
       const int row = mt * 128 + rr;
       // halo mode: M tile mt covers columns [8 mt, 8 mt + 8) of the 16-row CTA tile
@@ -641,15 +661,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       const int t = tc.t0 + dt, h = tc.h0 + dh, w = tc.w0 + dw;
       const bool valid = (t < p.To) && (h < p.Ho) && (w < p.Wo);
       const long long ooff = (long long)tc.b * p.osB + (long long)t * p.osT + (long long)h * p.osH + (long long)w * p.osW;
-      bf16* orow = reinterpret_cast<bf16*>(p.out) + ooff + tc.n0;
-      // origin of this M tile's store box
-      const int sw0 = tc.w0 + (p.halo ? 8 * mt : 0);
-      const int sh0 = tc.h0 + ((!p.halo && p.MT == 2 && p.BT == p.sBT) ? mt * p.sBH : 0);
-      const int st0 = tc.t0 + ((!p.halo && p.MT == 2 && p.BT != p.sBT) ? mt * p.sBT : 0);
       const bf16* r0 = nullptr;
       const bf16* r1 = nullptr;
       const bf16* r2 = nullptr;
-      const bool res_direct = (p.res_mode == 1 && !p.res_mma);
       if (valid && res_direct) {
         r0 = p.res + (long long)tc.b * p.rsB + (long long)t * p.rsT + (long long)h * p.rsH + (long long)w * p.rsW + tc.n0;
       } else if (valid && p.res_mode == 3) {
@@ -662,41 +676,74 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         if (tb < p.resT) r1 = p.res + sp + (long long)tb * p.rsT;
         if (tcn < p.resT) r2 = p.res + sp + (long long)tcn * p.rsT;
       }
+      // this lane's row in the next staging buffer, once the TMA store that last used the buffer has read it
+      auto stage_row = [&]() -> uint8_t* {
+        const uint32_t b = (p.stg_bufs == 2) ? (nstore & 1u) : 0u;
+        if (lane == 0) { if (p.stg_bufs == 2) tma_store_wait_read1(); else tma_store_wait_read(); }
+        __syncwarp();
+        return wstg_gen + b * 4096u + (uint32_t)lane * 128u;
+      };
+      auto store_rows = [&](const CUtensorMap* m, int c0) {
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          const uint32_t b = (p.stg_bufs == 2) ? (nstore & 1u) : 0u;
+          tma_store_5d(m, wstg + b * 4096u, c0, tc.w0 + qw0, tc.h0 + qh0, tc.t0 + qt0, tc.b);
+          tma_store_commit();
+        }
+        ++nstore;
+      };
+      // packed bf16 words of 64 channels -> staging row (TMA store) or global memory
+      auto put64 = [&](const uint32_t* pk, int ncol, const CUtensorMap* m, bf16* grow, int j) {
+        if (p.tma_store) {
+          uint8_t* my = stage_row();
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<uint4*>(my + ((g ^ swz) << 4)) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+          store_rows(m, tc.n0 + j);
+        } else if (valid) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            if (g * 8 < ncol) *reinterpret_cast<uint4*>(grow + j + g * 8) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+        }
+      };
+
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * p.MT + mt) * p.BN);
-      float lsum = 0.f, lsq = 0.f;
-      const bool store_a = (p.ln_mode != 1);
-      // ---- pass A: v = rb*(acc+bias) + ra*R ; plain mode stores it, LayerNorm modes also keep it in TMEM + statistics
-      for (int sl = sb; sl * 2 < nchunks; sl += ss) {
-        if (p.tma_store && store_a) {
-          if (leader) tma_store_wait_read();
-          asm volatile("bar.sync %0, 128;" ::"r"(3 + grp) : "memory");
-        }
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          const int ch = 2 * sl + c;
-          if (ch >= nchunks) break;
-          const int j = ch * 32;
+      uint64_t lsum2 = 0ull, lsq2 = 0ull;      // (even, odd) column partial sums
+      uint32_t keep[64];                       // bf16 pairs of this thread's (up to) 128 channels
+      // ---- pass A: v = rb*(acc+bias) + ra*R ; stored unless the LayerNorm replaces it; statistics for the LayerNorm
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int sl = sb + i * ss;
+        if (sl * 2 >= nchunks) break;
+        const int j = sl * 64;
+        const int ncol = (sl * 2 + 1 < nchunks) ? 64 : 32;
+#pragma unroll
+        for (int hc = 0; hc < 2; ++hc) {
+          if (hc * 32 >= ncol) break;
           uint32_t v[32];
-          tmem_ld32(tbase + (uint32_t)j, v);
+          tmem_ld32(tbase + (uint32_t)(j + hc * 32), v);
           tmem_ld_wait();
           float f[32];
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
-            const float4 bv = *reinterpret_cast<const float4*>(bias_s + j + g * 4);
-            f[g * 4 + 0] = p.rb * (__uint_as_float(v[g * 4 + 0]) + bv.x);
-            f[g * 4 + 1] = p.rb * (__uint_as_float(v[g * 4 + 1]) + bv.y);
-            f[g * 4 + 2] = p.rb * (__uint_as_float(v[g * 4 + 2]) + bv.z);
-            f[g * 4 + 3] = p.rb * (__uint_as_float(v[g * 4 + 3]) + bv.w);
+            const ulonglong2 bv = *reinterpret_cast<const ulonglong2*>(bias_s + j + hc * 32 + g * 4);
+            uint64_t a0 = add2(pk2(__uint_as_float(v[g * 4 + 0]), __uint_as_float(v[g * 4 + 1])), bv.x);
+            uint64_t a1 = add2(pk2(__uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3])), bv.y);
+            if (p.rb != 1.0f) { const uint64_t rb2 = pk2(p.rb, p.rb); a0 = mul2(a0, rb2); a1 = mul2(a1, rb2); }
+            upk2(a0, f[g * 4 + 0], f[g * 4 + 1]);
+            upk2(a1, f[g * 4 + 2], f[g * 4 + 3]);
           }
+          const int jj = j + hc * 32;
           if (valid && res_direct) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               float rv[8];
-              unpack8(*reinterpret_cast<const uint4*>(r0 + j + g * 8), rv);
+              unpack8(*reinterpret_cast<const uint4*>(r0 + jj + g * 8), rv);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) f[g * 8 + i] = fmaf(p.ra, rv[i], f[g * 8 + i]);
+              for (int e = 0; e < 8; ++e) f[g * 8 + e] = fmaf(p.ra, rv[e], f[g * 8 + e]);
             }
           } else if (valid && p.res_mode == 3) {
             const float s3 = p.ra * (1.0f / 3.0f);
@@ -704,63 +751,64 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             for (int g = 0; g < 4; ++g) {
               float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
               float rv[8];
-              if (r0) { unpack8(*reinterpret_cast<const uint4*>(r0 + j + g * 8), rv);
+              if (r0) { unpack8(*reinterpret_cast<const uint4*>(r0 + jj + g * 8), rv);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) acc[i] += rv[i]; }
-              if (r1) { unpack8(*reinterpret_cast<const uint4*>(r1 + j + g * 8), rv);
+                for (int e = 0; e < 8; ++e) acc[e] += rv[e]; }
+              if (r1) { unpack8(*reinterpret_cast<const uint4*>(r1 + jj + g * 8), rv);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) acc[i] += rv[i]; }
-              if (r2) { unpack8(*reinterpret_cast<const uint4*>(r2 + j + g * 8), rv);
+                for (int e = 0; e < 8; ++e) acc[e] += rv[e]; }
+              if (r2) { unpack8(*reinterpret_cast<const uint4*>(r2 + jj + g * 8), rv);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) acc[i] += rv[i]; }
+                for (int e = 0; e < 8; ++e) acc[e] += rv[e]; }
 #pragma unroll
-              for (int i = 0; i < 8; ++i) f[g * 8 + i] = fmaf(s3, acc[i], f[g * 8 + i]);
+              for (int e = 0; e < 8; ++e) f[g * 8 + e] = fmaf(s3, acc[e], f[g * 8 + e]);
             }
           }
-          if (p.ln_mode) {
+          if (p.out_f32) {
+            // external fp32 heads (never fused with LayerNorm): direct stores, only the real output channels
+            if (valid) {
+              float* of = reinterpret_cast<float*>(p.out) + ooff;
+              if (p.osC == 1 && tc.n0 + jj + 32 <= p.Co_real) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              lsum += f[i];
-              lsq = fmaf(f[i], f[i], lsq);
-              v[i] = __float_as_uint(f[i]);
-            }
-            tmem_st32(tbase + (uint32_t)j, v);
-          }
-          if (store_a) {
-            if (p.tma_store) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(my_stg + (((c * 4 + g) ^ swz) << 4)) = pack8(f + g * 8);
-            } else if (valid) {
-              if (p.out_f32) {
-                float* of = reinterpret_cast<float*>(p.out) + ooff;
-                if (p.osC == 1 && tc.n0 + j + 32 <= p.Co_real) {
-#pragma unroll
-                  for (int g = 0; g < 8; ++g)
-                    *reinterpret_cast<float4*>(of + tc.n0 + j + g * 4) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
-                } else {
-#pragma unroll
-                  for (int i = 0; i < 32; ++i)
-                    if (tc.n0 + j + i < p.Co_real) of[(long long)(tc.n0 + j + i) * p.osC] = f[i];
-                }
+                for (int g = 0; g < 8; ++g)
+                  *reinterpret_cast<float4*>(of + tc.n0 + jj + g * 4) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
               } else {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(orow + j + g * 8) = pack8(f + g * 8);
+                for (int e = 0; e < 32; ++e)
+                  if (tc.n0 + jj + e < p.Co_real) of[(long long)(tc.n0 + jj + e) * p.osC] = f[e];
               }
             }
+          } else {
+            if (p.ln_mode) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const uint64_t f2 = pk2(f[2 * e], f[2 * e + 1]);
+                lsum2 = add2(lsum2, f2);
+                lsq2 = fma2(f2, f2, lsq2);
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < 16; ++e) keep[i * 32 + hc * 16 + e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
           }
         }
-        if (p.tma_store && store_a) {
-          fence_async_smem();
-          asm volatile("bar.sync %0, 128;" ::"r"(3 + grp) : "memory");
-          if (leader) {
-            tma_store_5d(&maps.o, stg, tc.n0 + sl * 64, sw0, sh0, st0, tc.b);
-            tma_store_commit();
-          }
-        }
+        if (!p.out_f32 && store_a) put64(&keep[i * 32], ncol, &maps.o, reinterpret_cast<bf16*>(p.out) + ooff + tc.n0, j);
+      }
+      // the accumulator has been read: hand the TMEM stage back to the MMA issuer before the second pass
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (kPair) mbar_arrive_remote(tempty_bar(as), 0); else mbar_arrive(tempty_bar(as));
       }
       if (p.ln_mode) {
-        // ---- LayerNorm over the Cout values of this row (model_3dcausal.py:62-80, eps 1e-6), optional SiLU (:26-27)
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        // ---- LayerNorm over the Cout values of this row (model_3dcausal.py:62-80, eps 1e-6), optional SiLU (:26-27).
+        // Statistics come from the fp32 values, the normalised values from their bf16 rounding (what the unfused
+        // conv -> LayerNorm pair reads back from memory).
+        float lsum, lsq;
+        {
+          float a, b;
+          upk2(lsum2, a, b); lsum = a + b;
+          upk2(lsq2, a, b); lsq = a + b;
+        }
         if (p.MT == 1) {  // the other group holds the other slices of the row
           float* xs = stat_s + ((grp * 128 + rr) << 1);
           xs[0] = lsum; xs[1] = lsq;
@@ -768,66 +816,48 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           const float* ys = stat_s + ((((grp ^ 1) * 128) + rr) << 1);
           lsum += ys[0]; lsq += ys[1];
         }
-        const float inv_n = 1.0f / (float)p.BN;
         const float mean = lsum * inv_n;
         float var = fmaf(-mean, mean, lsq * inv_n);
         var = var < 0.f ? 0.f : var;
         const float rstd = rsqrtf(var + 1e-6f);
         const float nmr = -mean * rstd;
+        const uint64_t rstd2 = pk2(rstd, rstd), nmr2 = pk2(nmr, nmr);
         bf16* nrow = reinterpret_cast<bf16*>(p.ln_mode == 1 ? p.out : p.out2) + ooff + tc.n0;
         const CUtensorMap* nmap = (p.ln_mode == 1) ? &maps.o : &maps.o2;
-        for (int sl = sb; sl * 2 < nchunks; sl += ss) {
-          if (p.tma_store) {
-            if (leader) tma_store_wait_read();
-            asm volatile("bar.sync %0, 128;" ::"r"(3 + grp) : "memory");
-          }
-#pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            const int ch = 2 * sl + c;
-            if (ch >= nchunks) break;
-            const int j = ch * 32;
-            uint32_t v[32];
-            tmem_ld32(tbase + (uint32_t)j, v);
-            tmem_ld_wait();
-            float f[32];
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const float4 gv = *reinterpret_cast<const float4*>(gamma_s + j + g * 4);
-              const float4 bv = *reinterpret_cast<const float4*>(beta_s + j + g * 4);
-              f[g * 4 + 0] = fmaf(fmaf(__uint_as_float(v[g * 4 + 0]), rstd, nmr), gv.x, bv.x);
-              f[g * 4 + 1] = fmaf(fmaf(__uint_as_float(v[g * 4 + 1]), rstd, nmr), gv.y, bv.y);
-              f[g * 4 + 2] = fmaf(fmaf(__uint_as_float(v[g * 4 + 2]), rstd, nmr), gv.z, bv.z);
-              f[g * 4 + 3] = fmaf(fmaf(__uint_as_float(v[g * 4 + 3]), rstd, nmr), gv.w, bv.w);
-            }
+        for (int i = 0; i < 2; ++i) {
+          const int sl = sb + i * ss;
+          if (sl * 2 >= nchunks) break;
+          const int j = sl * 64;
+          const int ncol = (sl * 2 + 1 < nchunks) ? 64 : 32;
+          uint32_t o[32];
+#pragma unroll
+          for (int g = 0; g < 16; ++g) {
+            if (g * 4 >= ncol) break;
+            const ulonglong2 gv = *reinterpret_cast<const ulonglong2*>(gamma_s + j + g * 4);
+            const ulonglong2 bv = *reinterpret_cast<const ulonglong2*>(beta_s + j + g * 4);
+            const uint32_t a2 = keep[i * 32 + 2 * g], b2 = keep[i * 32 + 2 * g + 1];
+            uint64_t y0 = fma2(fma2(pk2(bf16_lo(a2), bf16_hi(a2)), rstd2, nmr2), gv.x, bv.x);
+            uint64_t y1 = fma2(fma2(pk2(bf16_lo(b2), bf16_hi(b2)), rstd2, nmr2), gv.y, bv.y);
             if (p.ln_silu) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = silu_f(f[i]);
+              // y holds h = LN(v)/2 (gamma, beta were halved): silu = h + h * tanh(h)
+              float h0, h1, h2, h3;
+              upk2(y0, h0, h1);
+              upk2(y1, h2, h3);
+              y0 = fma2(y0, pk2(tanh_approx(h0), tanh_approx(h1)), y0);
+              y1 = fma2(y1, pk2(tanh_approx(h2), tanh_approx(h3)), y1);
             }
-            if (p.tma_store) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(my_stg + (((c * 4 + g) ^ swz) << 4)) = pack8(f + g * 8);
-            } else if (valid) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(nrow + j + g * 8) = pack8(f + g * 8);
-            }
+            float o0, o1, o2, o3;
+            upk2(y0, o0, o1);
+            upk2(y1, o2, o3);
+            o[2 * g] = pack_bf16x2(o0, o1);
+            o[2 * g + 1] = pack_bf16x2(o2, o3);
           }
-          if (p.tma_store) {
-            fence_async_smem();
-            asm volatile("bar.sync %0, 128;" ::"r"(3 + grp) : "memory");
-            if (leader) {
-              tma_store_5d(nmap, stg, tc.n0 + sl * 64, sw0, sh0, st0, tc.b);
-              tma_store_commit();
-            }
-          }
+          put64(o, ncol, nmap, nrow, j);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (kPair) mbar_arrive_remote(tempty_bar(as), 0); else mbar_arrive(tempty_bar(as));
-      }
     }
-    if (p.tma_store && leader) tma_store_wait_all();
+    if (p.tma_store && lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -1044,19 +1074,20 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
     int ntaps_eff = p.kt * p.kh * p.kw;
     if (ntaps_eff * t.num_kc >= 48) t.tma_store = 0;
   }
-  t.sBH = t.BH; t.sBT = t.BT;
-  if (t.MT == 2 && !t.halo) {
-    if (t.BT >= 2) t.sBT = t.BT / 2; else t.sBH = t.BH / 2;
-    if (t.BW * t.sBH * t.sBT != 128) t.tma_store = 0;
-  }
   t.res_mma = (p.res_mode == 1 && p.ra == 1.0f && p.rb == 1.0f && t.BN % 64 == 0 && p.Co % 64 == 0 && p.rsW % 8 == 0 && p.rsH % 8 == 0 &&
                p.rsT % 8 == 0 && p.rsB % 8 == 0 && (((uintptr_t)p.res) & 15) == 0) ? 1 : 0;
   const int bn_local = t.pair ? t.BN / 2 : t.BN;
   const size_t stage_bytes = (t.halo ? 0 : (size_t)t.MT * kABytes) + (size_t)bn_local * 128;
   const size_t budget = 222 * 1024;
-  const size_t staging = t.tma_store ? 2 * 16384 : 0;
   const size_t fixed = 1024 /*align*/ + 8 * 2 * 8 + 64 + 2 * 768 * 4 + 2 * 128 * 2 * 4 + 256;
   const size_t a_ring = (size_t)t.a_stages * t.halo_bytes;
+  // one staging buffer per epilogue warp: a second one (VT_TC_STG=2, if the ring keeps >= 3 stages) costs operand
+  // stages, which was measured to matter more (model step 143.3 -> 140.6 ms, profiles/notes_r1.md)
+  t.stg_bufs = 1;
+  static int stg_env = -1;
+  if (stg_env < 0) { const char* e = getenv("VT_TC_STG"); stg_env = e ? atoi(e) : 1; }
+  if (stg_env >= 2 && t.tma_store && (budget - fixed - a_ring - (size_t)kEpiWarps * 2 * 4096) / stage_bytes >= 3) t.stg_bufs = 2;
+  const size_t staging = t.tma_store ? (size_t)kEpiWarps * t.stg_bufs * 4096 : 0;
   int stages = (int)((budget - fixed - staging - a_ring) / stage_bytes);
   if (stages > 8) stages = 8;
   {
@@ -1129,9 +1160,12 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   };
   maps.r = maps.a[0]; maps.e = maps.b; maps.o = maps.a[0]; maps.o2 = maps.a[0];
   if (t.tma_store) {
-    const int sbw = t.halo ? 8 : t.BW;
-    if (!encode_out(&maps.o, out, p.To, p.osW, p.osH, p.osT, p.osB, sbw, t.sBH, t.sBT)) return cudaErrorInvalidValue;
-    if (t.ln_mode == 2 && !encode_out(&maps.o2, t.out2, p.To, p.osW, p.osH, p.osT, p.osB, sbw, t.sBH, t.sBT)) return cudaErrorInvalidValue;
+    // box of one warp's 32 rows: the first 32 positions of the (w, h, t) box order
+    int qw = t.halo ? 8 : (t.BW < 32 ? t.BW : 32);
+    int qh = t.halo ? 4 : (t.BH < 32 / qw ? t.BH : 32 / qw);
+    int qt = 32 / (qw * qh);
+    if (!encode_out(&maps.o, out, p.To, p.osW, p.osH, p.osT, p.osB, qw, qh, qt)) return cudaErrorInvalidValue;
+    if (t.ln_mode == 2 && !encode_out(&maps.o2, t.out2, p.To, p.osW, p.osH, p.osT, p.osB, qw, qh, qt)) return cudaErrorInvalidValue;
   }
   if (t.res_mma) {
     static bf16* ident_dev[64] = {nullptr};   // 256 x 256 identity, built once per device on the launching stream
