@@ -227,15 +227,17 @@ def run_b200_arm(args):
             out_host.copy_(dec, non_blocking=True)
         return dec
 
+    # the clock sampler starts BEFORE the warm-up: nvidia-smi takes ~1 s to initialise NVML, and doing that inside the
+    # timed region cost the first steps ~10 % (profiles/notes_r1.md); its samples cover warm-up + timed steps, all under load
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_resident()
     torch.cuda.synchronize(dev)
 
     # ---- device-timed region (inputs resident in HBM)
-    sampler = ClockSampler(local)
     vdist.barrier()
     torch.cuda.synchronize(dev)
-    sampler.start()
     lib.vt_launch_count(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

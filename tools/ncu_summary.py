@@ -36,8 +36,8 @@ if os.path.exists(path):
         agg[name][1] += ns
     tot = sum(v[1] for v in agg.values())
     with open(os.path.join(out_dir, f"launches_{tag}.md"), "w") as f:
-        f.write(f"# ncu launch list, round {tag}\n\n`ncu --metrics gpu__time_duration.sum --clock-control none` over `python tools/ncu_target.py 8 2`\n"
-                "(model build + weight packing + 2 forwards of 8 clips 17x256x256, bf16).  Times are cold-cache and serialised:\n"
+        f.write(f"# ncu launch list, round {tag}\n\n`ncu --metrics gpu__time_duration.sum --clock-control none` over `python bench.py --steps 2 --warmup 3 --no-cpu-baseline`\n"
+                "(model build + weight packing + PSNR check + device-resident and end-to-end steps of 8 clips 17x256x256, bf16).  Times are cold-cache and serialised:\n"
                 "compare SHARES, not absolutes.\n\n| kernel | launches | total ms | share |\n|---|---:|---:|---:|\n")
         for k, (n, ns) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| `{k}` | {n} | {ns / 1e6:.3f} | {100 * ns / tot:.1f}% |\n")
