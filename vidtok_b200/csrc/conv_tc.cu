@@ -362,7 +362,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
   float* sbias = reinterpret_cast<float*>(smem_gen + (bias_base - smem_base));   // [2][bias 256 | gamma 256 | beta 256]
-  float* stat_s = sbias + 2 * 768;                                                // [2 groups][128 rows][sum, sumsq]
+  float* stat_s = sbias + 2 * 768;                                                // [tile parity][2 groups][128 rows][sum, sumsq]
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&maps.a[0]);
@@ -810,10 +810,13 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           upk2(lsq2, a, b); lsq = a + b;
         }
         if (p.MT == 1) {  // the other group holds the other slices of the row
-          float* xs = stat_s + ((grp * 128 + rr) << 1);
+          // double-buffered by tile parity: the partner group reads right after the barrier, this group may already be
+          // writing the next tile's statistics
+          float* st_ = stat_s + (it & 1u) * 512u;
+          float* xs = st_ + ((grp * 128 + rr) << 1);
           xs[0] = lsum; xs[1] = lsq;
           asm volatile("bar.sync 2, %0;" ::"n"(kEpiWarps * 32) : "memory");
-          const float* ys = stat_s + ((((grp ^ 1) * 128) + rr) << 1);
+          const float* ys = st_ + ((((grp ^ 1) * 128) + rr) << 1);
           lsum += ys[0]; lsq += ys[1];
         }
         const float mean = lsum * inv_n;
@@ -1079,7 +1082,7 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   const int bn_local = t.pair ? t.BN / 2 : t.BN;
   const size_t stage_bytes = (t.halo ? 0 : (size_t)t.MT * kABytes) + (size_t)bn_local * 128;
   const size_t budget = 222 * 1024;
-  const size_t fixed = 1024 /*align*/ + 8 * 2 * 8 + 64 + 2 * 768 * 4 + 2 * 128 * 2 * 4 + 256;
+  const size_t fixed = 1024 /*align*/ + 8 * 2 * 8 + 64 + 2 * 768 * 4 + 2 * 2 * 128 * 2 * 4 + 256;
   const size_t a_ring = (size_t)t.a_stages * t.halo_bytes;
   // one staging buffer per epilogue warp: a second one (VT_TC_STG=2, if the ring keeps >= 3 stages) costs operand
   // stages, which was measured to matter more (model step 143.3 -> 140.6 ms, profiles/notes_r1.md)
