@@ -5,7 +5,7 @@
 // loading), every thread then writes im2col rows (81 values, bf16) straight into the canonical K-major
 // SWIZZLE_128B layout (16-byte unit u of row r lives at unit u ^ (r & 7)), fences the generic->async proxy, and one
 // thread issues 8 tcgen05.mma (M=128, N=Cout, K=128 with zero padding).  The epilogue adds the bias and writes the
-// bf16 channels-last activation.  The kernel is HBM-bound on its 2*Cout bytes/position output.
+// bf16 channels-last activation.  The patch loads of tile i+1 are in flight (registers) during the epilogue of tile i.
 #include <cstdio>
 
 #include "common.cuh"
@@ -31,6 +31,7 @@ struct StemParams {
 constexpr int BW = 16, BH = 8;
 constexpr int PW = BW + 2, PH = BH + 2;
 constexpr int kATile = 2 * 128 * 128;  // two 64-wide K chunks of 128 rows x 128 B
+constexpr int kPatchIt = 9;            // patch values per thread: Ci * 3 * PH * PW <= 4 * 540 = 2160 <= 9 * 256
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -132,35 +133,49 @@ __global__ void __launch_bounds__(256, 1) conv_stem_kernel(const StemParams p, c
     h0 = th * BH;
     w0 = tw * BW;
   };
-  // stage the halo patch and write the im2col rows of one tile into A buffer `buf`
-  auto build = [&](long long tile, int buf) {
+  // Halo patch of one tile: the global loads are issued back to back into registers (kPatchIt per thread) so that their
+  // latency overlaps the epilogue of the previous tile; they are stored to shared memory afterwards.
+  auto load_patch = [&](long long tile, float (&pv)[kPatchIt]) {
     int b, t, h0, w0;
     decode(tile, b, t, h0, w0);
-    for (uint32_t i = tid; i < patch_floats; i += 256) {
-      const int ww = i % PW;
-      uint32_t r = i / PW;
-      const int hh = r % PH;
-      r /= PH;
-      const int a = r % 3, ci = r / 3;
-      const int hv = h0 + hh - 1, wv = w0 + ww - 1;
-      int tv = t + a - 2;  // virtual time axis: [t_rep copies of frame 0][T frames]
+#pragma unroll
+    for (int k = 0; k < kPatchIt; ++k) {
+      const uint32_t i = (uint32_t)tid + (uint32_t)k * 256u;
       float v = 0.f;
-      bool ok = hv >= 0 && hv < p.H && wv >= 0 && wv < p.W;
-      if (tv < 0 && p.t_mode == 2) {
-        if (ok) v = p.cache[((((long long)b * p.Ci + ci) * 2 + (2 + tv)) * p.H + hv) * p.W + wv];
-        ok = false;
-      } else if (tv < 0) {
-        if (p.t_mode == 0) ok = false;
-        tv = 0;
+      if (i < patch_floats) {
+        const int ww = i % PW;
+        uint32_t r = i / PW;
+        const int hh = r % PH;
+        r /= PH;
+        const int a = r % 3, ci = r / 3;
+        const int hv = h0 + hh - 1, wv = w0 + ww - 1;
+        int tv = t + a - 2;  // virtual time axis: [t_rep copies of frame 0][T frames]
+        bool ok = hv >= 0 && hv < p.H && wv >= 0 && wv < p.W;
+        if (tv < 0 && p.t_mode == 2) {
+          if (ok) v = p.cache[((((long long)b * p.Ci + ci) * 2 + (2 + tv)) * p.H + hv) * p.W + wv];
+          ok = false;
+        } else if (tv < 0) {
+          if (p.t_mode == 0) ok = false;
+          tv = 0;
+        }
+        if (ok) {
+          int ti = tv - p.t_rep;
+          ti = ti < 0 ? 0 : ti;
+          v = p.x[((((long long)b * p.Ci + ci) * p.T + ti) * p.H + hv) * p.W + wv];
+        }
       }
-      if (ok) {
-        int ti = tv - p.t_rep;
-        ti = ti < 0 ? 0 : ti;
-        v = p.x[((((long long)b * p.Ci + ci) * p.T + ti) * p.H + hv) * p.W + wv];
-      }
-      patch[i] = v;
+      pv[k] = v;
     }
-    __syncthreads();
+  };
+  auto store_patch = [&](const float (&pv)[kPatchIt]) {
+#pragma unroll
+    for (int k = 0; k < kPatchIt; ++k) {
+      const uint32_t i = (uint32_t)tid + (uint32_t)k * 256u;
+      if (i < patch_floats) patch[i] = pv[k];
+    }
+  };
+  // im2col rows of the staged patch into A buffer `buf` (canonical K-major SWIZZLE_128B layout)
+  auto im2col = [&](int buf) {
     const int row = tid & 127, half = tid >> 7;
     const int dh = row / BW, dw = row % BW;
     const float* prow = patch + dh * PW + dw;
@@ -234,18 +249,26 @@ __global__ void __launch_bounds__(256, 1) conv_stem_kernel(const StemParams p, c
 
   long long tile = blockIdx.x;
   uint32_t it = 0;
+  float pv[kPatchIt];
   if (tile < p.num_tiles) {
-    build(tile, 0);
+    load_patch(tile, pv);
+    store_patch(pv);
+    __syncthreads();
+    im2col(0);
     __syncthreads();
     issue(0);
   }
   for (; tile < p.num_tiles; tile += gridDim.x, ++it) {
     const long long next = tile + gridDim.x;
+    const bool has_next = next < p.num_tiles;
     const int buf = it & 1;
-    if (next < p.num_tiles) build(next, buf ^ 1);   // overlaps the MMA of `tile`
+    if (has_next) load_patch(next, pv);     // loads in flight across the epilogue
     epilogue(tile, buf, (it >> 1) & 1u);
+    if (has_next) store_patch(pv);
     __syncthreads();
-    if (next < p.num_tiles) issue(buf ^ 1);
+    if (has_next) im2col(buf ^ 1);
+    __syncthreads();
+    if (has_next) issue(buf ^ 1);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
