@@ -220,11 +220,37 @@ def run_b200_arm(args):
         with torch.no_grad():
             return model(x_dev)
 
-    def step_e2e():
+    # End-to-end leg: the call a user makes (model(x) on the current stream) with every step's input coming from pinned host
+    # memory and every step's reconstruction going back to pinned host memory.  The copies run on a second stream, double
+    # buffered: H2D of step k+1 and D2H of step k-1 overlap the kernels of step k (each step's copies stay inside the timed
+    # region: the first H2D and the last D2H are not hidden).
+    copy_stream = torch.cuda.Stream(device=dev)
+    in_bufs = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
+
+    def run_e2e(steps):
+        main = torch.cuda.current_stream(dev)
+        ready = [torch.cuda.Event(), torch.cuda.Event()]   # input buffer i holds its step's clip
+        freed = [torch.cuda.Event(), torch.cuda.Event()]   # the step that read input buffer i has finished
+        dec = None
         with torch.no_grad():
-            xd = x_host.to(dev, non_blocking=True)
-            _, dec, _ = model(xd)
-            out_host.copy_(dec, non_blocking=True)
+            with torch.cuda.stream(copy_stream):
+                in_bufs[0].copy_(x_host, non_blocking=True)
+                ready[0].record(copy_stream)
+            for k in range(steps):
+                cur = k & 1
+                main.wait_event(ready[cur])
+                _, dec, _ = model(in_bufs[cur])
+                freed[cur].record(main)
+                dec.record_stream(copy_stream)
+                with torch.cuda.stream(copy_stream):
+                    if k + 1 < steps:
+                        if k >= 1:
+                            copy_stream.wait_event(freed[cur ^ 1])
+                        in_bufs[cur ^ 1].copy_(x_host, non_blocking=True)
+                        ready[cur ^ 1].record(copy_stream)
+                    copy_stream.wait_event(freed[cur])
+                    out_host.copy_(dec, non_blocking=True)
+        main.wait_stream(copy_stream)
         return dec
 
     # the clock sampler starts BEFORE the warm-up: nvidia-smi takes ~1 s to initialise NVML, and doing that inside the
@@ -254,14 +280,12 @@ def run_b200_arm(args):
     value = frames / (ms / 1e3)
 
     # ---- end to end through the public API with host buffers
-    for _ in range(2):
-        step_e2e()
+    run_e2e(2)
     torch.cuda.synchronize(dev)
     vdist.barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
-    for _ in range(args.steps):
-        step_e2e()
+    dec = run_e2e(args.steps)
     e3.record()
     torch.cuda.synchronize(dev)
     vdist.barrier()
@@ -341,7 +365,9 @@ def run_b200_arm(args):
                        "weights": "random (synth_state_dict seed 0)", "l2": "per-step activations are GBs, far larger than the 126 MB L2"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": nbytes + 4 * B * 4 * 5 * 32 * 32, "d2h_bytes_per_step": nbytes},
+                    "h2d_bytes_per_step": nbytes + 4 * B * 4 * 5 * 32 * 32, "d2h_bytes_per_step": nbytes,
+                    "pipeline": "every step copies its clips from pinned host memory and its reconstruction back; the copies run on a "
+                                "second stream, double buffered against the previous / next step's kernels"},
             "gpu_launches": launches,
             "roofline": roof,
             "cpu_baseline": cpu,
