@@ -4,13 +4,17 @@
 //   M = output positions, tiled as boxes of BT x BH x BW = 128 positions (one UMMA M=128 tile),
 //   N = Cout tile (BN <= 256 TMEM columns, fp32 accumulators, double-buffered: 2*BN columns),
 //   K = taps x Cin, consumed in steps of 64 channels (one 128-byte swizzle row) per tap.
-// A operand: for every (tap, 64-channel chunk) ONE 5-D TMA box load of the shifted input window
-//   {64, BW, BH, BT, 1} at (c0, w0+dw, h0+dh, t, b): spatial/temporal zero padding is the TMA out-of-bounds
-//   fill, the causal front pad is either skipped taps (zeros), a clamped coordinate (replicate, v1.1 first chunk)
-//   or a second tensor map over the per-layer cache (v1.1 later chunks).  No im2col buffer, no padded copy.
-// B operand: 2-D TMA box {64, BN} of the pre-packed K-major bf16 weights [Cout][taps*Cin].
-// Both land in shared memory in the canonical K-major SWIZZLE_128B layout and feed
-// tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) issued by one thread; accumulators live in TMEM.
+// A operand, two formulations:
+//   * halo mode (stride-1 kh x kw > 1 layers): ONE 5-D TMA box per (time tap, 64-channel chunk) loads the CTA tile's input
+//     window with its spatial halo; the kh*kw taps are UMMA descriptors that start (bb*hP + c) 128-byte rows into it
+//     (TcParams::halo).  ~3x fewer activation bytes cross L2 -> SM.
+//   * otherwise one box {64, BW, BH, BT, 1} at (c0, w0+dw, h0+dh, t, b) per (tap, 64-channel chunk).
+//   In both, spatial/temporal zero padding is the TMA out-of-bounds fill; the causal front pad is either skipped taps
+//   (zeros), a clamped coordinate (replicate, v1.1 first chunk) or a second tensor map over the per-layer cache (v1.1
+//   later chunks).  No im2col buffer, no padded copy.
+// B operand: TMA box {64, BN} of the pre-packed K-major bf16 weights [Cout][taps*Cin] (half of it per CTA in pair mode).
+// Both land in shared memory in the canonical K-major SWIZZLE_128B layout and feed tcgen05.mma.kind::f16 (K=16):
+// cta_group::1 with M=128, or cta_group::2 with M=256 across a CTA pair (template kPair); accumulators live in TMEM.
 // Warp roles (persistent CTA, one per SM): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator,
 // warps 3-10 = epilogue (tcgen05.ld -> bias / residual / mix / LayerNorm -> bf16 -> per-warp swizzled staging -> TMA
 // store), overlapping the next tile's main loop through the second TMEM accumulator stage.
@@ -932,8 +936,7 @@ void conv_tc_set_pair(bool on) { g_pair_mode = on ? 1 : 0; }
 // diagnostics: how many 2-CTA clusters of conv_tc_kernel can be co-resident with `smem` dynamic bytes per CTA
 int conv_tc_cluster_query(int smem, char* msg, int cap) {
   cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(148);
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
@@ -1208,8 +1211,7 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   ProfScope _ps("conv_tc", 2.0 * Mrows * p.kt * p.kh * p.kw * p.Ci * p.Co,
                 2.0 * ((double)p.B * p.Ti * p.Hi * p.Wi * p.Ci) + Mrows * p.Co * (tout == DT_F32 ? 4.0 : 2.0), s, det);
   if (t.pair) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
