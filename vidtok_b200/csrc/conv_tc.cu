@@ -82,6 +82,7 @@ struct TcParams {
   // clipped by the tensor bounds)
   int tma_store;
   int stg_bufs;              // staging buffers per warp (4 KB each): 2 when shared memory allows, else 1
+  int store_stream;          // TMA stores carry an L2 evict-first hint (outputs much larger than L2)
   uint32_t stage_off;        // byte offset of the staging buffers [8 warps][stg_bufs][4 KB] from the aligned smem base
   // cta_group::2: two CTAs of a cluster (one TPC) work on one 2*MT*128-row tile; each loads its own rows of A and half of
   // the B (weight) rows, the leader issues M=256 MMAs that read both halves -> weight bytes per FLOP are halved again
@@ -163,6 +164,18 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
   asm volatile(
       "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+      ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+// same with an L2 evict-first policy: results far larger than L2 are not re-read before they would be evicted anyway, and
+// should not push the input frames that neighbouring taps / tiles still need out of the cache
+__device__ __forceinline__ void tma_store_5d_stream(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b64 pol;\n\t"
+      "createpolicy.fractional.L2::evict_first.b64 pol, 1.0;\n\t"
+      "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5, %6}], [%1], pol;\n\t"
+      "}"
       ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
@@ -692,7 +705,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         __syncwarp();
         if (lane == 0) {
           const uint32_t b = (p.stg_bufs == 2) ? (nstore & 1u) : 0u;
-          tma_store_5d(m, wstg + b * 4096u, c0, tc.w0 + qw0, tc.h0 + qh0, tc.t0 + qt0, tc.b);
+          if (p.store_stream) tma_store_5d_stream(m, wstg + b * 4096u, c0, tc.w0 + qw0, tc.h0 + qh0, tc.t0 + qt0, tc.b);
+          else tma_store_5d(m, wstg + b * 4096u, c0, tc.w0 + qw0, tc.h0 + qh0, tc.t0 + qt0, tc.b);
           tma_store_commit();
         }
         ++nstore;
@@ -1079,6 +1093,12 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
     // the staging buffers cost a pipeline stage; long-K layers hide the direct-store epilogue behind their main loop
     int ntaps_eff = p.kt * p.kh * p.kw;
     if (ntaps_eff * t.num_kc >= 48) t.tma_store = 0;
+  }
+  {
+    static int ev_env = -1;   // VT_TC_EVICT=0: experiment knob
+    if (ev_env < 0) { const char* e = getenv("VT_TC_EVICT"); ev_env = e ? atoi(e) : 1; }
+    const double out_bytes = (double)p.B * p.To * p.Ho * p.Wo * p.Co * 2.0;
+    t.store_stream = (ev_env && out_bytes > 256e6) ? 1 : 0;
   }
   t.res_mma = (p.res_mode == 1 && p.ra == 1.0f && p.rb == 1.0f && t.BN % 64 == 0 && p.Co % 64 == 0 && p.rsW % 8 == 0 && p.rsH % 8 == 0 &&
                p.rsT % 8 == 0 && p.rsB % 8 == 0 && (((uintptr_t)p.res) & 15) == 0) ? 1 : 0;
