@@ -1,13 +1,19 @@
 #!/usr/bin/env python
-"""Benchmark of the tokenizer hot path: frames/sec for full encode -> regularize -> decode of
-vidtok_kl_causal_488_4chn on synthetic 17x256x256 clips (BASELINE.json metric, configs[1]).
+"""Benchmark of the tokenizer hot path: frames/sec for full encode -> regularize -> decode on synthetic clips.
 
-  python bench.py --gpus N --steps K --warmup W            # B200 arm (one process per GPU under torchrun for N > 1)
-  python bench.py --impl reference --gpus N --steps K ...  # reference arm: the reference's CPU path (oracle port)
+  python bench.py --gpus N --steps K --warmup W                       # B200 arm, BASELINE.json configs[1] (the headline)
+  python bench.py --config {kl488,fsq488,v11long,kl41616} [--precision {bf16,exact,mixed,fma}]
+  python bench.py --impl reference [--config ...] --steps K ...        # reference arm: the reference's CPU path (oracle port)
 
-A "step" is one pass of the hot path over one batch of 8 clips per GPU (weak scaling).  `value` is timed with CUDA
-events with the inputs already resident in HBM; `e2e` goes through the public Python API
-(vidtok.models.autoencoder.AutoencodingEngine.forward) from pinned host memory and back.  One JSON line on rank 0.
+A "step" is one pass of the hot path over one batch of clips per GPU (weak scaling; one process per GPU under torchrun for
+N > 1).  `value` is timed with CUDA events with the inputs already resident in HBM; `e2e` goes through the public Python API
+(AutoencodingEngine.forward resolved from the YAML target strings) from pinned host memory and back.  One JSON line on rank 0.
+
+configs (BASELINE.json `configs`):
+  kl488    [1] vidtok_kl_causal_488_4chn, 8 clips 17x256x256 per GPU, bf16 (default: the metric BASELINE.json is quoted on)
+  fsq488   [2] vidtok_fsq_causal_488_32768, 8 clips 17x256x256 per GPU, "mixed" = encoder bf16x3 (bit-exact codes), decoder bf16
+  v11long  [3] vidtok_kl_causal_488_16chn v1.1, one 129x256x256 video per GPU, tiled t_chunk_enc=16 with overlap, bf16
+  kl41616  [4] vidtok_kl_causal_41616_4chn, 4 clips 17x512x512 per GPU (32 clips over 8 GPUs), bf16
 """
 from __future__ import annotations
 
@@ -26,25 +32,57 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 METRIC = "frames/sec encode+decode, kl_causal_488 17x256x256"
-FLOPS_PER_CLIP = 20.691e12  # BASELINE.md section 2 (FlopCounterMode over the reference graph)
-T_CLIP, H_CLIP, W_CLIP = 17, 256, 256
+
+# flops: algorithmic FLOPs per clip / video (FlopCounterMode over the reference graph)
+CONFIGS = {
+    "kl488": dict(idx=1, name="vidtok_kl_causal_488_4chn", metric=METRIC, version="v1_0", reg="kl", z=4, ch_mult=(1, 2, 4, 4),
+                  T=17, H=256, W=256, batch=8, flops=20.691e12, precision="bf16", tiling=None),
+    "fsq488": dict(idx=2, name="vidtok_fsq_causal_488_32768", metric="frames/sec encode+decode, fsq_causal_488_32768 17x256x256",
+                   version="v1_0", reg="fsq", z=5, ch_mult=(1, 2, 4, 4), T=17, H=256, W=256, batch=8, flops=20.690e12,
+                   precision="mixed", tiling=None),
+    "v11long": dict(idx=3, name="vidtok_kl_causal_488_16chn v1.1", metric="frames/sec encode+decode, kl_causal_488_16chn_v1_1 129x256x256 tiled",
+                    version="v1_1", reg="kl", z=16, ch_mult=(1, 2, 4, 4), T=129, H=256, W=256, batch=1, flops=160.38e12,
+                    precision="bf16", tiling=(16, 4, True)),
+    "kl41616": dict(idx=4, name="vidtok_kl_causal_41616_4chn", metric="frames/sec encode+decode, kl_causal_41616 17x512x512",
+                    version="v1_0", reg="kl", z=4, ch_mult=(1, 2, 4, 4, 4), T=17, H=512, W=512, batch=4, flops=85.627e12,
+                    precision="bf16", tiling=None),
+}
+DTYPE_OF = {"bf16": "bf16", "exact": "bf16x3 (hi|lo split bf16 operands, fp32-class results)", "mixed": "encoder bf16x3, decoder bf16",
+            "fma": "f32"}
 
 
-def model_cfg(ch=128):
-    """configs/vidtok_kl_causal_488_4chn.yaml:1-36 (model section)."""
-    ep = dict(double_z=True, z_channels=4, in_channels=3, out_ch=3, ch=ch, ch_mult=[1, 2, 4, 4],
+def model_cfg(c, ch=128):
+    """model section of configs/<name>.yaml (e.g. configs/vidtok_kl_causal_488_4chn.yaml:1-36)."""
+    v11 = c["version"] == "v1_1"
+    ep = dict(double_z=(c["reg"] == "kl"), z_channels=c["z"], in_channels=3, out_ch=3, ch=ch, ch_mult=list(c["ch_mult"]),
               time_downsample_factor=4, num_res_blocks=2, dropout=0.0, use_checkpoint=False,
               init_pad_mode="replicate", norm_type="layernorm", fix_encoder=False, fix_decoder=False)
+    if v11:
+        ep["interpolation_mode"] = "trilinear"   # configs/vidtok_v1_1/*.yaml:27
+    mod = "vidtok.modules.model_3dcausal_v1_1" if v11 else "vidtok.modules.model_3dcausal"
+    if c["reg"] == "fsq":
+        rc = {"target": "vidtok.modules.regularizers.FSQRegularizer",
+              "params": {"levels": [8, 8, 8, 8, 8], "entropy_loss_weight": 0.1, "entropy_loss_annealing_factor": 1.2,
+                         "commitment_loss_weight": 0.25}}
+    else:
+        rc = {"target": "vidtok.modules.regularizers.DiagonalGaussianRegularizer"}
     return {
-        "target": "vidtok.models.autoencoder.AutoencodingEngine",
+        "target": "vidtok.models.autoencoder_v1_1.AutoencodingEngine" if v11 else "vidtok.models.autoencoder.AutoencodingEngine",
         "params": {
             "monitor": "val/rec_loss", "mode": "min", "ignore_keys": [],
-            "encoder_config": {"target": "vidtok.modules.model_3dcausal.EncoderCausal3DPadding", "params": ep},
-            "decoder_config": {"target": "vidtok.modules.model_3dcausal.DecoderCausal3DPadding", "params": dict(ep)},
-            "regularizer_config": {"target": "vidtok.modules.regularizers.DiagonalGaussianRegularizer"},
+            "encoder_config": {"target": mod + ".EncoderCausal3DPadding", "params": ep},
+            "decoder_config": {"target": mod + ".DecoderCausal3DPadding", "params": dict(ep)},
+            "regularizer_config": rc,
             "loss_config": {"target": "vidtok.modules.losses.GeneralLPIPSWithDiscriminator"},
         },
     }
+
+
+def workload_string(c, precision, B):
+    what = f"{c['name']} {precision}: batch {B} clip{'s' if B > 1 else ''} {c['T']}x{c['H']}x{c['W']} per GPU"
+    if c["tiling"]:
+        what += f", tiled t_chunk_enc={c['tiling'][0]} t_chunk_dec={c['tiling'][1]} use_overlap={c['tiling'][2]}"
+    return what + f" (BASELINE.json configs[{c['idx']}])"
 
 
 def load_peaks():
@@ -101,18 +139,26 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------
-# CPU reference (oracle port of the reference's PyTorch CPU path)
+# CPU reference (oracle port of the reference's PyTorch CPU path).  No CUDA library is touched here: the weight shapes
+# come from the oracle's parameter table (pinned against the reference's state_dict in tests/test_oracle_golden.py).
 # --------------------------------------------------------------------------------------------------
-def oracle_model(sd):
-    from oracle.vidtok_oracle import OracleModel, cfg_from_model_yaml
-    return OracleModel(cfg_from_model_yaml(model_cfg()), sd)
+def oracle_model(c, sd=None):
+    from oracle.vidtok_oracle import OracleModel, cfg_from_model_yaml, reference_param_shapes
+    from vidtok_b200.synth import synth_state_dict
+    ocfg = cfg_from_model_yaml(model_cfg(c))
+    if sd is None:
+        sd = synth_state_dict(reference_param_shapes(ocfg), seed=0)
+    om = OracleModel(ocfg, sd)
+    if c["tiling"]:
+        om.use_tiling, om.t_chunk_enc, om.t_chunk_dec, om.use_overlap = True, c["tiling"][0], c["tiling"][1], c["tiling"][2]
+    return om
 
 
 def cpu_forward_timed(om, x, noise_seed=4321):
     torch.manual_seed(noise_seed)
     t0 = time.perf_counter()
-    z, dec, _ = om.forward(x)
-    return time.perf_counter() - t0, dec
+    z, dec, log = om.forward(x)
+    return time.perf_counter() - t0, dec, log
 
 
 def pick_cpu_threads(om):
@@ -124,15 +170,13 @@ def pick_cpu_threads(om):
         cores = min(cores, len(os.sched_getaffinity(0)))
     except Exception:
         pass
-    x = synth_clip(1, T_CLIP, 32, 32)
+    x = synth_clip(1, 17, 32, 32)
     best_t, best_n = None, cores
     for n in sorted({cores, max(cores // 2, 1), max(cores // 4, 1), 32, 16, 8}):
         if n > cores:
             continue
         torch.set_num_threads(n)
-        t, _ = cpu_forward_timed(om, x)
-        t2, _ = cpu_forward_timed(om, x)
-        t = min(t, t2)
+        t = min(cpu_forward_timed(om, x)[0], cpu_forward_timed(om, x)[0])
         if best_t is None or t < best_t:
             best_t, best_n = t, n
         elif t > 1.5 * best_t:  # more threads only oversubscribe from here on
@@ -141,48 +185,53 @@ def pick_cpu_threads(om):
     return best_n
 
 
-def pick_cpu_sample(om, budget_s: float, steps: int):
-    """Largest sample clip (17 x S x S, S in 256/128/64) whose `steps` forwards fit the budget, from a 64x64 probe."""
+def cpu_sample_shape(c, om, budget_s: float, steps: int):
+    """Largest sample (T_s x S x S) of the config's workload whose `steps` forwards fit the budget, from a 64x64 probe.
+    The spatial size shrinks first (256/512 -> 128 -> 64); the tiled long video also shrinks to 33 frames (three chunks:
+    first frame, two full chunks with look-ahead)."""
     from vidtok_b200.synth import synth_clip
-    t_probe, _ = cpu_forward_timed(om, synth_clip(1, T_CLIP, 64, 64))
-    t_probe2, _ = cpu_forward_timed(om, synth_clip(1, T_CLIP, 64, 64))
-    t64 = min(t_probe, t_probe2)
-    for S in (256, 128, 64):
+    T_s = c["T"] if not c["tiling"] else 33
+    t64 = min(cpu_forward_timed(om, synth_clip(1, T_s, 64, 64))[0], cpu_forward_timed(om, synth_clip(1, T_s, 64, 64))[0])
+    sizes = [s for s in (c["H"], 256, 128, 64) if s <= c["H"]]
+    for S in dict.fromkeys(sizes):
         if t64 * (S / 64) ** 2 * steps <= budget_s:
-            return S
-    return 64
+            return T_s, S
+    return T_s, 64
 
 
-def run_reference_arm(args):
+def cpu_units_scale(c, T_s, S):
+    """frames of the full-size workload that one sample forward is worth (pixel-count scaling; stated in `sample`)"""
+    return (T_s * S * S) / float(c["T"] * c["H"] * c["W"]) * c["T"]
+
+
+def run_reference_arm(args, c):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from vidtok_b200.compat_util import instantiate_from_config  # noqa: F401  (manifest source for weight shapes)
-    from vidtok_b200.engine import NativeModel, TokenizerSpec
-    from vidtok_b200.synth import synth_clip, synth_state_dict
-    spec = TokenizerSpec.from_params(model_cfg()["params"]["encoder_config"]["params"], 0)
-    sd = synth_state_dict(dict(NativeModel(spec).manifest()), seed=0)
-    om = oracle_model(sd)
+    from vidtok_b200.synth import synth_clip
+    om = oracle_model(c)
     cores = pick_cpu_threads(om)
     total = args.steps + args.warmup
-    S = pick_cpu_sample(om, budget_s=240.0, steps=total)
-    x = synth_clip(1, T_CLIP, S, S)
+    T_s, S = cpu_sample_shape(c, om, budget_s=240.0, steps=total)
+    x = synth_clip(1, T_s, S, S)
     for _ in range(args.warmup):
         cpu_forward_timed(om, x)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         cpu_forward_timed(om, x)
     el = time.perf_counter() - t0
-    scale = (S * S) / float(H_CLIP * W_CLIP)
-    fps = T_CLIP * args.steps / el * scale
-    sample = f"1 clip 3x{T_CLIP}x{S}x{S} per step on {cores} host threads of {os.cpu_count()} visible (oracle port of the reference PyTorch CPU path)"
-    if S != 256:
-        sample += f"; value scaled by the pixel ratio {scale:.4f} to 256x256-frame units"
+    fps = cpu_units_scale(c, T_s, S) * args.steps / el
+    full = (T_s, S) == (c["T"], c["H"])
+    sample = f"1 clip 3x{T_s}x{S}x{S} per step on {cores} host threads of {os.cpu_count()} visible (oracle port of the reference PyTorch CPU path, fp32)"
+    if not full:
+        sample += (f"; a full-size {c['T']}x{c['H']}x{c['W']} step does not fit the few-minute budget of {total} steps on the CPU, so the value is the "
+                   f"sample's voxels/s converted to {c['H']}x{c['W']}-frame units (x{(S * S) / float(c['H'] * c['W']):.4f} per frame)")
     line = {
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": c["metric"], "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "vidtok_kl_causal_488_4chn: clips 17x256x256 (reference CPU path, fp32)", "sample": sample},
+        "config": {"workload": f"{c['name']}: clips {c['T']}x{c['H']}x{c['W']} (reference CPU path, fp32; BASELINE.json configs[{c['idx']}])",
+                   "sample": sample, "full_size_step": full},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -192,7 +241,9 @@ def run_reference_arm(args):
 # --------------------------------------------------------------------------------------------------
 # B200 arm
 # --------------------------------------------------------------------------------------------------
-def run_b200_arm(args):
+def run_b200_arm(args, c):
+    import __graft_entry__ as ge
+    ge.build()
     from vidtok_b200 import _native as N
     from vidtok_b200 import dist as vdist
     from vidtok_b200.compat_util import instantiate_from_config
@@ -203,15 +254,21 @@ def run_b200_arm(args):
     rank, world, local = vdist.init_from_env("nccl")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    B = args.batch
-    model = instantiate_from_config(model_cfg())
+    B = args.batch or c["batch"]
+    T, H, W = c["T"], c["H"], c["W"]
+    precision = args.precision or c["precision"]
+    model = instantiate_from_config(model_cfg(c))
     sd = synth_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed=0)
     model.load_state_dict(sd)
     model = model.to(dev).eval()
-    model.precision = "bf16"
+    model.precision = precision
+    if c["tiling"]:
+        # exactly what scripts/inference_evaluate.py:144-150 does
+        model.use_tiling = True
+        model.t_chunk_enc, model.t_chunk_dec, model.use_overlap = c["tiling"]
     lib = N.lib()
 
-    x_host = synth_clip(B, T_CLIP, H_CLIP, W_CLIP, seed=1234 + rank).pin_memory()
+    x_host = synth_clip(B, T, H, W, seed=1234 + rank).pin_memory()
     out_host = torch.empty_like(x_host).pin_memory()
     x_dev = x_host.to(dev)
     torch.manual_seed(4321)
@@ -276,7 +333,7 @@ def run_b200_arm(args):
     clocks = sampler.stop()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     ms = float(vdist.allreduce_max(ms)[0])
-    frames = world * B * T_CLIP * args.steps
+    frames = world * B * T * args.steps
     value = frames / (ms / 1e3)
 
     # ---- end to end through the public API with host buffers
@@ -294,21 +351,22 @@ def run_b200_arm(args):
     e2e_value = frames / (ms_e2e / 1e3)
 
     # ---- the one collective: global PSNR(input, reconstruction) from per-rank partial sums (NCCL all-reduce)
-    psnr_b200 = vdist.global_psnr(vdist.psnr_partial(x_dev, dec))
+    psnr_b200 = vdist.global_psnr(vdist.psnr_partial(x_dev, dec.float()))
 
     # ---- per-kernel attribution of one step (CUDA events around every launch, on the launch stream)
     peaks = load_peaks()
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "ncu_conv_tc_r1.json")
-    if os.path.exists(tpath):  # dram__bytes_read+write per launch from the committed `ncu --set full` capture
+    tpath = os.path.join(ROOT, "profiles", "ncu_conv_tc_r2.json")
+    if not os.path.exists(tpath):
+        tpath = os.path.join(ROOT, "profiles", "ncu_conv_tc_r1.json")
+    if os.path.exists(tpath) and args.config == "kl488":  # dram__bytes_read+write per launch from the committed `ncu --set full` capture
         try:
             cap = json.load(open(tpath))
             vals = [l["dram_read_bytes"] + l["dram_write_bytes"] for l in cap["launches"] if l.get("dram_read_bytes") is not None]
-            traffic = {"bytes_per_launch_avg": sum(vals) / len(vals), "launches_captured": len(vals), "source": "profiles/ncu_conv_tc_r1.json"}
+            traffic = {"bytes_per_launch_avg": sum(vals) / len(vals), "launches_captured": len(vals), "source": os.path.relpath(tpath, ROOT)}
         except Exception:
             traffic = None
     roof = None
-    prof = {}
     if rank == 0:
         lib.vt_profile_start()
         step_resident()
@@ -326,52 +384,63 @@ def run_b200_arm(args):
                     "frac": ach / peak, "traffic": traffic, "launches_per_step": d["launches"],
                     "avg_launch_ms": d["ms"] / max(d["launches"], 1), "share_of_step": d["ms"] / tot_ms,
                     "algorithmic_flops_per_step": d["flops"], "peak_source": peaks["source"],
-                    "whole_path": {"achieved": FLOPS_PER_CLIP * world * B * args.steps / (ms / 1e3) / 1e12 / world, "unit": "TFLOP/s per GPU",
-                                   "frac": FLOPS_PER_CLIP * B * args.steps / (ms / 1e3) / 1e12 / peaks["tflops"]},
+                    "note": ("achieved = algorithmic FLOPs of the kernel's launches / their summed durations; conv_tc3 (bf16x3) executes "
+                             "3 tensor-core MACs per algorithmic MAC, so its ceiling against the bf16 peak is 1/3"),
+                    "whole_path": {"achieved": c["flops"] * B * args.steps / (ms / 1e3) / 1e12, "unit": "TFLOP/s per GPU (algorithmic)",
+                                   "frac": c["flops"] * B * args.steps / (ms / 1e3) / 1e12 / peaks["tflops"]},
+                    "sum_kernel_ms": tot_ms,
                     "kernels_ms": {k: round(v["ms"], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}}
 
-    # ---- CPU baseline + PSNR parity on clip 0 (rank 0, N == 1 only)
+    # ---- CPU baseline + parity on one sample (rank 0, N == 1 only): PSNR for KL, code mismatches for FSQ
     cpu = None
-    psnr = {"b200_all_clips": psnr_b200}
+    parity = {"psnr_b200_all_clips": psnr_b200}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        om = oracle_model(sd)
+        om = oracle_model(c, sd)
         cores = pick_cpu_threads(om)
-        S = pick_cpu_sample(om, budget_s=40.0, steps=1)
-        xs = x_host[:1] if S == 256 else synth_clip(1, T_CLIP, S, S)
-        el, dec_ref = cpu_forward_timed(om, xs)
-        scale = (S * S) / float(H_CLIP * W_CLIP)
-        sample = f"1 clip 3x{T_CLIP}x{S}x{S}, 1 forward, fp32, {cores} host threads of {os.cpu_count()} visible (oracle port of the reference PyTorch CPU path)"
-        if S != 256:
-            sample += f"; value scaled by the pixel ratio {scale:.4f} to 256x256-frame units"
-        cpu = {"value": T_CLIP / el * scale, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
-        # PSNR gate on the same clip, same weights, same noise
+        T_s, S = cpu_sample_shape(c, om, budget_s=40.0, steps=1)
+        xs = x_host[:1] if (T_s, S) == (T, H) else synth_clip(1, T_s, S, S)
+        el, dec_ref, log_ref = cpu_forward_timed(om, xs)
+        sample = (f"1 clip 3x{T_s}x{S}x{S}, 1 forward, fp32, {cores} host threads of {os.cpu_count()} visible (oracle port of the "
+                  "reference PyTorch CPU path)")
+        if (T_s, S) != (T, H):
+            sample += f"; value = the sample's voxels/s in {H}x{W}-frame units"
+        cpu = {"value": cpu_units_scale(c, T_s, S) / el, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
         with torch.no_grad():
             torch.manual_seed(4321)
-            _, dec_g, _ = model(xs.to(dev))
+            _, dec_g, log_g = model(xs.to(dev))
         from vidtok_b200.dist import psnr_partial
-        pg = psnr_partial(xs, dec_g.cpu())
+        pg = psnr_partial(xs, dec_g.float().cpu())
         pr = psnr_partial(xs, dec_ref)
-        psnr.update({"clip": f"3x{T_CLIP}x{S}x{S}", "b200_bf16": float(pg[0] / pg[1]), "reference_cpu_fp32": float(pr[0] / pr[1]),
-                     "abs_diff_db": abs(float(pg[0] / pg[1]) - float(pr[0] / pr[1])), "gate_db": 0.01})
+        parity.update({"clip": f"3x{T_s}x{S}x{S}", "precision": precision, "psnr_b200": float(pg[0] / pg[1]),
+                       "psnr_reference_cpu_fp32": float(pr[0] / pr[1]),
+                       "psnr_abs_diff_db": abs(float(pg[0] / pg[1]) - float(pr[0] / pr[1])), "psnr_gate_db": 0.01,
+                       "max_abs_diff": float((dec_g.float().cpu() - dec_ref).abs().max())})
+        if c["reg"] == "fsq":
+            bad = log_g["indices"].cpu() != log_ref["indices"]
+            parity.update({"fsq_code_mismatches": int(bad.sum()), "fsq_codes": int(bad.numel()),
+                           "fsq_gate": "0 mismatches outside the 1e-4 tie band (tests/test_gpu_full.py::test_config3)"})
 
     if rank == 0:
         nbytes = x_host.numel() * x_host.element_size()
+        Tz = int(z.shape[2])
+        noise_bytes = 4 * B * c["z"] * Tz * int(z.shape[3]) * int(z.shape[4]) if c["reg"] == "kl" else 0
         line = {
-            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "metric": c["metric"], "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_OF[precision],
             "data": "synthetic",
-            "config": {"workload": "vidtok_kl_causal_488_4chn bf16: batch 8 clips 17x256x256 per GPU (BASELINE.json configs[1])",
+            "config": {"workload": workload_string(c, precision, B), "bench_config": args.config, "precision": precision,
                        "clips_per_gpu": B, "parallelism": f"dp{world} (clips sharded, no data-path collective)",
-                       "weights": "random (synth_state_dict seed 0)", "l2": "per-step activations are GBs, far larger than the 126 MB L2"},
+                       "weights": "random (synth_state_dict seed 0)", "algorithmic_flops_per_clip": c["flops"],
+                       "l2": "per-step activations are GBs, far larger than the 126 MB L2"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": nbytes + 4 * B * 4 * 5 * 32 * 32, "d2h_bytes_per_step": nbytes,
+                    "h2d_bytes_per_step": nbytes + noise_bytes, "d2h_bytes_per_step": nbytes,
                     "pipeline": "every step copies its clips from pinned host memory and its reconstruction back; the copies run on a "
                                 "second stream, double buffered against the previous / next step's kernels"},
             "gpu_launches": launches,
             "roofline": roof,
             "cpu_baseline": cpu,
-            "psnr": psnr,
+            "psnr": parity,
         }
         print(json.dumps(line), flush=True)
     if torch.distributed.is_initialized():
@@ -384,15 +453,16 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=8, help="clips per GPU")
+    ap.add_argument("--config", default="kl488", choices=sorted(CONFIGS.keys()))
+    ap.add_argument("--precision", default=None, choices=["bf16", "exact", "mixed", "fma"], help="default: the config's")
+    ap.add_argument("--batch", type=int, default=0, help="clips per GPU (default: the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    import __graft_entry__ as ge
-    ge.build()
+    c = CONFIGS[args.config]
     if args.impl == "reference":
-        run_reference_arm(args)
+        run_reference_arm(args, c)   # CPU only: the CUDA library is neither built nor loaded here
     else:
-        run_b200_arm(args)
+        run_b200_arm(args, c)
 
 
 if __name__ == "__main__":

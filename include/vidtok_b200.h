@@ -38,11 +38,18 @@ typedef enum {
   VT_ERR_NO_DEVICE = -5   /* no sm_100 device: there is deliberately no CPU fallback */
 } vt_status;
 
-/* Precision modes.  EXACT: fp32 activations, fp32 FMA accumulation (parity gate: 1e-3 max-abs, FSQ codes
- * equal).  BF16: bf16 activations/weights on tcgen05 tensor cores with fp32 accumulation (throughput
- * mode: PSNR within 0.01 dB). */
+/* Precision modes.
+ * EXACT_TC (the parity mode): fp32-class results on the tcgen05 tensor cores.  Activations and weights are kept as
+ *   two bf16 planes (hi = bf16(v), lo = bf16(v - hi)); every K step issues hi*hi + lo*hi + hi*lo into the fp32 TMEM
+ *   accumulator ("bf16x3"), LayerNorm / SiLU / regularizers in fp32.  Gate: 1e-3 max-abs, FSQ codes equal.
+ * BF16 (the throughput mode): bf16 activations / weights, fp32 accumulation.  Gate: PSNR within 0.01 dB.
+ * MIXED: encoder in EXACT_TC (bit-exact FSQ codes / 1e-3 latents), decoder in BF16.
+ * FMA32 (VT_PREC_EXACT, kept for cross-checks): fp32 activations on fp32 FMA kernels, no tensor cores. */
 #define VT_PREC_EXACT 0
+#define VT_PREC_FMA32 0
 #define VT_PREC_BF16 1
+#define VT_PREC_EXACT_TC 2
+#define VT_PREC_MIXED 3
 
 #define VT_NORM_LAYERNORM 0
 #define VT_NORM_GROUPNORM 1
@@ -120,17 +127,19 @@ int32_t vt_latent_shape(const vt_model* m, int32_t T, int32_t H, int32_t W, int3
 int32_t vt_decoded_frames(const vt_model* m, int32_t Tz);
 int64_t vt_workspace_bytes(const vt_model* m, int32_t precision, int32_t B, int32_t T, int32_t H, int32_t W);
 
-/* x: device fp32 [B,in_channels,T,H,W].  noise: device fp32 [B,z,Tz,Hz,Wz] = the reference's
+/* x: device fp32 [B,C,T,H,W]; C must equal in_channels (a mismatch is rejected: the reference raises a shape error in
+ * conv_in, model_3dcausal.py:634).  noise: device fp32 [B,z,Tz,Hz,Wz] = the reference's
  * torch.randn(mean.shape) (distributions.py:17), required for KL with kl_sample, else NULL.
  * Outputs (device, caller-allocated): z fp32 [B,z,Tz,Hz,Wz]; indices int32 [B,Tz,Hz,Wz] (FSQ, may be
  * NULL); kl_loss 1 float (KL, may be NULL); h_pre fp32 [B,2z|z,Tz,Hz,Wz] encoder output before the
  * regularizer (may be NULL). */
-int32_t vt_encode(vt_model* m, int32_t precision, const float* x, int32_t B, int32_t T, int32_t H, int32_t W,
+int32_t vt_encode(vt_model* m, int32_t precision, const float* x, int32_t B, int32_t C, int32_t T, int32_t H, int32_t W,
                   const float* noise, float* z, int32_t* indices, float* kl_loss, float* h_pre, void* workspace,
                   int64_t workspace_bytes, void* stream);
-/* z: device fp32 [B,z,Tz,Hz,Wz], or (from_indices) int32 [B,Tz,Hz,Wz] (autoencoder.py:205-217).
+/* z: device fp32 [B,Cz,Tz,Hz,Wz] with Cz == z_channels, or (from_indices; Cz ignored) int32 [B,Tz,Hz,Wz]
+ * (autoencoder.py:205-217).
  * x_out: device fp32 [B,out_ch,vt_decoded_frames(Tz),Hz*s,Wz*s]. */
-int32_t vt_decode(vt_model* m, int32_t precision, const void* z, int32_t from_indices, int32_t B, int32_t Tz,
+int32_t vt_decode(vt_model* m, int32_t precision, const void* z, int32_t from_indices, int32_t B, int32_t Cz, int32_t Tz,
                   int32_t Hz, int32_t Wz, float* x_out, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- temporal tiling with causal caches (v1.1: tile_encode / tile_decode,
@@ -141,13 +150,13 @@ int32_t vt_chunk_state_create(vt_model* m, int32_t precision, int32_t B, int32_t
                               int32_t use_overlap, vt_chunk_state** out);
 void vt_chunk_state_destroy(vt_chunk_state* s);
 int64_t vt_chunk_workspace_bytes(const vt_chunk_state* s, int32_t T_chunk);
-/* x_chunk: device fp32 [B,C,Tc,H,W] (dense).  Outputs as vt_encode, for this chunk only. */
-int32_t vt_encode_chunk(vt_chunk_state* s, int32_t is_first, const float* x_chunk, int32_t Tc, const float* noise,
+/* x_chunk: device fp32 [B,C,Tc,H,W] (dense), C == in_channels.  Outputs as vt_encode, for this chunk only. */
+int32_t vt_encode_chunk(vt_chunk_state* s, int32_t is_first, const float* x_chunk, int32_t C, int32_t Tc, const float* noise,
                         float* z, int32_t* indices, float* kl_loss, void* workspace, int64_t workspace_bytes,
                         void* stream);
-/* z_chunk: device fp32 [B,z,Tzc,Hz,Wz] including the look-ahead frame when overlap applies; x_out receives
+/* z_chunk: device fp32 [B,Cz,Tzc,Hz,Wz] (Cz == z_channels) including the look-ahead frame when overlap applies; x_out receives
  * all decoded frames of this chunk (the caller trims the look-ahead tail as autoencoder_v1_1.py:327-328). */
-int32_t vt_decode_chunk(vt_chunk_state* s, int32_t is_first, const float* z_chunk, int32_t Tzc, float* x_out,
+int32_t vt_decode_chunk(vt_chunk_state* s, int32_t is_first, const float* z_chunk, int32_t Cz, int32_t Tzc, float* x_out,
                         void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- single operators, exposed for the parity tests (same kernels the model path launches) ---- */
@@ -161,17 +170,52 @@ typedef struct vt_conv_desc {
   int32_t res_mode;                 /* 0 none, 1 out = conv + res, 2 out = a*res[t/2] + (1-a)*conv, 3 out = a*avgpool3(res) + (1-a)*conv */
   float alpha;
 } vt_conv_desc;
-/* x/res/out are channels-last activations in the precision's activation type (fp32 or bf16);
- * w fp32 [Co,Ci,kt,kh,kw]; bias fp32 [Co].  force_simt != 0 runs the FMA kernel even in BF16 mode. */
+/* x/res/out are channels-last activations in the precision's activation type: fp32 (FMA32), bf16 (BF16), or hi|lo split
+ * bf16 rows [..., hi(C) | lo(C)] (EXACT_TC; value = hi + lo); w fp32 [Co,Ci,kt,kh,kw]; bias fp32 [Co].
+ * BF16 / EXACT_TC run the tcgen05 kernel (an unsupported geometry is an error, never a silent fallback) unless
+ * force_simt != 0, which runs the fp32-FMA kernel on the same operands. */
 int32_t vt_op_conv(int32_t precision, int32_t force_simt, const vt_conv_desc* d, const void* x, const float* w,
                    const float* bias, const void* res, void* out, void* stream);
+/* The variants of the convolution the model path uses beyond vt_conv_desc: v1.1 time padding (replicated first frame /
+ * per-layer cache, model_3dcausal_v1_1.py:216-236), LayerNorm(+SiLU) fused into the epilogue (model_3dcausal.py:62-80),
+ * dropped leading output frames (:883-885), fp32 [B,C,T,H,W] output (the heads), residual as a mix. */
+typedef struct vt_conv_ex {
+  vt_conv_desc d;
+  int32_t force_simt;
+  int32_t t_mode;          /* 0 zeros, 1 replicate frame 0, 2 `cache` holds cacheT frames [B,cacheT,H,W,C] in front of x */
+  int32_t cacheT;
+  int32_t ln_mode;         /* 0 none, 1 out := act(LN(v)), 2 out := v and out2 := act(LN(v)) */
+  int32_t ln_silu;
+  int32_t to_off;          /* leading output frames dropped */
+  int32_t out_f32_ncdhw;   /* out is fp32 [B,Co,To,Ho,Wo] */
+  int32_t res_mix;         /* res_mode 1 computes alpha*res + (1-alpha)*conv instead of res + conv */
+  int32_t res_t_mode;      /* res_mode 3 front pad: 0 zero, 1 frame 0, 2 `cache` = 1 frame [B,1,H,W,C] */
+} vt_conv_ex;
+int32_t vt_op_conv_ex(int32_t precision, const vt_conv_ex* e, const void* x, const void* cache, const float* w,
+                      const float* bias, const void* res, const float* gamma, const float* beta, void* out, void* out2,
+                      void* stream);
+/* Encoder stem from the caller's fp32 [B,Ci,T,H,W] (t_rep replicated leading frames); out channels-last
+ * [B,T+t_rep,H,W,Co] in the precision's activation type (BF16 / EXACT_TC). */
+int32_t vt_op_conv_stem(int32_t precision, const float* x, const float* w, const float* bias, void* out, int32_t B,
+                        int32_t Ci, int32_t T, int32_t H, int32_t W, int32_t Co, int32_t t_rep, void* stream);
+/* Decoder head of the BF16 mode (tap-planes GEMM + gather): x bf16 [B,T,H,W,Ci] -> out fp32 [B,Co,T-to_off,H,W]. */
+int32_t vt_op_head_planes(const void* x, const float* w, const float* bias, float* out, int32_t B, int32_t T, int32_t H,
+                          int32_t W, int32_t Ci, int32_t Co, int32_t to_off, void* stream);
+/* "nearest 2x upsample then conv" through the phase-collapsed weights (kind 0: Upsample, w [Co,Ci,3,3];
+ * kind 1: v1.0 TimeUpsampleResCausal2x, w [C,C,3,3,3], alpha = sigmoid(mix_factor)); gamma/beta/out2 optional: the
+ * following LayerNorm(+SiLU) fused into the phase convolutions. */
+int32_t vt_op_upsample_conv(int32_t precision, int32_t kind, const void* x, const float* w, const float* bias, float alpha,
+                            const float* gamma, const float* beta, int32_t ln_silu, void* out, void* out2, int32_t B,
+                            int32_t T, int32_t H, int32_t W, int32_t Ci, int32_t Co, void* stream);
 /* y = silu?(norm(x)) over channels-last x [rows, C]; groupnorm variants take frame geometry. */
 int32_t vt_op_layernorm(int32_t precision, const void* x, const float* gamma, const float* beta, void* y,
                         int64_t rows, int32_t C, int32_t apply_silu, void* stream);
 int32_t vt_op_groupnorm(int32_t precision, const void* x, const float* gamma, const float* beta, void* y,
                         int64_t frames, int64_t positions_per_frame, int32_t C, int32_t per_position,
                         int32_t apply_silu, void* workspace, int64_t workspace_bytes, void* stream);
-/* per-frame single-head attention core: q,k,v,o channels-last [frames, tokens, C]; scale = C^-0.5 */
+/* per-frame single-head attention core: q,k,v,o channels-last [frames, tokens, C]; scale = C^-0.5.  Runs what the
+ * model path runs: tcgen05 GEMMs in BF16 / EXACT_TC when tokens % 64 == 0 and C % 64 == 0, fp32 FMAs otherwise.
+ * workspace: frames*tokens*(8*tokens + 24*C) + 65536 bytes is always enough. */
 int32_t vt_op_attention(int32_t precision, const void* q, const void* k, const void* v, void* o, int32_t frames,
                         int32_t tokens, int32_t C, void* workspace, int64_t workspace_bytes, void* stream);
 int32_t vt_op_fsq(const float* h, int32_t d, const int32_t* levels, int64_t positions_per_batch, int32_t B,

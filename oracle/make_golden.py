@@ -29,7 +29,7 @@ from oracle import ref_shim  # noqa: E402
 from oracle.vidtok_oracle import OracleModel, cfg_from_model_yaml  # noqa: E402
 from vidtok_b200.synth import synth_clip, synth_state_dict, weights_fingerprint  # noqa: E402
 
-GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+GOLDEN_DIR = os.environ.get("VIDTOK_GOLDEN_OUT", os.path.join(ROOT, "tests", "golden"))   # override: regeneration test
 
 
 def model_yaml(version="v1_0", reg="kl", ch=16, ch_mult=(1, 2, 4, 4), z=4, norm="layernorm", interp=None,

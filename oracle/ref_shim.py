@@ -56,22 +56,32 @@ def _install_stubs():
 
 
 def import_reference():
-    """Returns the reference `vidtok` package (imported from REFERENCE_ROOT, unmodified)."""
+    """Returns the reference `vidtok` package (imported from REFERENCE_ROOT, unmodified).
+
+    This repo ships a regular `vidtok` package with the same import paths (the drop-in shims); a regular package anywhere
+    on sys.path beats the reference's namespace package, so every sys.path entry that holds a `vidtok/__init__.py` is
+    dropped for this process and the already-imported shim modules are forgotten before the reference is imported."""
     if not reference_available():
         raise RuntimeError(f"reference not present at {REFERENCE_ROOT}")
     _install_stubs()
-    # our own repo ships a `vidtok` compat package with the same import paths; make sure the
-    # reference one wins inside this process.
     for k in [k for k in sys.modules if k == "vidtok" or k.startswith("vidtok.")]:
         del sys.modules[k]
-    if REFERENCE_ROOT in sys.path:
-        sys.path.remove(REFERENCE_ROOT)
-    sys.path.insert(0, REFERENCE_ROOT)
+    ref = os.path.abspath(REFERENCE_ROOT)
+    keep = []
+    for p in sys.path:
+        q = os.path.abspath(p or ".")
+        if q != ref and os.path.isfile(os.path.join(q, "vidtok", "__init__.py")):
+            continue   # the shim package's parent directory (usually the repo root / the script's cwd)
+        if q != ref:
+            keep.append(p)
+    sys.path[:] = [ref] + keep
+    import importlib
+    importlib.invalidate_caches()
     import vidtok  # noqa: F401
     import vidtok.models.autoencoder  # noqa: F401
     import vidtok.models.autoencoder_v1_1  # noqa: F401
 
-    assert vidtok.__path__[0].startswith(REFERENCE_ROOT), vidtok.__path__
+    assert all(os.path.abspath(p).startswith(ref) for p in vidtok.__path__), list(vidtok.__path__)
     return vidtok
 
 

@@ -541,3 +541,79 @@ def compute_psnr(x: Tensor, y: Tensor) -> Tensor:
         y = y.permute(0, 2, 1, 3, 4).reshape(-1, y.shape[1], y.shape[3], y.shape[4])
     mse = torch.mean((x - y) ** 2, dim=[1, 2, 3])
     return (-10 * torch.log10(mse + 1e-8)).mean(dim=0)
+
+
+# --------------------------------------------------------------------------------------------------
+# parameter table: the checkpoint keys / shapes the reference modules register
+# (EncoderCausal3D.__init__ model_3dcausal.py:535-620, DecoderCausal3D.__init__ :724-811; v1.1 identical keys)
+# --------------------------------------------------------------------------------------------------
+def reference_param_shapes(cfg: OracleCfg) -> Dict[str, Tuple[int, ...]]:
+    """{state_dict key: shape} of the reference model for `cfg` -- lets the CPU-only legs (bench.py reference arm,
+    tests) build synthetic weights without touching the CUDA library."""
+    out: Dict[str, Tuple[int, ...]] = {}
+    ln = cfg.norm_type == "layernorm"
+
+    def norm(key, c):
+        k = key + ".norm" if ln else key
+        out[k + ".weight"], out[k + ".bias"] = (c,), (c,)
+
+    def conv3d(key, co, ci, k=3):
+        out[key + ".conv.weight"], out[key + ".conv.bias"] = (co, ci, k, k, k), (co,)
+
+    def conv1d(key, co, ci):
+        out[key + ".conv.weight"], out[key + ".conv.bias"] = (co, ci, 3), (co,)
+
+    def conv2d(key, co, ci, k):
+        out[key + ".weight"], out[key + ".bias"] = (co, ci, k, k), (co,)
+
+    def res2d(key, ci, co):
+        norm(key + ".norm1", ci); conv2d(key + ".conv1", co, ci, 3); norm(key + ".norm2", co); conv2d(key + ".conv2", co, co, 3)
+        if ci != co:
+            conv2d(key + ".nin_shortcut", co, ci, 1)
+
+    def res1d(key, c):
+        norm(key + ".norm1", c); conv1d(key + ".conv1", c, c); norm(key + ".norm2", c); conv1d(key + ".conv2", c, c)
+
+    def res3d(key, c):
+        norm(key + ".norm1", c); conv3d(key + ".conv1", c, c); norm(key + ".norm2", c); conv3d(key + ".conv2", c, c)
+
+    def attn(key, c):
+        norm(key + ".norm", c)
+        for n in ("q", "k", "v", "proj_out"):
+            conv3d(f"{key}.{n}", c, c, 1)
+
+    L = cfg.nres
+    conv3d("encoder.conv_in", cfg.ch, cfg.in_channels)
+    block_in = cfg.ch
+    for l in range(L):
+        block_out = cfg.ch * cfg.ch_mult[l]
+        for b in range(cfg.num_res_blocks):
+            res2d(f"encoder.down.{l}.block.{b}", block_in, block_out)
+            res1d(f"encoder.down_temporal.{l}.block.{b}", block_out)
+            block_in = block_out
+        if l in cfg.enc_spatial_ds():
+            conv2d(f"encoder.down.{l}.downsample.conv", block_in, block_in, 3)
+            if l in cfg.enc_tempo_ds():
+                out[f"encoder.down_temporal.{l}.downsample.mix_factor"] = (1,)
+                conv3d(f"encoder.down_temporal.{l}.downsample.conv", block_in, block_in)
+    res3d("encoder.mid.block_1", block_in); attn("encoder.mid.attn_1", block_in); res3d("encoder.mid.block_2", block_in)
+    norm("encoder.norm_out", block_in)
+    conv3d("encoder.conv_out", (2 if cfg.double_z else 1) * cfg.z_channels, block_in)
+
+    block_in = cfg.ch * cfg.ch_mult[L - 1]
+    conv3d("decoder.conv_in", block_in, cfg.z_channels)
+    res3d("decoder.mid.block_1", block_in); attn("decoder.mid.attn_1", block_in); res3d("decoder.mid.block_2", block_in)
+    for l in reversed(range(L)):
+        block_out = cfg.ch * cfg.ch_mult[l]
+        for b in range(cfg.num_res_blocks + 1):
+            res2d(f"decoder.up.{l}.block.{b}", block_in, block_out)
+            res1d(f"decoder.up_temporal.{l}.block.{b}", block_out)
+            block_in = block_out
+        if l in cfg.dec_spatial_us():
+            conv2d(f"decoder.up.{l}.upsample.conv", block_in, block_in, 3)
+        if l in cfg.dec_tempo_us():
+            out[f"decoder.up_temporal.{l}.upsample.mix_factor"] = (1,)
+            conv3d(f"decoder.up_temporal.{l}.upsample.conv", block_in, block_in)
+    norm("decoder.norm_out", block_in)
+    conv3d("decoder.conv_out", cfg.out_ch, block_in)
+    return out

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/vidtok_b200.h but not exported"
     assert declared == set(N.EXPORTS), declared ^ set(N.EXPORTS)
-    assert N.lib().vt_abi_version() == 1
+    assert N.lib().vt_abi_version() == 2
 
 
 @pytest.mark.parametrize("case", golden_cases())
@@ -79,8 +79,12 @@ def test_latent_geometry_and_workspace_dry_run():
     assert nm.decoded_frames(5) == 17 and nm.decoded_frames(4) == 13
     assert nm.spatial_factor() == 8
     ws_bf16 = N.lib().vt_workspace_bytes(nm.handle, N.PREC_BF16, 8, 17, 256, 256)
-    ws_fp32 = N.lib().vt_workspace_bytes(nm.handle, N.PREC_EXACT, 8, 17, 256, 256)
+    ws_fp32 = N.lib().vt_workspace_bytes(nm.handle, N.PREC_FMA32, 8, 17, 256, 256)
+    ws_x3 = N.lib().vt_workspace_bytes(nm.handle, N.PREC_EXACT_TC, 8, 17, 256, 256)
+    ws_mix = N.lib().vt_workspace_bytes(nm.handle, N.PREC_MIXED, 8, 17, 256, 256)
     assert 4e9 < ws_bf16 < 40e9 and ws_bf16 < ws_fp32 < 80e9
+    assert ws_bf16 < ws_x3 < 80e9 and ws_bf16 <= ws_mix <= ws_x3
+    assert N.lib().vt_workspace_bytes(nm.handle, 7, 8, 17, 256, 256) == -1
     assert N.lib().vt_workspace_bytes(nm.handle, N.PREC_BF16, 1, 17, 250, 256) == -1
     assert b"multiples of 8" in N.lib().vt_last_error()
     spec11 = TokenizerSpec(version=1, ch=128, ch_mult=(1, 2, 4, 4), num_res_blocks=2, z_channels=16, double_z=True,

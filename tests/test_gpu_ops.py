@@ -122,7 +122,7 @@ def test_layernorm(C_, silu):
         ref = ref * torch.sigmoid(ref)
     xd, gd, bd = x.cuda(), g.cuda(), b.cuda()
     y = torch.empty_like(xd)
-    N.check(N.lib().vt_op_layernorm(N.PREC_EXACT, C.c_void_p(xd.data_ptr()), C.c_void_p(gd.data_ptr()), C.c_void_p(bd.data_ptr()),
+    N.check(N.lib().vt_op_layernorm(N.PREC_FMA32, C.c_void_p(xd.data_ptr()), C.c_void_p(gd.data_ptr()), C.c_void_p(bd.data_ptr()),
                                     C.c_void_p(y.data_ptr()), rows, C_, int(silu), None))
     torch.cuda.synchronize()
     assert float((y.cpu() - ref).abs().max()) < 1e-5
@@ -153,7 +153,7 @@ def test_groupnorm(per_position):
     gd, bd = g.cuda(), b.cuda()
     y = torch.empty_like(xd)
     ws = torch.empty(frames * 64 * 4, dtype=torch.uint8, device="cuda")
-    N.check(N.lib().vt_op_groupnorm(N.PREC_EXACT, C.c_void_p(xd.data_ptr()), C.c_void_p(gd.data_ptr()), C.c_void_p(bd.data_ptr()),
+    N.check(N.lib().vt_op_groupnorm(N.PREC_FMA32, C.c_void_p(xd.data_ptr()), C.c_void_p(gd.data_ptr()), C.c_void_p(bd.data_ptr()),
                                     C.c_void_p(y.data_ptr()), frames, H * W, C_, int(per_position), 1,
                                     C.c_void_p(ws.data_ptr()), ws.numel(), None))
     torch.cuda.synchronize()
@@ -168,7 +168,7 @@ def test_attention_core():
     qd, kd, vd = q.cuda(), k.cuda(), v.cuda()
     o = torch.empty_like(qd)
     ws = torch.empty(frames * tokens * tokens * 8 + 4096, dtype=torch.uint8, device="cuda")
-    N.check(N.lib().vt_op_attention(N.PREC_EXACT, C.c_void_p(qd.data_ptr()), C.c_void_p(kd.data_ptr()), C.c_void_p(vd.data_ptr()),
+    N.check(N.lib().vt_op_attention(N.PREC_FMA32, C.c_void_p(qd.data_ptr()), C.c_void_p(kd.data_ptr()), C.c_void_p(vd.data_ptr()),
                                     C.c_void_p(o.data_ptr()), frames, tokens, C_, C.c_void_p(ws.data_ptr()), ws.numel(), None))
     torch.cuda.synchronize()
     assert float((o.cpu() - ref).abs().max()) < 2e-5

@@ -1,1 +1,2 @@
-from vidtok_b200.compat_util import compute_psnr, get_obj_from_str, instantiate_from_config, print0  # noqa: F401
+from vidtok_b200.compat_util import (compute_psnr, compute_ssim, default, exists, get_obj_from_str, get_valid_dirs,  # noqa: F401
+                                     get_valid_paths, instantiate_from_config, isheatmap, print0, seed_anything)

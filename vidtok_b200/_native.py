@@ -6,7 +6,9 @@ import ctypes as C
 import os
 
 VT_MAX_LEVELS = 8
-PREC_EXACT, PREC_BF16 = 0, 1
+# include/vidtok_b200.h: FMA32 (fp32 FMA kernels), BF16 (tcgen05), EXACT_TC (bf16x3 split operands on tcgen05), MIXED
+PREC_FMA32, PREC_BF16, PREC_EXACT_TC, PREC_MIXED = 0, 1, 2, 3
+PREC_EXACT = PREC_EXACT_TC  # the parity mode
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvidtok_b200.so")
 
@@ -31,6 +33,11 @@ class ConvDesc(C.Structure):
         "ut", "uh", "uw", "res_mode")] + [("alpha", C.c_float)]
 
 
+class ConvEx(C.Structure):
+    _fields_ = [("d", ConvDesc)] + [(n, C.c_int32) for n in (
+        "force_simt", "t_mode", "cacheT", "ln_mode", "ln_silu", "to_off", "out_f32_ncdhw", "res_mix", "res_t_mode")]
+
+
 _P, _I32, _I64 = C.c_void_p, C.c_int32, C.c_int64
 _SIGS = {
     "vt_last_error": (C.c_char_p, []),
@@ -49,14 +56,18 @@ _SIGS = {
     "vt_latent_shape": (_I32, [_P, _I32, _I32, _I32, C.POINTER(_I32), C.POINTER(_I32), C.POINTER(_I32)]),
     "vt_decoded_frames": (_I32, [_P, _I32]),
     "vt_workspace_bytes": (_I64, [_P, _I32, _I32, _I32, _I32, _I32]),
-    "vt_encode": (_I32, [_P, _I32, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _I64, _P]),
-    "vt_decode": (_I32, [_P, _I32, _P, _I32, _I32, _I32, _I32, _I32, _P, _P, _I64, _P]),
+    "vt_encode": (_I32, [_P, _I32, _P, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _I64, _P]),
+    "vt_decode": (_I32, [_P, _I32, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _I64, _P]),
     "vt_chunk_state_create": (_I32, [_P, _I32, _I32, _I32, _I32, _I32, _I32, C.POINTER(_P)]),
     "vt_chunk_state_destroy": (None, [_P]),
     "vt_chunk_workspace_bytes": (_I64, [_P, _I32]),
-    "vt_encode_chunk": (_I32, [_P, _I32, _P, _I32, _P, _P, _P, _P, _P, _I64, _P]),
-    "vt_decode_chunk": (_I32, [_P, _I32, _P, _I32, _P, _P, _I64, _P]),
+    "vt_encode_chunk": (_I32, [_P, _I32, _P, _I32, _I32, _P, _P, _P, _P, _P, _I64, _P]),
+    "vt_decode_chunk": (_I32, [_P, _I32, _P, _I32, _I32, _P, _P, _I64, _P]),
     "vt_op_conv": (_I32, [_I32, _I32, C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),
+    "vt_op_conv_ex": (_I32, [_I32, C.POINTER(ConvEx), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "vt_op_conv_stem": (_I32, [_I32, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
+    "vt_op_head_planes": (_I32, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
+    "vt_op_upsample_conv": (_I32, [_I32, _I32, _P, _P, _P, C.c_float, _P, _P, _I32, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     "vt_op_layernorm": (_I32, [_I32, _P, _P, _P, _P, _I64, _I32, _I32, _P]),
     "vt_op_groupnorm": (_I32, [_I32, _P, _P, _P, _P, _I64, _I64, _I32, _I32, _I32, _P, _I64, _P]),
     "vt_op_attention": (_I32, [_I32, _P, _P, _P, _P, _I32, _I32, _I32, _P, _I64, _P]),

@@ -96,6 +96,9 @@ struct ConvP {
   int res_t_mode;                     // mode 3 front pad: 0 zero (v1.0), 1 replicate frame 0, 2 res_cache (1 frame)
   const void* res_cache;              // [B,1,H,W,C]
   float ra, rb;
+  // activations (input, cache, residual, bf16-class output) are hi|lo split bf16 planes (DT_SPLIT): every position holds
+  // 2*C bf16 values, the strides above count bf16 elements (isW = 2*Ci for a dense tensor), channel c's lo part is at c + C
+  int split;
 };
 
 struct ConvLaunch {  // host-side convenience

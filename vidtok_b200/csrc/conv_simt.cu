@@ -3,6 +3,7 @@
 // ConvP (common.cuh).  GEMM view: M = B*To*Ho*Wo output positions, N = Cout, K = kt*kh*kw*Cin ordered
 // tap-major / channel-minor; weights are pre-packed as [K][Cout] fp32.
 #include <cstdio>
+#include <type_traits>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -25,7 +26,7 @@ __device__ __forceinline__ const TIn* gather_ptr(const ConvP& p, const TIn* __re
     if (p.t_mode == 2) {
       int ct = p.cacheT + tv;
       return reinterpret_cast<const TIn*>(p.cache) +
-             ((((long long)b * p.cacheT + ct) * p.Hi + hi) * p.Wi + wi) * (long long)p.Ci;
+             ((((long long)b * p.cacheT + ct) * p.Hi + hi) * p.Wi + wi) * (long long)p.Ci * ((std::is_same<TIn, bf16>::value && p.split) ? 2 : 1);
     }
     tv = 0;
   }
@@ -33,6 +34,27 @@ __device__ __forceinline__ const TIn* gather_ptr(const ConvP& p, const TIn* __re
   ti = ti < 0 ? 0 : ti;
   if (p.ut == 2) ti >>= 1;
   return x + (long long)b * p.isB + (long long)ti * p.isT + (long long)hi * p.isH + (long long)wi * p.isW;
+}
+
+// 4 (or ncount) consecutive channels starting at q; split tensors (hi | lo planes, DT_SPLIT) add the lo plane at q + C
+template <typename T>
+__device__ __forceinline__ void ld4s(const ConvP& p, const T* q, int C, int ncount, float (&t)[4]) {
+  t[0] = t[1] = t[2] = t[3] = 0.f;
+  if (ncount == 4) {
+    load4(q, t);
+  } else {
+    for (int j = 0; j < ncount; ++j) t[j] = to_f(q[j]);
+  }
+  if (std::is_same<T, bf16>::value && p.split) {
+    float u[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ncount == 4) {
+      load4(q + C, u);
+    } else {
+      for (int j = 0; j < ncount; ++j) u[j] = to_f(q[C + j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t[j] += u[j];
+  }
 }
 
 template <typename TRes>
@@ -43,11 +65,7 @@ __device__ __forceinline__ void residual4(const ConvP& p, int b, int to, int ho,
   if (p.res_mode == 1 || p.res_mode == 2) {
     int tr = (p.res_mode == 2) ? (to >> 1) : to;
     const TRes* q = R + (long long)b * p.rsB + (long long)tr * p.rsT + (long long)ho * p.rsH + (long long)wo * p.rsW + n;
-    if (ncount == 4) {
-      load4(q, r);
-    } else {
-      for (int j = 0; j < ncount; ++j) r[j] = to_f(q[j]);
-    }
+    ld4s<TRes>(p, q, p.Co, ncount, r);
   } else if (p.res_mode == 3) {
     // AvgPool3d((3,1,1), stride (2,1,1)) over [front pad 1][R]  (model_3dcausal.py:242,250)
 #pragma unroll
@@ -59,15 +77,11 @@ __device__ __forceinline__ void residual4(const ConvP& p, int b, int to, int ho,
       } else if (p.res_t_mode == 1) {
         q = R + (long long)b * p.rsB + (long long)ho * p.rsH + (long long)wo * p.rsW + n;
       } else if (p.res_t_mode == 2) {
-        q = reinterpret_cast<const TRes*>(p.res_cache) + (((long long)b * p.Ho + ho) * p.Wo + wo) * (long long)p.Co + n;
+        q = reinterpret_cast<const TRes*>(p.res_cache) + (((long long)b * p.Ho + ho) * p.Wo + wo) * (long long)p.Co * ((std::is_same<TRes, bf16>::value && p.split) ? 2 : 1) + n;
       }
       if (q) {
-        float t[4] = {0.f, 0.f, 0.f, 0.f};
-        if (ncount == 4) {
-          load4(q, t);
-        } else {
-          for (int j = 0; j < ncount; ++j) t[j] = to_f(q[j]);
-        }
+        float t[4];
+        ld4s<TRes>(p, q, p.Co, ncount, t);
 #pragma unroll
         for (int j = 0; j < 4; ++j) r[j] += t[j];
       }
@@ -141,7 +155,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvP p, const TIn
           int t2 = tap / p.kw;
           int bb = t2 % p.kh, a = t2 / p.kh;
           const TIn* q = gather_ptr<TIn>(p, x, rb[i], rt[i], rh[i], rw[i], a, bb, c);
-          if (q) load4(q + ci, ra[i]);
+          if (q) ld4s<TIn>(p, q + ci, p.Ci, 4, ra[i]);
         }
       } else {
 #pragma unroll
@@ -153,7 +167,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvP p, const TIn
             int t2 = tap / p.kw;
             int bb = t2 % p.kh, a = t2 / p.kh;
             const TIn* q = gather_ptr<TIn>(p, x, rb[i], rt[i], rh[i], rw[i], a, bb, c);
-            if (q) ra[i][j] = to_f(q[(long long)ci * p.isC]);
+            if (q) ra[i][j] = to_f(q[(long long)ci * p.isC]) + ((std::is_same<TIn, bf16>::value && p.split) ? to_f(q[(long long)(ci + p.Ci) * p.isC]) : 0.f);
           }
         }
       }
@@ -239,7 +253,14 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvP p, const TIn
     }
     TOut* o = out + (long long)b * p.osB + (long long)to * p.osT + (long long)ho * p.osH + (long long)wo * p.osW +
               (long long)n * p.osC;
-    if (vecO) {
+    if (std::is_same<TOut, bf16>::value && p.split) {
+      // hi | lo planes (TOut = bf16, osC == 1)
+      for (int j = 0; j < ncount; ++j) {
+        const TOut h = from_f<TOut>(v[j]);
+        o[j] = h;
+        o[p.Co + j] = from_f<TOut>(v[j] - to_f(h));
+      }
+    } else if (vecO) {
       store4(o, v);
     } else {
       for (int j = 0; j < ncount; ++j) o[(long long)j * p.osC] = from_f<TOut>(v[j]);
@@ -279,8 +300,18 @@ cudaError_t launch_typed(const ConvP& p, const void* x, const float* w, void* ou
 
 }  // namespace
 
+// DT_SPLIT tensors are bf16 planes: the caller sets p.split when the bf16-typed operands (input / residual / output)
+// are split; fp32 external tensors (tin / tout == DT_F32) are unaffected by the flag.
 cudaError_t launch_conv_simt(const ConvP& p, DType tin, DType tout, DType tres, const void* x, const float* w,
                              void* out, cudaStream_t s) {
+  if (tin == DT_SPLIT || tout == DT_SPLIT || tres == DT_SPLIT) {
+    if (!p.split) return cudaErrorInvalidValue;
+    if (tin == DT_SPLIT) tin = DT_BF16;
+    if (tout == DT_SPLIT) tout = DT_BF16;
+    if (tres == DT_SPLIT) tres = DT_BF16;
+  } else if (p.split) {
+    return cudaErrorInvalidValue;
+  }
   if (tin == DT_F32 && tout == DT_F32 && tres == DT_F32) return launch_typed<float, float, float>(p, x, w, out, s);
   if (tin == DT_BF16 && tout == DT_BF16 && tres == DT_BF16) return launch_typed<bf16, bf16, bf16>(p, x, w, out, s);
   if (tin == DT_F32 && tout == DT_BF16 && tres == DT_BF16) return launch_typed<float, bf16, bf16>(p, x, w, out, s);

@@ -71,13 +71,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr) : "memory");
 }
 
-__global__ void __launch_bounds__(256, 1) conv_stem_kernel(const StemParams p, const bf16* __restrict__ wpk /*[Co][128]*/) {
+// kSplit (EXACT_TC mode): the im2col rows and the weights are hi|lo bf16 pairs, every K=16 step issues hi*hi + lo*hi +
+// hi*lo into the same accumulator, and the output is written as hi | lo planes ([..., 2*Co]).
+template <bool kSplit>
+__global__ void __launch_bounds__(256, 1) conv_stem_kernel(const StemParams p, const bf16* __restrict__ wpk /*[Co][128] or [Co][hi 128 | lo 128]*/) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  // layout: A[2] (2 x 32 KB) | B (Co x 256 B) | patch (Ci*3*PH*PW floats) | bias | barriers | tmem slot
-  const uint32_t offA = 0, offB = 2 * kATile;
-  const uint32_t offP = offB + (uint32_t)p.Co * 256u;
+  constexpr uint32_t kPl = kSplit ? 2u : 1u;
+  // layout: A[2 buffers][planes] (32 KB each) | B[planes] (Co x 256 B each) | patch (Ci*3*PH*PW floats) | bias | barriers | tmem slot
+  const uint32_t offA = 0, offB = 2 * kPl * kATile;
+  const uint32_t offP = offB + kPl * (uint32_t)p.Co * 256u;
   const uint32_t patch_floats = (uint32_t)p.Ci * 3 * PH * PW;
   const uint32_t offBias = offP + ((patch_floats * 4 + 15) & ~15u);
   const uint32_t offLut = offBias + 256 * 4;   // im2col k -> patch offset (or -1)
@@ -91,11 +95,12 @@ __global__ void __launch_bounds__(256, 1) conv_stem_kernel(const StemParams p, c
   const int units = (K + 7) / 8;  // 16-byte units of real data per im2col row (11 for Ci = 3)
 
   // ---- one-time setup: zero both A buffers, stage weights (swizzled) and bias, barriers, TMEM
-  for (uint32_t i = tid; i < 2 * kATile / 16; i += 256) reinterpret_cast<uint4*>(gen + offA)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < p.Co * 16; i += 256) {
-    const int row = i >> 4, U = i & 15, kc = U >> 3, u = U & 7;
-    const uint4 v = *reinterpret_cast<const uint4*>(wpk + (long long)row * 128 + U * 8);
-    *reinterpret_cast<uint4*>(gen + offB + kc * (p.Co * 128) + row * 128 + ((u ^ (row & 7)) << 4)) = v;
+  for (uint32_t i = tid; i < 2 * kPl * kATile / 16; i += 256) reinterpret_cast<uint4*>(gen + offA)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < p.Co * 16 * (int)kPl; i += 256) {
+    const int pl = i / (p.Co * 16), r = i % (p.Co * 16);
+    const int row = r >> 4, U = r & 15, kc = U >> 3, u = U & 7;
+    const uint4 v = *reinterpret_cast<const uint4*>(wpk + (long long)row * 128 * kPl + pl * 128 + U * 8);
+    *reinterpret_cast<uint4*>(gen + offB + pl * (p.Co * 256) + kc * (p.Co * 128) + row * 128 + ((u ^ (row & 7)) << 4)) = v;
   }
   for (int i = tid; i < p.Co; i += 256) sbias[i] = p.bias ? p.bias[i] : 0.f;
   if (tid < 128) {
@@ -179,7 +184,7 @@ __global__ void __launch_bounds__(256, 1) conv_stem_kernel(const StemParams p, c
     const int row = tid & 127, half = tid >> 7;
     const int dh = row / BW, dw = row % BW;
     const float* prow = patch + dh * PW + dw;
-    uint8_t* arow = gen + offA + buf * kATile + row * 128;
+    uint8_t* arow = gen + offA + buf * (kPl * kATile) + row * 128;
     const int u_begin = half == 0 ? 0 : (units + 1) / 2, u_end = half == 0 ? (units + 1) / 2 : units;
     for (int u = u_begin; u < u_end; ++u) {
       float f[8];
@@ -188,27 +193,39 @@ __global__ void __launch_bounds__(256, 1) conv_stem_kernel(const StemParams p, c
         const int off = lut[u * 8 + e];
         f[e] = off >= 0 ? prow[off] : 0.f;
       }
-      uint4 pk;
+      uint4 pk, pl;
       __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+      __nv_bfloat162* l2 = reinterpret_cast<__nv_bfloat162*>(&pl);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+      for (int e = 0; e < 4; ++e) {
+        h2[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+        if constexpr (kSplit) l2[e] = __floats2bfloat162_rn(f[2 * e] - __low2float(h2[e]), f[2 * e + 1] - __high2float(h2[e]));
+      }
       const int kc = u >> 3, uu = u & 7;
       *reinterpret_cast<uint4*>(arow + kc * (128 * 128) + ((uu ^ (row & 7)) << 4)) = pk;
+      if constexpr (kSplit) *reinterpret_cast<uint4*>(arow + kATile + kc * (128 * 128) + ((uu ^ (row & 7)) << 4)) = pl;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   };
   auto issue = [&](int buf) {
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t sa = base + offA + buf * kATile, sb = base + offB;
+      const uint32_t sa = base + offA + buf * (kPl * kATile), sb = base + offB;
       uint32_t accum = 0;
 #pragma unroll
       for (int kc = 0; kc < 2; ++kc)
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          umma_f16(tmem_base + (uint32_t)(buf * p.Co), make_sdesc(sa + kc * (128 * 128)) + (uint64_t)(k * 2),
-                   make_sdesc(sb + kc * (p.Co * 128)) + (uint64_t)(k * 2), idesc, accum);
+          const uint64_t ah = make_sdesc(sa + kc * (128 * 128)) + (uint64_t)(k * 2);
+          const uint64_t bh = make_sdesc(sb + kc * (p.Co * 128)) + (uint64_t)(k * 2);
+          umma_f16(tmem_base + (uint32_t)(buf * p.Co), ah, bh, idesc, accum);
           accum = 1;
+          if constexpr (kSplit) {
+            const uint64_t al = make_sdesc(sa + kATile + kc * (128 * 128)) + (uint64_t)(k * 2);
+            const uint64_t bl = make_sdesc(sb + p.Co * 256 + kc * (p.Co * 128)) + (uint64_t)(k * 2);
+            umma_f16(tmem_base + (uint32_t)(buf * p.Co), al, bh, idesc, 1u);
+            umma_f16(tmem_base + (uint32_t)(buf * p.Co), ah, bl, idesc, 1u);
+          }
         }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(buf ? bar1 : bar0) : "memory");
     }
@@ -223,7 +240,7 @@ __global__ void __launch_bounds__(256, 1) conv_stem_kernel(const StemParams p, c
     const int h = h0 + row / BW, w = w0 + row % BW;
     const bool valid = h < p.H && w < p.W;
     const int ncols = p.Co / 2;
-    bf16* orow = p.out + ((((long long)b * p.To + t) * p.H + h) * p.W + w) * p.Co + half * ncols;
+    bf16* orow = p.out + ((((long long)b * p.To + t) * p.H + h) * p.W + w) * (p.Co * (int)kPl) + half * ncols;
     const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.Co + half * ncols);
     for (int j = 0; j < ncols; j += 32) {
       uint32_t v[32];
@@ -232,15 +249,19 @@ __global__ void __launch_bounds__(256, 1) conv_stem_kernel(const StemParams p, c
       if (valid) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          uint4 pk;
+          uint4 pk, pl;
           __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+          __nv_bfloat162* l2 = reinterpret_cast<__nv_bfloat162*>(&pl);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int c = j + g * 8 + 2 * e;
-            h2[e] = __floats2bfloat162_rn(__uint_as_float(v[g * 8 + 2 * e]) + sbias[half * ncols + c],
-                                          __uint_as_float(v[g * 8 + 2 * e + 1]) + sbias[half * ncols + c + 1]);
+            const float f0 = __uint_as_float(v[g * 8 + 2 * e]) + sbias[half * ncols + c];
+            const float f1 = __uint_as_float(v[g * 8 + 2 * e + 1]) + sbias[half * ncols + c + 1];
+            h2[e] = __floats2bfloat162_rn(f0, f1);
+            if constexpr (kSplit) l2[e] = __floats2bfloat162_rn(f0 - __low2float(h2[e]), f1 - __high2float(h2[e]));
           }
           *reinterpret_cast<uint4*>(orow + j + g * 8) = pk;
+          if constexpr (kSplit) *reinterpret_cast<uint4*>(orow + p.Co + j + g * 8) = pl;
         }
       }
     }
@@ -310,13 +331,14 @@ cudaError_t launch_stem_cache_update(const float* x, float* cache, int B, int Ci
 bool conv_stem_supported(const ConvP& p) {
   if (p.kt != 3 || p.kh != 3 || p.kw != 3 || p.st != 1 || p.sh != 1 || p.sw != 1) return false;
   if (p.ut != 1 || p.uh != 1 || p.uw != 1 || p.to_off != 0 || p.res_mode != 0) return false;
-  if (p.Ci * 27 > 128 || p.Co % 64 != 0 || p.Co > 256) return false;
+  if (p.Ci * 27 > 128 || p.Co % 64 != 0 || p.Co > (p.split ? 128 : 256)) return false;
   if (p.t_mode == 2 && (!p.cache || p.cacheT != 2)) return false;
   if (p.pt != 2 || p.ph != 1 || p.pw != 1) return false;
   if (p.Ho != p.Hi || p.Wo != p.Wi || p.To != p.t_rep + p.Ti) return false;
   // external NCDHW fp32 input, dense channels-last bf16 output
   if (p.isW != 1 || p.isH != p.Wi || p.isT != (long long)p.Hi * p.Wi || p.isC != p.isT * p.Ti || p.isB != p.isC * p.Ci) return false;
-  if (p.osC != 1 || p.osW != p.Co || p.osH != (long long)p.Wo * p.Co || p.osT != p.osH * p.Ho || p.osB != p.osT * p.To) return false;
+  const long long oc = (long long)p.Co * (p.split ? 2 : 1);
+  if (p.osC != 1 || p.osW != oc || p.osH != (long long)p.Wo * oc || p.osT != p.osH * p.Ho || p.osB != p.osT * p.To) return false;
   return true;
 }
 
@@ -331,26 +353,30 @@ cudaError_t launch_conv_stem(const ConvP& p, const float* x, const bf16* wpk, bf
   uint32_t cols = 32;
   while (cols < (uint32_t)(2 * p.Co)) cols <<= 1;
   t.tmem_cols = cols;
-  const size_t smem = 1024 + 2 * kATile + (size_t)p.Co * 256 + (((size_t)p.Ci * 3 * PH * PW * 4 + 15) & ~(size_t)15) + 256 * 4 + 128 * 4 + 64;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(conv_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+  const size_t pl = p.split ? 2 : 1;
+  const size_t smem = 1024 + pl * 2 * kATile + pl * (size_t)p.Co * 256 + (((size_t)p.Ci * 3 * PH * PW * 4 + 15) & ~(size_t)15) + 256 * 4 + 128 * 4 + 64;
+  // per-device state: the attribute applies to the current device only
+  static bool attr[64] = {false};
+  static int sms[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (!attr[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(conv_stem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_stem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) return e;
-    attr = true;
+    attr[dev] = true;
+    cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (sms[dev] <= 0) sms[dev] = 148;
   }
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
-  }
+  const int num_sms = sms[dev];
   const double M = (double)t.num_tiles * 128;
   char det[96] = "";
   if (prof_enabled()) snprintf(det, sizeof(det), "k333 %d->%d @%dx%dx%d", p.Ci, p.Co, p.To, p.Hi, p.Wi);
-  ProfScope _ps("conv_stem", 2.0 * M * 27 * p.Ci * p.Co, (double)p.B * p.Ci * p.Ti * p.Hi * p.Wi * 4.0 + M * p.Co * 2.0, s, det);
+  ProfScope _ps(p.split ? "conv_stem3" : "conv_stem", 2.0 * M * 27 * p.Ci * p.Co, (double)p.B * p.Ci * p.Ti * p.Hi * p.Wi * 4.0 + M * p.Co * 2.0 * pl, s, det);
   const unsigned grid = (unsigned)(t.num_tiles < num_sms ? t.num_tiles : num_sms);
-  conv_stem_kernel<<<grid, 256, smem, s>>>(t, wpk);
+  if (p.split) conv_stem_kernel<true><<<grid, 256, smem, s>>>(t, wpk);
+  else conv_stem_kernel<false><<<grid, 256, smem, s>>>(t, wpk);
   count_launch();
   return cudaGetLastError();
 }

@@ -95,7 +95,11 @@ struct TcParams {
   // group stride (SBO) = hP rows, and hP % 8 == 0 keeps the swizzle phase of every group equal (= descriptor base offset).
   int halo, hP, a_stages;
   uint32_t halo_bytes;
-
+  // split operands (EXACT_TC mode, kernel template kSplit): activations and weights are stored as two bf16 planes
+  // hi = bf16(v), lo = bf16(v - hi) side by side in the channel dimension ([..., hi(C) | lo(C)]); every K step loads
+  // A_hi, A_lo, B_hi, B_lo and issues A_hi*B_hi + A_lo*B_hi + A_hi*B_lo into the same fp32 TMEM accumulator
+  // (error ~2^-17 per product: fp32-class results on the bf16 tensor pipe).  Channel coordinate of the lo plane:
+  int split, a_lo, b_lo, o_lo;   // = Cin, Kpad, Cout
 };
 
 struct TcMaps {
@@ -350,7 +354,7 @@ __device__ __forceinline__ bool tap_time(const TcParams& p, const TileCoord& tc,
 
 // Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3..10 = epilogue (two warps per TMEM
 // lane quarter, alternating 32-column chunks).
-template <bool kPair>
+template <bool kPair, bool kSplit>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -363,8 +367,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   const uint32_t a_bytes = (uint32_t)p.MT * kABytes;
   const int bn_local = kPair ? p.BN / 2 : p.BN;           // weight rows this CTA stages
   const uint32_t b_bytes = (uint32_t)bn_local * 128u;
-  const uint32_t stage_bytes = p.halo ? b_bytes : a_bytes + b_bytes;   // halo mode: the stage ring holds B tiles only
-  const uint32_t ring_base = smem_base + (p.halo ? (uint32_t)p.a_stages * p.halo_bytes : 0u);
+  constexpr uint32_t kPl = kSplit ? 2u : 1u;               // operand planes per tile (hi | lo)
+  // stage layout: [A_hi | A_lo | B_hi | B_lo] (A part absent in halo mode: the stage ring then holds B tiles only)
+  const uint32_t stage_bytes = kPl * (p.halo ? b_bytes : a_bytes + b_bytes);
+  const uint32_t win_bytes = kPl * p.halo_bytes;           // one halo window slot: [hi window | lo window]
+  const uint32_t ring_base = smem_base + (p.halo ? (uint32_t)p.a_stages * win_bytes : 0u);
   const uint32_t bar_base = ring_base + p.stages * stage_bytes + (p.tma_store ? (uint32_t)(kEpiWarps * p.stg_bufs) * 4096u : 0u);
   // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2], fullA[a_stages], emptyA[a_stages];
   // then tmem ptr; then bias[2][256]
@@ -437,11 +444,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     // B (or A|B) stage: wait for the slot, post the expected bytes (pair mode: the leader posts both CTAs' bytes, the
     // peer's loads credit the leader's barrier directly; the peer cannot run ahead of the phase because it waits on its
     // own empty barrier, which the leader's multicast commit signals)
-    auto acquire = [&]() {
+    auto acquire = [&](uint32_t bytes) {
       mbar_wait(empty_bar(stage), phase ^ 1u);
       if (el) {
-        if constexpr (!kPair) mbar_expect_tx(full_bar(stage), stage_bytes);
-        else if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * stage_bytes);
+        if constexpr (!kPair) mbar_expect_tx(full_bar(stage), bytes);
+        else if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * bytes);
       }
     };
     auto advance = [&]() { if (++stage == nstages) { stage = 0; phase ^= 1u; } };
@@ -453,13 +460,19 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       if constexpr (kPair) tma_load_5d_2sm(dst, m, bar, c0, cw, ch, ct, cb);
       else tma_load_5d(dst, m, bar, c0, cw, ch, ct, cb);
     };
-    // halo window of one (time tap, 64-channel chunk)
-    auto load_window = [&](const CUtensorMap* m, int c0, int cw, int ch, int ct, int cb) {
+    // weight tile(s) of one K step into the B part of the current stage (split: hi plane, then lo plane at k + b_lo)
+    auto load_b_planes = [&](uint32_t dst, const CUtensorMap* m, int kcol, int n, int wb_) {
+      load_b(dst, m, kcol, n, wb_);
+      if constexpr (kSplit) load_b(dst + b_bytes, m, p.b_lo + kcol, n, wb_);
+    };
+    // halo window of one (time tap, 64-channel chunk); lo_off = channel offset of the lo plane in that tensor
+    auto load_window = [&](const CUtensorMap* m, int c0, int lo_off, int cw, int ch, int ct, int cb) {
       mbar_wait(emptyA_bar(sA), phA ^ 1u);
       if (el) {
-        if constexpr (!kPair) mbar_expect_tx(fullA_bar(sA), p.halo_bytes);
-        else if (rank == 0) mbar_expect_tx(fullA_bar(sA), 2u * p.halo_bytes);
-        load_a(smem_base + (uint32_t)sA * p.halo_bytes, fullA_bar(sA), m, c0, cw, ch, ct, cb);
+        if constexpr (!kPair) mbar_expect_tx(fullA_bar(sA), win_bytes);
+        else if (rank == 0) mbar_expect_tx(fullA_bar(sA), 2u * win_bytes);
+        load_a(smem_base + (uint32_t)sA * win_bytes, fullA_bar(sA), m, c0, cw, ch, ct, cb);
+        if constexpr (kSplit) load_a(smem_base + (uint32_t)sA * win_bytes + p.halo_bytes, fullA_bar(sA), m, lo_off + c0, cw, ch, ct, cb);
       }
       if (++sA == p.a_stages) { sA = 0; phA ^= 1u; }
     };
@@ -474,11 +487,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         if (halo) {
           const CUtensorMap* mapA = from_cache ? &maps.c : &maps.a[0];
           for (int kc = 0; kc < num_kc; ++kc) {
-            load_window(mapA, kc * 64, tc.w0 - p.pw, tc.h0 - p.ph, tv, tc.b);
+            load_window(mapA, kc * 64, p.a_lo, tc.w0 - p.pw, tc.h0 - p.ph, tv, tc.b);
             int kcol = a * nsp * p.Ci + kc * 64;
             for (int sp = 0; sp < nsp; ++sp, kcol += p.Ci) {
-              acquire();
-              if (el) load_b(ring_base + stage * stage_bytes, &maps.b, kcol, tc.n0 + n_off, wb);
+              acquire(stage_bytes);
+              if (el) load_b_planes(ring_base + stage * stage_bytes, &maps.b, kcol, tc.n0 + n_off, wb);
               advance();
             }
           }
@@ -502,11 +515,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
               }
               if (from_cache) mapA = &maps.c;
               for (int kc = 0; kc < num_kc; ++kc) {
-                acquire();
+                acquire(stage_bytes);
                 if (el) {
                   const uint32_t sa = smem_base + stage * stage_bytes;
                   load_a(sa, full_bar(stage), mapA, kc * 64, cw, ch, tv, tc.b);
-                  load_b(sa + a_bytes, &maps.b, kcol + kc * 64, tc.n0 + n_off, wb);
+                  if constexpr (kSplit) load_a(sa + a_bytes, full_bar(stage), mapA, p.a_lo + kc * 64, cw, ch, tv, tc.b);
+                  load_b_planes(sa + kPl * a_bytes, &maps.b, kcol + kc * 64, tc.n0 + n_off, wb);
                 }
                 advance();
               }
@@ -515,17 +529,19 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         }
       }
       // out += I * residual : A = residual tile of this output box, channels [n0 + 64g, +64); B = identity columns
+      // (split: A_hi and A_lo tiles of the residual against the same identity tile; the B_lo slot stays unused)
       for (int g = 0; g < res_steps; ++g) {
         if (halo) {
-          load_window(&maps.r, tc.n0 + g * 64, tc.w0 - p.pw, tc.h0 - p.ph, tc.t0, tc.b);
-          acquire();
+          load_window(&maps.r, tc.n0 + g * 64, p.o_lo, tc.w0 - p.pw, tc.h0 - p.ph, tc.t0, tc.b);
+          acquire(b_bytes);
           if (el) load_b(ring_base + stage * stage_bytes, &maps.e, g * 64, n_off, 0);
         } else {
-          acquire();
+          acquire(kPl * a_bytes + b_bytes);
           if (el) {
             const uint32_t sa = smem_base + stage * stage_bytes;
             load_a(sa, full_bar(stage), &maps.r, tc.n0 + g * 64, tc.w0, tc.h0, tc.t0, tc.b);
-            load_b(sa + a_bytes, &maps.e, g * 64, n_off, 0);
+            if constexpr (kSplit) load_a(sa + a_bytes, full_bar(stage), &maps.r, p.o_lo + tc.n0 + g * 64, tc.w0, tc.h0, tc.t0, tc.b);
+            load_b(sa + kPl * a_bytes, &maps.e, g * 64, n_off, 0);
           }
         }
         advance();
@@ -542,7 +558,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       const uint32_t hi_b = 64u | (1u << 14) | (2u << 29);
       const uint32_t hi_a = halo ? (((uint32_t)p.hP * 8u) | (1u << 14) | (2u << 29)) : hi_b;
       const uint32_t mt_step = halo ? 64u : (uint32_t)(kABytes >> 4);   // next M tile: 8 window rows / 16 KB
-      const uint32_t b_addr0 = halo ? ring_base : smem_base + a_bytes;
+      const uint32_t b_addr0 = halo ? ring_base : smem_base + kPl * a_bytes;
+      const uint32_t a_pl = (halo ? p.halo_bytes : a_bytes) >> 4;       // descriptor distance hi plane -> lo plane (A)
+      const uint32_t b_pl = b_bytes >> 4;                               // (B)
       int stage = 0, sA = 0;
       uint32_t phase = 0, phA = 0;
       uint32_t it = 0;
@@ -551,30 +569,33 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         if constexpr (kPair) umma_f16_2sm_lohi(d, alo, hi_a, blo, hi_b, idesc, acc);
         else umma_f16_lohi(d, alo, hi_a, blo, hi_b, idesc, acc);
       };
+      // the 4 K=16 MMAs of one 64-channel step for one M tile; split: hi*hi + lo*hi (+ hi*lo unless `res`: the residual
+      // steps multiply by the identity, which has no lo plane)
+      auto mma64 = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t acc, bool res) {
+#pragma unroll
+        for (uint32_t j = 0; j < 8u; j += 2u) {
+          mma(d, a_lo + j, b_lo + j, j == 0 ? acc : 1u);
+          if constexpr (kSplit) {
+            mma(d, a_lo + a_pl + j, b_lo + j, 1u);
+            if (!res) mma(d, a_lo + j, b_lo + b_pl + j, 1u);
+          }
+        }
+      };
       // one K step (64 channels): A tile(s) at descriptor word a_lo against the B tile of the current stage
-      auto kstep = [&](uint32_t a_lo, uint32_t acc) {
+      auto kstep = [&](uint32_t a_lo, uint32_t acc, bool res) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         if (el) {
           const uint32_t b_lo = (((b_addr0 + stage * stage_bytes) & 0x3FFFFu) >> 4) | 0x10000u;
-          mma(tmem_d, a_lo, b_lo, acc);
-          mma(tmem_d, a_lo + 2u, b_lo + 2u, 1u);
-          mma(tmem_d, a_lo + 4u, b_lo + 4u, 1u);
-          mma(tmem_d, a_lo + 6u, b_lo + 6u, 1u);
-          if (MT == 2) {
-            const uint32_t a1 = a_lo + mt_step, d1 = tmem_d + BNu;
-            mma(d1, a1, b_lo, acc);
-            mma(d1, a1 + 2u, b_lo + 2u, 1u);
-            mma(d1, a1 + 4u, b_lo + 4u, 1u);
-            mma(d1, a1 + 6u, b_lo + 6u, 1u);
-          }
+          mma64(tmem_d, a_lo, b_lo, acc, res);
+          if (MT == 2) mma64(tmem_d + BNu, a_lo + mt_step, b_lo, acc, res);
           if constexpr (kPair) umma_commit_2sm(empty_bar(stage)); else umma_commit(empty_bar(stage));
         }
         if (++stage == nstages) { stage = 0; phase ^= 1u; }
       };
       auto stage_a_lo = [&]() { return (((smem_base + stage * stage_bytes) & 0x3FFFFu) >> 4) | 0x10000u; };
       auto window_lo = [&](int row0) {
-        return (((smem_base + (uint32_t)sA * p.halo_bytes + (uint32_t)row0 * 128u) & 0x3FFFFu) >> 4) | 0x10000u;
+        return (((smem_base + (uint32_t)sA * win_bytes + (uint32_t)row0 * 128u) & 0x3FFFFu) >> 4) | 0x10000u;
       };
       auto release_window = [&]() {
         if (el) { if constexpr (kPair) umma_commit_2sm(emptyA_bar(sA)); else umma_commit(emptyA_bar(sA)); }
@@ -596,14 +617,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
               mbar_wait(fullA_bar(sA), phA);
               for (int bb = 0; bb < p.kh; ++bb)
                 for (int c = 0; c < p.kw; ++c) {
-                  kstep(window_lo(bb * p.hP + c), accum);
+                  kstep(window_lo(bb * p.hP + c), accum, false);
                   accum = 1;
                 }
               release_window();
             }
           } else {
             for (int s = nsp * num_kc; s > 0; --s) {
-              kstep(stage_a_lo(), accum);
+              kstep(stage_a_lo(), accum, false);
               accum = 1;
             }
           }
@@ -611,10 +632,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         for (int g = 0; g < res_steps; ++g) {
           if (halo) {
             mbar_wait(fullA_bar(sA), phA);
-            kstep(window_lo(p.ph * p.hP + p.pw), 1u);
+            kstep(window_lo(p.ph * p.hP + p.pw), 1u, true);
             release_window();
           } else {
-            kstep(stage_a_lo(), 1u);
+            kstep(stage_a_lo(), 1u, true);
           }
         }
         if (el) { if constexpr (kPair) umma_commit_2sm(tfull_bar(as)); else umma_commit(tfull_bar(as)); }
@@ -662,7 +683,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         for (int i = et; i < p.BN; i += kEpiWarps * 32) {
           b_[i] = (p.bias && tc.n0 + i < p.Co_real) ? p.bias[tc.n0 + i] : 0.f;
           // with SiLU the normalisation produces y/2 directly (silu(y) = h + h*tanh(h), h = y/2)
-          if (p.ln_mode) { const float sc = p.ln_silu ? 0.5f : 1.0f; b_[256 + i] = sc * p.ln_gamma[tc.n0 + i]; b_[512 + i] = sc * p.ln_beta[tc.n0 + i]; }
+          if (p.ln_mode) { const float sc = (p.ln_silu && !kSplit) ? 0.5f : 1.0f; b_[256 + i] = sc * p.ln_gamma[tc.n0 + i]; b_[512 + i] = sc * p.ln_beta[tc.n0 + i]; }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
       }
@@ -689,7 +710,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         const int ta = 2 * t - 1, tb = 2 * t, tcn = 2 * t + 1;
         if (ta >= 0) r0 = p.res + sp + (long long)ta * p.rsT;
         else if (p.res_t_mode == 1) r0 = p.res + sp;
-        else if (p.res_t_mode == 2) r0 = p.res_cache + (((long long)tc.b * p.Ho + h) * p.Wo + w) * (long long)p.Co + tc.n0;
+        else if (p.res_t_mode == 2) r0 = p.res_cache + (((long long)tc.b * p.Ho + h) * p.Wo + w) * (long long)p.Co * (kSplit ? 2 : 1) + tc.n0;
         if (tb < p.resT) r1 = p.res + sp + (long long)tb * p.rsT;
         if (tcn < p.resT) r2 = p.res + sp + (long long)tcn * p.rsT;
       }
@@ -712,23 +733,171 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         ++nstore;
       };
       // packed bf16 words of 64 channels -> staging row (TMA store) or global memory
-      auto put64 = [&](const uint32_t* pk, int ncol, const CUtensorMap* m, bf16* grow, int j) {
+      // (coff: channel offset of the plane being written: 0, or Cout for the lo plane of a split tensor)
+      auto put64 = [&](const uint32_t* pk, int ncol, const CUtensorMap* m, bf16* grow, int j, int coff = 0) {
         if (p.tma_store) {
           uint8_t* my = stage_row();
 #pragma unroll
           for (int g = 0; g < 8; ++g)
             *reinterpret_cast<uint4*>(my + ((g ^ swz) << 4)) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-          store_rows(m, tc.n0 + j);
+          store_rows(m, coff + tc.n0 + j);
         } else if (valid) {
 #pragma unroll
           for (int g = 0; g < 8; ++g)
-            if (g * 8 < ncol) *reinterpret_cast<uint4*>(grow + j + g * 8) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+            if (g * 8 < ncol) *reinterpret_cast<uint4*>(grow + coff + j + g * 8) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
         }
       };
 
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * p.MT + mt) * p.BN);
+      if constexpr (kSplit) {
+        // ---- EXACT_TC epilogue: fp32 values straight from the accumulator (re-read per pass: the main loop is three
+        // times as long as in bf16 mode, the epilogue has the time), two-pass LayerNorm statistics, full-precision
+        // SiLU, results written as hi | lo bf16 planes.
+        const bf16* rl0 = r0 ? r0 + p.o_lo : nullptr;   // lo planes of the residual rows
+        const bf16* rl1 = r1 ? r1 + p.o_lo : nullptr;
+        const bf16* rl2 = r2 ? r2 + p.o_lo : nullptr;
+        auto add_row = [&](const bf16* rh, const bf16* rl, int jj, float sc, float (&f)[32]) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float a[8], b[8];
+            unpack8(*reinterpret_cast<const uint4*>(rh + jj + g * 8), a);
+            unpack8(*reinterpret_cast<const uint4*>(rl + jj + g * 8), b);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[g * 8 + e] = fmaf(sc, a[e] + b[e], f[g * 8 + e]);
+          }
+        };
+        // v = rb * (acc + bias) + ra * R for the 32 channels [jj, jj + 32) of this thread's row
+        auto chunk = [&](int jj, float (&f)[32]) {
+          uint32_t v[32];
+          tmem_ld32(tbase + (uint32_t)jj, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]) + bias_s[jj + e];
+          if (p.rb != 1.0f) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) f[e] *= p.rb;
+          }
+          if (valid && res_direct) {
+            add_row(r0, rl0, jj, p.ra, f);
+          } else if (valid && p.res_mode == 3) {
+            float acc3[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) acc3[e] = 0.f;
+            if (r0) add_row(r0, rl0, jj, 1.0f, acc3);
+            if (r1) add_row(r1, rl1, jj, 1.0f, acc3);
+            if (r2) add_row(r2, rl2, jj, 1.0f, acc3);
+            const float s3 = p.ra * (1.0f / 3.0f);
+#pragma unroll
+            for (int e = 0; e < 32; ++e) f[e] = fmaf(s3, acc3[e], f[e]);
+          }
+        };
+        // sum over this thread's channels of g(v); completed across the two groups when they share a row (MT == 1)
+        float mean = 0.f, rstd = 0.f;
+        if (p.ln_mode) {
+          float* st_ = stat_s + (it & 1u) * 512u;
+          float part = 0.f;
+#pragma unroll 1
+          for (int i = 0; i < 2; ++i) {
+            const int sl = sb + i * ss;
+            if (sl * 2 >= nchunks) break;
+            const int ncol = (sl * 2 + 1 < nchunks) ? 64 : 32;
+#pragma unroll 1
+            for (int hc = 0; hc * 32 < ncol; ++hc) {
+              float f[32];
+              chunk(sl * 64 + hc * 32, f);
+#pragma unroll
+              for (int e = 0; e < 32; ++e) part += f[e];
+            }
+          }
+          if (p.MT == 1) {
+            st_[(grp * 128 + rr) << 1] = part;
+            asm volatile("bar.sync 2, %0;" ::"n"(kEpiWarps * 32) : "memory");
+            part += st_[((grp ^ 1) * 128 + rr) << 1];
+          }
+          mean = part * inv_n;
+          part = 0.f;
+#pragma unroll 1
+          for (int i = 0; i < 2; ++i) {
+            const int sl = sb + i * ss;
+            if (sl * 2 >= nchunks) break;
+            const int ncol = (sl * 2 + 1 < nchunks) ? 64 : 32;
+#pragma unroll 1
+            for (int hc = 0; hc * 32 < ncol; ++hc) {
+              float f[32];
+              chunk(sl * 64 + hc * 32, f);
+#pragma unroll
+              for (int e = 0; e < 32; ++e) { const float d = f[e] - mean; part = fmaf(d, d, part); }
+            }
+          }
+          if (p.MT == 1) {
+            st_[((grp * 128 + rr) << 1) + 1] = part;
+            asm volatile("bar.sync 2, %0;" ::"n"(kEpiWarps * 32) : "memory");
+            part += st_[(((grp ^ 1) * 128 + rr) << 1) + 1];
+          }
+          rstd = 1.0f / sqrtf(part * inv_n + 1e-6f);
+        }
+        auto emit = [&](bool normalized, void* optr, const CUtensorMap* m) {
+          bf16* grow = reinterpret_cast<bf16*>(optr) + ooff + tc.n0;
+#pragma unroll 1
+          for (int i = 0; i < 2; ++i) {
+            const int sl = sb + i * ss;
+            if (sl * 2 >= nchunks) break;
+            const int j = sl * 64;
+            const int ncol = (sl * 2 + 1 < nchunks) ? 64 : 32;
+            uint32_t hw[32], lw[32];
+#pragma unroll
+            for (int hc = 0; hc < 2; ++hc) {
+              if (hc * 32 >= ncol) break;
+              const int jj = j + hc * 32;
+              float f[32];
+              chunk(jj, f);
+              if (normalized) {
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                  float y = (f[e] - mean) * rstd * gamma_s[jj + e] + beta_s[jj + e];
+                  if (p.ln_silu) y = silu_exact(y);
+                  f[e] = y;
+                }
+              }
+              if (p.out_f32) {
+                // external fp32 heads / attention scores: direct stores, only the real output channels
+                if (valid) {
+                  float* of = reinterpret_cast<float*>(optr) + ooff;
+                  if (p.osC == 1 && tc.n0 + jj + 32 <= p.Co_real) {
+#pragma unroll
+                    for (int g = 0; g < 8; ++g)
+                      *reinterpret_cast<float4*>(of + tc.n0 + jj + g * 4) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+                  } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                      if (tc.n0 + jj + e < p.Co_real) of[(long long)(tc.n0 + jj + e) * p.osC] = f[e];
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                  const uint32_t h2 = pack_bf16x2(f[2 * e], f[2 * e + 1]);
+                  hw[hc * 16 + e] = h2;
+                  lw[hc * 16 + e] = pack_bf16x2(f[2 * e] - bf16_lo(h2), f[2 * e + 1] - bf16_hi(h2));
+                }
+              }
+            }
+            if (!p.out_f32) {
+              put64(hw, ncol, m, grow, j, 0);
+              put64(lw, ncol, m, grow, j, p.o_lo);
+            }
+          }
+        };
+        if (store_a) emit(false, p.out, &maps.o);
+        if (p.ln_mode) emit(true, p.ln_mode == 1 ? p.out : p.out2, p.ln_mode == 1 ? &maps.o : &maps.o2);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (kPair) mbar_arrive_remote(tempty_bar(as), 0); else mbar_arrive(tempty_bar(as));
+        }
+      } else {
       uint64_t lsum2 = 0ull, lsq2 = 0ull;      // (even, odd) column partial sums
       uint32_t keep[64];                       // bf16 pairs of this thread's (up to) 128 channels
       // ---- pass A: v = rb*(acc+bias) + ra*R ; stored unless the LayerNorm replaces it; statistics for the LayerNorm
@@ -877,6 +1046,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           put64(o, ncol, nmap, nrow, j);
         }
       }
+      }  // !kSplit
     }
     if (p.tma_store && lane == 0) tma_store_wait_all();
   }
@@ -915,6 +1085,22 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
+// Per-device state: cudaFuncSetAttribute applies to the current device only, and the SM count may differ.
+constexpr int kMaxDev = 64;
+int device_num_sms() {
+  static int sms[kMaxDev] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDev) return 148;
+  if (sms[dev] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    sms[dev] = n > 0 ? n : 148;
+  }
+  return sms[dev];
+}
+cudaError_t ensure_func_attrs();
+
 bool choose_tile(const ConvP& p, int rows, int& BW, int& BH, int& BT, long long* padded_out = nullptr) {
   const bool allow_bt = (p.st == 1) && (p.t_mode == 0);
   long long best = -1;
@@ -944,12 +1130,29 @@ int choose_bn(int Co) {
 
 }  // namespace
 
+namespace {
+cudaError_t ensure_func_attrs() {
+  static bool done[kMaxDev] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDev) return cudaErrorInvalidDevice;
+  if (done[dev]) return cudaSuccess;
+  const int mx = 227 * 1024;
+  cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  if (e == cudaSuccess) done[dev] = true;
+  return e;
+}
+}  // namespace
+
 const char* conv_tc_last_error() { return g_tc_err.c_str(); }
 void conv_tc_set_pair(bool on) { g_pair_mode = on ? 1 : 0; }
 
 // diagnostics: how many 2-CTA clusters of conv_tc_kernel can be co-resident with `smem` dynamic bytes per CTA
 int conv_tc_cluster_query(int smem, char* msg, int cap) {
-  cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+  cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(148);
   cfg.blockDim = dim3(kThreads);
@@ -960,9 +1163,9 @@ int conv_tc_cluster_query(int smem, char* msg, int cap) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int n = -1;
-  cudaError_t e2 = cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<true>, &cfg);
+  cudaError_t e2 = cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<true, false>, &cfg);
   cudaFuncAttributes fa;
-  cudaFuncGetAttributes(&fa, conv_tc_kernel<true>);
+  cudaFuncGetAttributes(&fa, conv_tc_kernel<true, false>);
   snprintf(msg, cap, "setattr=%s occ=%s clusters=%d regs=%d static_smem=%zu maxdyn=%d", cudaGetErrorString(e), cudaGetErrorString(e2), n,
            fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes);
   return n;
@@ -976,9 +1179,11 @@ bool conv_tc_supported(const ConvP& p, DType tout, bool planning) {
   if (p.Ci % 64 != 0) return no("Cin % 64 != 0");
   const int Co_pad = (p.Co + 31) / 32 * 32;
   if (choose_bn(Co_pad) == 0) return no("Cout has no valid N tile");
-  if (p.isC != 1 || p.isW != p.Ci || p.isH != (long long)p.Wi * p.Ci || p.isT != (long long)p.Hi * p.Wi * p.Ci) return no("input is not dense channels-last");
+  const long long cw = p.split ? 2 : 1;
+  if (p.split ? (tout == DT_BF16) : (tout == DT_SPLIT)) return no("activation layout of input and output differ");
+  if (p.isC != 1 || p.isW != cw * p.Ci || p.isH != (long long)p.Wi * cw * p.Ci || p.isT != (long long)p.Hi * p.Wi * cw * p.Ci) return no("input is not dense channels-last");
   if (p.isB % 8 != 0) return no("batch stride not 16-byte aligned");
-  if (tout == DT_BF16) {
+  if (tout != DT_F32) {
     if (p.Co % 32 != 0) return no("bf16 output needs Cout % 32 == 0");
     if (p.osC != 1 || p.osW % 8 != 0 || p.osH % 8 != 0 || p.osT % 8 != 0 || p.osB % 8 != 0) return no("output rows are not 16-byte aligned channels-last");
   }
@@ -987,7 +1192,7 @@ bool conv_tc_supported(const ConvP& p, DType tout, bool planning) {
   if (p.st != 1 && p.st != 2) return no("time stride");
   if (p.ut != 1 || p.uh != 1 || p.uw != 1 || p.t_rep != 0) return no("folded upsampling / replicate prefix");
   if (p.res_mode != 0 && p.res_mode != 1 && p.res_mode != 3) return no("residual mode");
-  if (p.res_mode != 0 && tout != DT_BF16) return no("residual with fp32 output");
+  if (p.res_mode != 0 && tout == DT_F32) return no("residual with fp32 output");
   if (p.t_mode == 2 && p.sh != 1) return no("cache mode with spatial stride");
   if (!planning && p.t_mode == 2 && (!p.cache || p.cacheT <= 0)) return no("cache mode without cache");
   if (p.Wi > 65535 || p.Hi > 65535) return no("extent");
@@ -1000,24 +1205,32 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
                            int w_batches, long long w_batch_stride, const TcLnFusion* ln) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { g_tc_err = "cuTensorMapEncodeTiled unavailable"; return cudaErrorNotSupported; }
+  const bool split = p.split != 0;
+  const int cw = split ? 2 : 1;              // bf16 elements per logical channel (hi | lo planes)
+  const bool out_bf16 = tout != DT_F32;      // DT_BF16, or DT_SPLIT (two bf16 planes)
+  if (split != (tout == DT_SPLIT) && tout != DT_F32) { g_tc_err = "split activations need a split (or fp32) output"; return cudaErrorInvalidValue; }
   TcParams t;
   memset(&t, 0, sizeof(t));
   const int Co_pad = (p.Co + 31) / 32 * 32;
+  const int num_sms = device_num_sms();
+  static int mt_env = -1;     // VT_TC_MT=1: experiment knob, forces one M tile per CTA
+  if (mt_env < 0) { const char* e = getenv("VT_TC_MT"); mt_env = e ? atoi(e) : 2; }
+  static int halo_env = -1;   // VT_TC_HALO=0 switches the halo windows off (experiment knob)
+  if (halo_env < 0) { const char* e = getenv("VT_TC_HALO"); halo_env = e ? atoi(e) : 1; }
+  const bool pair_wanted = pair_mode() == 2 || pair_mode() == 1 || pair_mode() < 0 || (pair_mode() == 3 && choose_bn(Co_pad) == 256);
+  size_t smem = 0;
+  int bn_local = 0;
+  // Tile geometry + shared-memory plan.  Split operands double every operand tile: when the preferred geometry (halo
+  // windows, two M tiles) leaves fewer than 2 pipeline stages, fall back to the next simpler one.
+  auto plan = [&](bool allow_halo, bool allow_mt2) -> int {
+  const int mt_cap = allow_mt2 ? mt_env : 1;
+  t.halo = 0; t.hP = 0; t.a_stages = 0; t.halo_bytes = 0;
   t.BN = choose_bn(Co_pad);
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
-  }
   // two M tiles per CTA tile when the N tile is narrow: one B (weight) tile then feeds 256 output rows, which halves
   // the weight bytes per FLOP (the N<=128 layers are operand-bandwidth bound otherwise)
   t.MT = 1;
   long long pad1 = 0, pad2 = 0;
-  if (!choose_tile(p, 128, t.BW, t.BH, t.BT, &pad1)) { g_tc_err = "no tile shape"; return cudaErrorInvalidValue; }
-  static int mt_cap = -1;   // VT_TC_MT=1: experiment knob, forces one M tile per CTA
-  if (mt_cap < 0) { const char* e = getenv("VT_TC_MT"); mt_cap = e ? atoi(e) : 2; }
+  if (!choose_tile(p, 128, t.BW, t.BH, t.BT, &pad1)) { g_tc_err = "no tile shape"; return -1; }
   if (t.BN <= 128 && mt_cap >= 2) {
     int bw2, bh2, bt2;
     if (choose_tile(p, 256, bw2, bh2, bt2, &pad2) && pad2 <= pad1 + pad1 / 16 &&
@@ -1030,7 +1243,6 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   t.tileBH = t.BH; t.tileBT = t.BT;
   // default policy (VT_TC_PAIR unset): pairs wherever there are enough tiles (N = 128, k133: 1247 -> 1336 TF/s, with the
   // halo window 1343 -> 1599; profiles/notes_r1.md)
-  const bool pair_wanted = pair_mode() == 2 || pair_mode() == 1 || pair_mode() < 0 || (pair_mode() == 3 && t.BN == 256);
   if (w_batches <= 1 && pair_wanted) {
     int bwp, bhp, btp;
     long long padp = 0;
@@ -1047,11 +1259,9 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   }
   // halo mode: spatial taps reuse one shared-memory window (see TcParams::halo)
   {
-    static int halo_env = -1;   // VT_TC_HALO=0 switches the halo windows off (experiment knob)
-    if (halo_env < 0) { const char* e = getenv("VT_TC_HALO"); halo_env = e ? atoi(e) : 1; }
     const bool geom = p.sh == 1 && p.sw == 1 && p.kh * p.kw > 1 && p.kh <= 3 && p.kw <= 3 && p.Ho == p.Hi && p.Wo == p.Wi &&
                       w_batches <= 1 && p.Wo % 8 == 0 && p.Ho % 16 == 0;
-    if (halo_env && geom) {
+    if (allow_halo && halo_env && geom) {
       const long long pos = (long long)p.B * p.To * p.Ho * p.Wo;
       const long long ntl = Co_pad / t.BN;
       int mt = 1;
@@ -1067,10 +1277,57 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
       t.a_stages = 2;
     }
   }
-  t.B = p.B; t.To = p.To; t.Ho = p.Ho; t.Wo = p.Wo; t.Co = p.Co; t.Ti = p.Ti;
   t.tilesW = (p.Wo + t.BW - 1) / t.BW; t.tilesH = (p.Ho + t.tileBH - 1) / t.tileBH; t.tilesT = (p.To + t.tileBT - 1) / t.tileBT;
   t.num_n_tiles = Co_pad / t.BN;
   t.num_tiles = (long long)p.B * t.tilesT * t.tilesH * t.tilesW * t.num_n_tiles;
+  // epilogue strategy
+  t.tma_store = (out_bf16 && p.osC == 1 && t.BN % 64 == 0 && p.osW % 8 == 0 && p.osH % 8 == 0 && p.osT % 8 == 0 && p.osB % 8 == 0 &&
+                 (((uintptr_t)out) & 15) == 0) ? 1 : 0;
+  {
+    // the staging buffers cost a pipeline stage; long-K layers hide the direct-store epilogue behind their main loop
+    int ntaps_eff = p.kt * p.kh * p.kw;
+    if (ntaps_eff * (p.Ci / 64) >= 48) t.tma_store = 0;
+  }
+  bn_local = t.pair ? t.BN / 2 : t.BN;
+  const size_t stage_bytes = (size_t)cw * ((t.halo ? 0 : (size_t)t.MT * kABytes) + (size_t)bn_local * 128);
+  const size_t budget = 222 * 1024;
+  const size_t fixed = 1024 /*align*/ + 8 * 2 * 8 + 64 + 2 * 768 * 4 + 2 * 2 * 128 * 2 * 4 + 256;
+  const size_t a_ring = (size_t)t.a_stages * t.halo_bytes * cw;
+  // one staging buffer per epilogue warp: a second one (VT_TC_STG=2, if the ring keeps >= 3 stages) costs operand
+  // stages, which was measured to matter more (model step 143.3 -> 140.6 ms, profiles/notes_r1.md)
+  t.stg_bufs = 1;
+  static int stg_env = -1;
+  if (stg_env < 0) { const char* e = getenv("VT_TC_STG"); stg_env = e ? atoi(e) : 1; }
+  if (stg_env >= 2 && t.tma_store && budget > fixed + a_ring + (size_t)kEpiWarps * 2 * 4096 &&
+      (budget - fixed - a_ring - (size_t)kEpiWarps * 2 * 4096) / stage_bytes >= 3) t.stg_bufs = 2;
+  const size_t staging = t.tma_store ? (size_t)kEpiWarps * t.stg_bufs * 4096 : 0;
+  if (budget < fixed + staging + a_ring + 2 * stage_bytes) return 1;
+  int stages = (int)((budget - fixed - staging - a_ring) / stage_bytes);
+  if (stages > 8) stages = 8;
+  {
+    static int cap = -1;   // VT_TC_STAGES: experiment knob (pipeline-depth sensitivity)
+    if (cap < 0) { const char* e = getenv("VT_TC_STAGES"); cap = e ? atoi(e) : 0; }
+    if (cap >= 2 && stages > cap) stages = cap;
+  }
+  if (stages < 2) return 1;
+  t.stages = stages;
+  // smem layout from the 1024-aligned base: [halo windows] [stages x (A | B)] [staging] [barriers | tmem slot | bias/gamma/beta | stats]
+  t.stage_off = (uint32_t)(a_ring + stages * stage_bytes);
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(2 * t.MT * t.BN)) cols <<= 1;
+  t.tmem_cols = cols;
+  smem = fixed + staging + a_ring + (size_t)stages * stage_bytes + 8 * (2 * stages + 4 + 2 * t.a_stages);
+  return 0;
+  };
+  {
+    int rc = plan(true, true);
+    if (rc == 1) rc = plan(false, true);
+    if (rc == 1) rc = plan(false, false);
+    if (rc == 1) g_tc_err = "not enough shared memory for 2 stages";
+    if (rc != 0) return cudaErrorInvalidValue;
+  }
+  t.split = split ? 1 : 0; t.a_lo = p.Ci; t.b_lo = Kpad; t.o_lo = p.Co;
+  t.B = p.B; t.To = p.To; t.Ho = p.Ho; t.Wo = p.Wo; t.Co = p.Co; t.Ti = p.Ti;
   t.kt = p.kt; t.kh = p.kh; t.kw = p.kw; t.Ci = p.Ci; t.num_kc = p.Ci / 64;
   t.st = p.st; t.pt = p.pt; t.ph = p.ph; t.pw = p.pw; t.to_off = p.to_off; t.sp = p.sh;
   t.t_mode = p.t_mode; t.cacheT = p.cacheT;
@@ -1081,59 +1338,24 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   t.out_f32 = (tout == DT_F32) ? 1 : 0;
   t.Co_real = p.Co;
   if (ln && ln->mode) {
-    if (t.BN != p.Co || tout != DT_BF16) { g_tc_err = "fused LayerNorm needs one N tile covering Cout and bf16 output"; return cudaErrorInvalidValue; }
+    if (t.BN != p.Co || !out_bf16) { g_tc_err = "fused LayerNorm needs one N tile covering Cout and bf16 output"; return cudaErrorInvalidValue; }
     t.ln_mode = ln->mode; t.ln_silu = ln->silu ? 1 : 0; t.ln_gamma = ln->gamma; t.ln_beta = ln->beta; t.out2 = ln->out2;
   }
   t.w_batched = w_batches > 1 ? 1 : 0;
   if (t.w_batched && w_batches != p.B) { g_tc_err = "batched weights need one weight matrix per batch element"; return cudaErrorInvalidValue; }
-  // epilogue strategy
-  t.tma_store = (tout == DT_BF16 && p.osC == 1 && t.BN % 64 == 0 && p.osW % 8 == 0 && p.osH % 8 == 0 && p.osT % 8 == 0 && p.osB % 8 == 0 &&
-                 (((uintptr_t)out) & 15) == 0) ? 1 : 0;
-  {
-    // the staging buffers cost a pipeline stage; long-K layers hide the direct-store epilogue behind their main loop
-    int ntaps_eff = p.kt * p.kh * p.kw;
-    if (ntaps_eff * t.num_kc >= 48) t.tma_store = 0;
-  }
   {
     static int ev_env = -1;   // VT_TC_EVICT=0: experiment knob
     if (ev_env < 0) { const char* e = getenv("VT_TC_EVICT"); ev_env = e ? atoi(e) : 1; }
-    const double out_bytes = (double)p.B * p.To * p.Ho * p.Wo * p.Co * 2.0;
+    const double out_bytes = (double)p.B * p.To * p.Ho * p.Wo * p.Co * 2.0 * cw;
     t.store_stream = (ev_env && out_bytes > 256e6) ? 1 : 0;
   }
   t.res_mma = (p.res_mode == 1 && p.ra == 1.0f && p.rb == 1.0f && t.BN % 64 == 0 && p.Co % 64 == 0 && p.rsW % 8 == 0 && p.rsH % 8 == 0 &&
                p.rsT % 8 == 0 && p.rsB % 8 == 0 && (((uintptr_t)p.res) & 15) == 0) ? 1 : 0;
-  const int bn_local = t.pair ? t.BN / 2 : t.BN;
-  const size_t stage_bytes = (t.halo ? 0 : (size_t)t.MT * kABytes) + (size_t)bn_local * 128;
-  const size_t budget = 222 * 1024;
-  const size_t fixed = 1024 /*align*/ + 8 * 2 * 8 + 64 + 2 * 768 * 4 + 2 * 2 * 128 * 2 * 4 + 256;
-  const size_t a_ring = (size_t)t.a_stages * t.halo_bytes;
-  // one staging buffer per epilogue warp: a second one (VT_TC_STG=2, if the ring keeps >= 3 stages) costs operand
-  // stages, which was measured to matter more (model step 143.3 -> 140.6 ms, profiles/notes_r1.md)
-  t.stg_bufs = 1;
-  static int stg_env = -1;
-  if (stg_env < 0) { const char* e = getenv("VT_TC_STG"); stg_env = e ? atoi(e) : 1; }
-  if (stg_env >= 2 && t.tma_store && (budget - fixed - a_ring - (size_t)kEpiWarps * 2 * 4096) / stage_bytes >= 3) t.stg_bufs = 2;
-  const size_t staging = t.tma_store ? (size_t)kEpiWarps * t.stg_bufs * 4096 : 0;
-  int stages = (int)((budget - fixed - staging - a_ring) / stage_bytes);
-  if (stages > 8) stages = 8;
-  {
-    static int cap = -1;   // VT_TC_STAGES: experiment knob (pipeline-depth sensitivity)
-    if (cap < 0) { const char* e = getenv("VT_TC_STAGES"); cap = e ? atoi(e) : 0; }
-    if (cap >= 2 && stages > cap) stages = cap;
-  }
-  if (stages < 2) { g_tc_err = "not enough shared memory for 2 stages"; return cudaErrorInvalidValue; }
-  t.stages = stages;
-  // smem layout from the 1024-aligned base: [stages x (A | B)] [staging 2 x 16 KB] [barriers | tmem slot | bias/gamma/beta | stats]
-  t.stage_off = (uint32_t)(a_ring + stages * stage_bytes);
-  uint32_t cols = 32;
-  while (cols < (uint32_t)(2 * t.MT * t.BN)) cols <<= 1;
-  t.tmem_cols = cols;
-  const size_t smem = fixed + staging + a_ring + (size_t)stages * stage_bytes + 8 * (2 * stages + 4 + 2 * t.a_stages);
 
   TcMaps maps;
   // activation view: element (c, w, h, t, b) at base + c + w*sw_ + h*sh_ + t*isT + b*bs  (elements)
   auto encode_act = [&](CUtensorMap* m, const bf16* base, int Wn, int Hn, long long sw_, long long sh_, int Tn, long long st_, long long bs) -> bool {
-    cuuint64_t dims[5] = {(cuuint64_t)p.Ci, (cuuint64_t)Wn, (cuuint64_t)Hn, (cuuint64_t)Tn, (cuuint64_t)p.B};
+    cuuint64_t dims[5] = {(cuuint64_t)(cw * p.Ci), (cuuint64_t)Wn, (cuuint64_t)Hn, (cuuint64_t)Tn, (cuuint64_t)p.B};
     cuuint64_t strides[4] = {(cuuint64_t)sw_ * 2, (cuuint64_t)sh_ * 2, (cuuint64_t)st_ * 2, (cuuint64_t)bs * 2};
     cuuint32_t box[5] = {64, (cuuint32_t)t.BW, (cuuint32_t)t.BH, (cuuint32_t)t.BT, 1};
     if (t.halo) { box[1] = (cuuint32_t)t.hP; box[2] = (cuuint32_t)(16 + p.kh - 1); }
@@ -1157,14 +1379,15 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   }
   if (p.t_mode == 2) {
     if (p.sh != 1) { g_tc_err = "cache mode with spatial stride"; return cudaErrorInvalidValue; }
-    if (!encode_act(&maps.c, (const bf16*)p.cache, p.Wi, p.Hi, p.isW, p.isH, p.cacheT, p.isT, (long long)p.cacheT * p.Hi * p.Wi * p.Ci)) return cudaErrorInvalidValue;
+    if (!encode_act(&maps.c, (const bf16*)p.cache, p.Wi, p.Hi, p.isW, p.isH, p.cacheT, p.isT, (long long)p.cacheT * p.Hi * p.Wi * p.Ci * cw)) return cudaErrorInvalidValue;
   } else {
     maps.c = maps.a[0];
   }
   {
     const int nb = w_batches > 1 ? w_batches : 1;
-    cuuint64_t dims[3] = {(cuuint64_t)Kpad, (cuuint64_t)Co_pad, (cuuint64_t)nb};
-    cuuint64_t strides[2] = {(cuuint64_t)Kpad * 2, (cuuint64_t)(nb > 1 ? w_batch_stride : (long long)Kpad * Co_pad) * 2};
+    // split weights: [Co_pad][hi(Kpad) | lo(Kpad)]
+    cuuint64_t dims[3] = {(cuuint64_t)(cw * Kpad), (cuuint64_t)Co_pad, (cuuint64_t)nb};
+    cuuint64_t strides[2] = {(cuuint64_t)(cw * Kpad) * 2, (cuuint64_t)(nb > 1 ? w_batch_stride : (long long)cw * Kpad * Co_pad) * 2};
     cuuint32_t box[3] = {64, (cuuint32_t)bn_local, 1};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = enc(&maps.b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(w_nk), dims, strides, box, es,
@@ -1174,7 +1397,7 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   }
   // output / residual maps (output geometry) and the identity used by the residual-through-MMA K steps
   auto encode_out = [&](CUtensorMap* m, const void* base, int Tn, long long sW, long long sH, long long sT, long long sB, int bw, int bh, int bt) -> bool {
-    cuuint64_t dims[5] = {(cuuint64_t)p.Co, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)Tn, (cuuint64_t)p.B};
+    cuuint64_t dims[5] = {(cuuint64_t)(cw * p.Co), (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)Tn, (cuuint64_t)p.B};
     cuuint64_t strides[4] = {(cuuint64_t)sW * 2, (cuuint64_t)sH * 2, (cuuint64_t)sT * 2, (cuuint64_t)sB * 2};
     cuuint32_t box[5] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bt, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
@@ -1213,12 +1436,9 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { g_tc_err = "cuTensorMapEncodeTiled(identity) failed: " + std::to_string((int)r); return cudaErrorInvalidValue; }
   }
-  static bool smem_set = false;
-  if (!smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+  {
+    cudaError_t e = ensure_func_attrs();
     if (e != cudaSuccess) { g_tc_err = "cudaFuncSetAttribute(smem)"; return e; }
-    smem_set = true;
   }
   unsigned grid = (unsigned)(t.num_tiles < num_sms ? t.num_tiles : num_sms);
   if (t.pair) {
@@ -1228,8 +1448,8 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   const double Mrows = (double)p.B * p.To * p.Ho * p.Wo;
   char det[96] = "";
   if (prof_enabled()) snprintf(det, sizeof(det), "k%d%d%d s%d%d %d->%d @%dx%dx%d tile%dx%dx%d bn%d mt%d%s", p.kt, p.kh, p.kw, p.st, p.sh, p.Ci, p.Co, p.To, p.Ho, p.Wo, t.tileBT, t.tileBH, t.BW, t.BN, t.MT, t.pair ? (t.halo ? " pair halo" : " pair") : (t.halo ? " halo" : ""));
-  ProfScope _ps("conv_tc", 2.0 * Mrows * p.kt * p.kh * p.kw * p.Ci * p.Co,
-                2.0 * ((double)p.B * p.Ti * p.Hi * p.Wi * p.Ci) + Mrows * p.Co * (tout == DT_F32 ? 4.0 : 2.0), s, det);
+  ProfScope _ps(split ? "conv_tc3" : "conv_tc", 2.0 * Mrows * p.kt * p.kh * p.kw * p.Ci * p.Co,
+                2.0 * cw * ((double)p.B * p.Ti * p.Hi * p.Wi * p.Ci) + Mrows * p.Co * (tout == DT_F32 ? 4.0 : 2.0 * cw), s, det);
   if (t.pair) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -1241,11 +1461,13 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, maps, t);
+    cudaError_t e = split ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true>, maps, t)
+                          : cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false>, maps, t);
     count_launch();
     return e != cudaSuccess ? e : cudaGetLastError();
   }
-  conv_tc_kernel<false><<<grid, kThreads, smem, s>>>(maps, t);
+  if (split) conv_tc_kernel<false, true><<<grid, kThreads, smem, s>>>(maps, t);
+  else conv_tc_kernel<false, false><<<grid, kThreads, smem, s>>>(maps, t);
   count_launch();
   return cudaGetLastError();
 }

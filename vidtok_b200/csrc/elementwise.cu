@@ -89,6 +89,85 @@ template <bool EXACT> __device__ __forceinline__ float act_silu(float x) {
   return EXACT ? silu_exact(x) : silu_f(x);
 }
 
+// ---- row accessors: one code path for plain (fp32 / bf16) rows and hi|lo split rows (DT_SPLIT, kernels.h) ----------
+// A split row of C logical channels is 2*C bf16 values: [hi(C) | lo(C)], value = hi + lo.
+struct split16 { bf16 v; };
+template <typename T> struct RowAcc {
+  static constexpr int W = 1;
+  static __device__ __forceinline__ float ld(const T* row, int C, int c) { return to_f(row[c]); }
+  static __device__ __forceinline__ void st(T* row, int C, int c, float v) { row[c] = from_f<T>(v); }
+};
+template <> struct RowAcc<split16> {
+  static constexpr int W = 2;
+  static __device__ __forceinline__ float ld(const split16* row, int C, int c) {
+    return __bfloat162float(row[c].v) + __bfloat162float(row[C + c].v);
+  }
+  static __device__ __forceinline__ void st(split16* row, int C, int c, float v) {
+    const bf16 h = __float2bfloat16_rn(v);
+    row[c].v = h;
+    row[C + c].v = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+};
+__device__ __forceinline__ void split8(const float (&f)[8], uint4& hi, uint4& lo) {
+  __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&hi);
+  __nv_bfloat162* l2 = reinterpret_cast<__nv_bfloat162*>(&lo);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h2[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    l2[i] = __floats2bfloat162_rn(f[2 * i] - __low2float(h2[i]), f[2 * i + 1] - __high2float(h2[i]));
+  }
+}
+__device__ __forceinline__ void join8(const uint4& hi, const uint4& lo, float (&f)[8]) {
+  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&hi);
+  const __nv_bfloat162* l2 = reinterpret_cast<const __nv_bfloat162*>(&lo);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __low2float(h2[i]) + __low2float(l2[i]);
+    f[2 * i + 1] = __high2float(h2[i]) + __high2float(l2[i]);
+  }
+}
+// LayerNorm(+SiLU) of split rows (EXACT_TC mode, C % 8 == 0): one warp per position, fp32 two-pass statistics,
+// full-precision SiLU; the row (<= 2 KB) is re-read from L1 for the second and third pass.
+template <bool SILU>
+__global__ void __launch_bounds__(256) layernorm_split_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, bf16* __restrict__ y,
+                                                              long long rows, int C) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const bf16* xr = x + row * 2 * C;
+  bf16* yr = y + row * 2 * C;
+  float s = 0.f;
+  for (int c = lane * 8; c < C; c += 256) {
+    float f[8];
+    join8(*reinterpret_cast<const uint4*>(xr + c), *reinterpret_cast<const uint4*>(xr + C + c), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += f[i];
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+  for (int c = lane * 8; c < C; c += 256) {
+    float f[8];
+    join8(*reinterpret_cast<const uint4*>(xr + c), *reinterpret_cast<const uint4*>(xr + C + c), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float d = f[i] - mean; q = fmaf(d, d, q); }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + 1e-6f);
+  for (int c = lane * 8; c < C; c += 256) {
+    float f[8];
+    join8(*reinterpret_cast<const uint4*>(xr + c), *reinterpret_cast<const uint4*>(xr + C + c), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float t = (f[i] - mean) * rstd * gamma[c + i] + beta[c + i];
+      f[i] = SILU ? silu_exact(t) : t;
+    }
+    uint4 hi, lo;
+    split8(f, hi, lo);
+    *reinterpret_cast<uint4*>(yr + c) = hi;
+    *reinterpret_cast<uint4*>(yr + C + c) = lo;
+  }
+}
+
 // ---- LayerNorm over channels (model_3dcausal.py:62-80; eps 1e-6, affine), optional SiLU (:26-27) --------
 // One warp per position; VPL vectors of 4 channels per lane held in registers (C == 128*VPL).
 template <typename T, int VPL, bool SILU, bool EXACT>
@@ -223,21 +302,22 @@ __global__ void __launch_bounds__(256) layernorm_gen_kernel(const T* __restrict_
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
-  const T* xr = x + row * C;
+  using A = RowAcc<T>;
+  const T* xr = x + row * C * A::W;
   float s = 0.f;
-  for (int c = lane; c < C; c += 32) s += to_f(xr[c]);
+  for (int c = lane; c < C; c += 32) s += A::ld(xr, C, c);
   const float mean = warp_sum(s) / C;
   float q = 0.f;
   for (int c = lane; c < C; c += 32) {
-    float d = to_f(xr[c]) - mean;
+    float d = A::ld(xr, C, c) - mean;
     q = fmaf(d, d, q);
   }
   const float var = warp_sum(q) / C;
   const float rstd = 1.0f / sqrtf(var + 1e-6f);
-  T* yr = y + row * C;
+  T* yr = y + row * C * A::W;
   for (int c = lane; c < C; c += 32) {
-    float t = (to_f(xr[c]) - mean) * rstd * gamma[c] + beta[c];
-    yr[c] = from_f<T>(SILU ? act_silu<EXACT>(t) : t);
+    float t = (A::ld(xr, C, c) - mean) * rstd * gamma[c] + beta[c];
+    A::st(yr, C, c, SILU ? act_silu<EXACT>(t) : t);
   }
 }
 
@@ -249,7 +329,8 @@ __global__ void __launch_bounds__(256) groupnorm_stats_kernel(const T* __restric
   const int cpg = C / 32;
   const long long frame = blockIdx.x / 32;
   const int g = blockIdx.x % 32;
-  const T* base = x + frame * pos_per_frame * C + g * cpg;
+  using A = RowAcc<T>;
+  const T* base = x + frame * pos_per_frame * C * A::W;
   const long long n = pos_per_frame * cpg;
   __shared__ float red[32];
   __shared__ float bc;
@@ -268,11 +349,11 @@ __global__ void __launch_bounds__(256) groupnorm_stats_kernel(const T* __restric
     return r;
   };
   float s = 0.f;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) s += to_f(base[(i / cpg) * C + (i % cpg)]);
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) s += A::ld(base + (i / cpg) * C * A::W, C, g * cpg + (int)(i % cpg));
   const float mean = block_sum(s) / (float)n;
   float q = 0.f;
   for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-    float d = to_f(base[(i / cpg) * C + (i % cpg)]) - mean;
+    float d = A::ld(base + (i / cpg) * C * A::W, C, g * cpg + (int)(i % cpg)) - mean;
     q = fmaf(d, d, q);
   }
   const float var = block_sum(q) / (float)n;
@@ -288,11 +369,13 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const T* __restric
                                                               long long total, long long pos_per_frame, int C) {
   const int cpg = C / 32;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    using A = RowAcc<T>;
     const int c = (int)(i % C);
-    const long long frame = (i / C) / pos_per_frame;
+    const long long pos = i / C;
+    const long long frame = pos / pos_per_frame;
     const float* st = stats + 2 * (frame * 32 + c / cpg);
-    float t = (to_f(x[i]) - st[0]) * st[1] * gamma[c] + beta[c];
-    y[i] = from_f<T>(SILU ? act_silu<EXACT>(t) : t);
+    float t = (A::ld(x + pos * C * A::W, C, c) - st[0]) * st[1] * gamma[c] + beta[c];
+    A::st(y + pos * C * A::W, C, c, SILU ? act_silu<EXACT>(t) : t);
   }
 }
 // per-position variant: statistics over the C/32 channels of one position (the temporal 1D blocks,
@@ -306,20 +389,22 @@ __global__ void __launch_bounds__(256) groupnorm_pos_kernel(const T* __restrict_
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long pos = i / 32;
     const int g = (int)(i % 32);
-    const T* xr = x + pos * C + g * cpg;
+    using A = RowAcc<T>;
+    const T* xr = x + pos * C * A::W;
+    const int c0 = g * cpg;
     float s = 0.f;
-    for (int c = 0; c < cpg; ++c) s += to_f(xr[c]);
+    for (int c = 0; c < cpg; ++c) s += A::ld(xr, C, c0 + c);
     const float mean = s / cpg;
     float q = 0.f;
     for (int c = 0; c < cpg; ++c) {
-      float d = to_f(xr[c]) - mean;
+      float d = A::ld(xr, C, c0 + c) - mean;
       q = fmaf(d, d, q);
     }
     const float rstd = 1.0f / sqrtf(q / cpg + 1e-6f);
-    T* yr = y + pos * C + g * cpg;
+    T* yr = y + pos * C * A::W;
     for (int c = 0; c < cpg; ++c) {
-      float t = (to_f(xr[c]) - mean) * rstd * gamma[g * cpg + c] + beta[g * cpg + c];
-      yr[c] = from_f<T>(SILU ? act_silu<EXACT>(t) : t);
+      float t = (A::ld(xr, C, c0 + c) - mean) * rstd * gamma[c0 + c] + beta[c0 + c];
+      A::st(yr, C, c0 + c, SILU ? act_silu<EXACT>(t) : t);
     }
   }
 }
@@ -327,8 +412,9 @@ __global__ void __launch_bounds__(256) groupnorm_pos_kernel(const T* __restrict_
 // ---- softmax over rows of fp32 scores -> P (attention, model_3dcausal.py:140) -----------------------------
 template <typename TOut>
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ S, TOut* __restrict__ P, int N) {
+  using A = RowAcc<TOut>;
   const float* s = S + (long long)blockIdx.x * N;
-  TOut* p = P + (long long)blockIdx.x * N;
+  TOut* p = P + (long long)blockIdx.x * N * A::W;
   __shared__ float red[8];
   __shared__ float bc;
   float m = -INFINITY;
@@ -356,7 +442,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
   }
   __syncthreads();
   const float inv = 1.0f / bc;
-  for (int i = threadIdx.x; i < N; i += 256) p[i] = from_f<TOut>(expf(s[i] - m) * inv);
+  for (int i = threadIdx.x; i < N; i += 256) A::st(p, N, i, expf(s[i] - m) * inv);
 }
 
 // ---- KL: DiagonalGaussianDistribution (distributions.py:5-28) + regularizer (regularizers.py:82-92) ------
@@ -457,8 +543,18 @@ __global__ void pack_w_kn_kernel(const float* __restrict__ w, float* __restrict_
   }
 }
 struct CollapseMap { int mt[3], mh[3], mw[3]; };
+// split != 0: rows are [hi(K) | lo(K)] (row length 2*K), lo = bf16(v - hi)
+__device__ __forceinline__ void put_w(bf16* out, long long row, int K, int k, float v, int split) {
+  const bf16 h = __float2bfloat16_rn(v);
+  if (split) {
+    out[row * 2 * K + k] = h;
+    out[row * 2 * K + K + k] = __float2bfloat16_rn(v - __bfloat162float(h));
+  } else {
+    out[row * K + k] = h;
+  }
+}
 __global__ void pack_w_collapsed_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Co, int Co_pad, int Ci,
-                                        int kt, int kh, int kw, CollapseMap cm, int kt2, int kh2, int kw2) {
+                                        int kt, int kh, int kw, CollapseMap cm, int kt2, int kh2, int kw2, int split) {
   const int K2 = kt2 * kh2 * kw2 * Ci;
   const long long total = (long long)Co_pad * K2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -473,11 +569,11 @@ __global__ void pack_w_collapsed_kernel(const float* __restrict__ w, bf16* __res
           for (int c = 0; c < kw; ++c)
             if (cm.mt[a] == a2 && cm.mh[b] == b2 && cm.mw[c] == c2)
               v += w[((long long)co * Ci + ci) * (kt * kh * kw) + (a * kh + b) * kw + c];
-    out[i] = __float2bfloat16_rn(v);
+    put_w(out, co, K2, k, v, split);
   }
 }
 __global__ void pack_w_nk_bf16_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Co, int Co_pad, int Ci, int taps,
-                                      int Kpad) {
+                                      int Kpad, int split) {
   const long long total = (long long)Co_pad * Kpad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(i % Kpad);
@@ -487,7 +583,7 @@ __global__ void pack_w_nk_bf16_kernel(const float* __restrict__ w, bf16* __restr
       const int tap = k / Ci, ci = k % Ci;
       v = w[((long long)co * Ci + ci) * taps + tap];
     }
-    out[i] = __float2bfloat16_rn(v);
+    put_w(out, co, Kpad, k, v, split);
   }
 }
 
@@ -514,6 +610,53 @@ __global__ void __launch_bounds__(256) time_interp2x_kernel(const T* __restrict_
 #pragma unroll
     for (int k = 0; k < 4; ++k) o[k] = __fadd_rn(__fmul_rn(l0, a[k]), __fmul_rn(l1, c[k]));
     store4(y + (b * 2 * Tn + j) * hwc + e, o);
+  }
+}
+// split rows: row = one position (2*C bf16); interpolate hi + lo in fp32 and re-split
+__global__ void __launch_bounds__(256) time_interp2x_split_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int B, int Tn,
+                                                                  long long hw, int C) {
+  const int c8 = C / 8;
+  const long long total = (long long)B * 2 * Tn * hw * c8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c8) * 8;
+    long long r = i / c8;
+    const long long pos = r % hw; r /= hw;
+    const int j = (int)(r % (2 * Tn));
+    const long long b = r / (2 * Tn);
+    float src = 0.5f * ((float)j + 0.5f) - 0.5f;
+    src = src < 0.f ? 0.f : src;
+    const int i0 = (int)src;
+    const int i1 = i0 + ((i0 < Tn - 1) ? 1 : 0);
+    const float l1 = src - (float)i0, l0 = 1.0f - l1;
+    const bf16* r0 = x + ((b * Tn + i0) * hw + pos) * 2 * C;
+    const bf16* r1 = x + ((b * Tn + i1) * hw + pos) * 2 * C;
+    float a[8], d[8], o[8];
+    join8(*reinterpret_cast<const uint4*>(r0 + c), *reinterpret_cast<const uint4*>(r0 + C + c), a);
+    join8(*reinterpret_cast<const uint4*>(r1 + c), *reinterpret_cast<const uint4*>(r1 + C + c), d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = __fadd_rn(__fmul_rn(l0, a[k]), __fmul_rn(l1, d[k]));
+    uint4 hi, lo;
+    split8(o, hi, lo);
+    bf16* yr = y + ((b * 2 * Tn + j) * hw + pos) * 2 * C;
+    *reinterpret_cast<uint4*>(yr + c) = hi;
+    *reinterpret_cast<uint4*>(yr + C + c) = lo;
+  }
+}
+// x [batch][rows][hi(cols) | lo(cols)] -> y [batch][cols][hi(rows) | lo(rows)]
+__global__ void __launch_bounds__(256) transpose_split_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int rows, int cols) {
+  __shared__ bf16 tile[2][32][34];
+  const bf16* xb = x + (long long)blockIdx.z * rows * cols * 2;
+  bf16* yb = y + (long long)blockIdx.z * rows * cols * 2;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    tile[0][i][tx] = xb[(long long)(r0 + i) * 2 * cols + c0 + tx];
+    tile[1][i][tx] = xb[(long long)(r0 + i) * 2 * cols + cols + c0 + tx];
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    yb[(long long)(c0 + i) * 2 * rows + r0 + tx] = tile[0][tx][i];
+    yb[(long long)(c0 + i) * 2 * rows + rows + r0 + tx] = tile[1][tx][i];
   }
 }
 template <typename T>
@@ -558,7 +701,7 @@ __global__ void __launch_bounds__(256) ncdhw_to_cl_kernel(const float* __restric
     int t = (int)(r % (Tn + t_rep)) - t_rep;
     const long long b = r / (Tn + t_rep);
     t = t < 0 ? 0 : t;
-    y[i] = from_f<T>(x[((b * C + c) * Tn + t) * hw + p]);
+    RowAcc<T>::st(y + (i / C) * C * RowAcc<T>::W, C, c, x[((b * C + c) * Tn + t) * hw + p]);
   }
 }
 // v1.1 causal cache update (model_3dcausal_v1_1.py:159-176,216-233): with xp = [pad (P frames)][x (Tc frames)],
@@ -645,6 +788,18 @@ __global__ void pack_w_tap_planes_kernel(const float* __restrict__ w, bf16* __re
   }
 }
 
+// hi|lo split rows <-> fp32 rows (small fallbacks of the EXACT_TC mode)
+__global__ void __launch_bounds__(256) split_to_f32_kernel(const split16* __restrict__ x, float* __restrict__ y, long long rows, int C) {
+  const long long total = rows * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    y[i] = RowAcc<split16>::ld(x + (i / C) * 2 * C, C, (int)(i % C));
+}
+__global__ void __launch_bounds__(256) f32_to_split_kernel(const float* __restrict__ x, split16* __restrict__ y, long long rows, int C) {
+  const long long total = rows * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    RowAcc<split16>::st(y + (i / C) * 2 * C, C, (int)(i % C), x[i]);
+}
+
 inline int grid_for(long long total, int block = 256) {
   long long g = (total + block - 1) / block;
   const long long cap = 148LL * 16;
@@ -671,7 +826,14 @@ cudaError_t launch_layernorm(DType t, const void* x, const float* gamma, const f
     if (silu) layernorm_gen_kernel<T, true, true><<<grid, 256, 0, s>>>((const T*)x, gamma, beta, (T*)y, rows, C);    \
     else layernorm_gen_kernel<T, false, true><<<grid, 256, 0, s>>>((const T*)x, gamma, beta, (T*)y, rows, C);        \
   } while (0)
-  if (t == DT_F32) {
+  if (t == DT_SPLIT) {
+    if (C % 8 == 0) {
+      if (silu) layernorm_split_kernel<true><<<grid, 256, 0, s>>>((const bf16*)x, gamma, beta, (bf16*)y, rows, C);
+      else layernorm_split_kernel<false><<<grid, 256, 0, s>>>((const bf16*)x, gamma, beta, (bf16*)y, rows, C);
+    } else {
+      VT_LN_GEN(split16);
+    }
+  } else if (t == DT_F32) {
     if (C == 128) VT_LN_VEC(float, 1);
     else if (C == 256) VT_LN_VEC(float, 2);
     else if (C == 512) VT_LN_VEC(float, 4);
@@ -722,6 +884,7 @@ cudaError_t launch_groupnorm(DType t, const void* x, const float* gamma, const f
   } while (0)
   (void)exact;
   if (t == DT_F32) VT_GN(float);
+  else if (t == DT_SPLIT) VT_GN(split16);
   else VT_GN(bf16);
 #undef VT_GN
   return cudaGetLastError();
@@ -731,6 +894,7 @@ cudaError_t launch_softmax_rows(DType tout, const float* S, void* P, long long r
   ProfScope _ps("softmax", 0.0, (double)rows * N * (4.0 + dtype_size(tout)), s);
   if (rows == 0) return cudaSuccess;
   if (tout == DT_F32) softmax_rows_kernel<float><<<(unsigned)rows, 256, 0, s>>>(S, (float*)P, N);
+  else if (tout == DT_SPLIT) softmax_rows_kernel<split16><<<(unsigned)rows, 256, 0, s>>>(S, (split16*)P, N);
   else softmax_rows_kernel<bf16><<<(unsigned)rows, 256, 0, s>>>(S, (bf16*)P, N);
   count_launch();
   return cudaGetLastError();
@@ -772,20 +936,31 @@ cudaError_t launch_pack_w_kn(const float* w, float* out, int Co, int Ci, int tap
   return cudaGetLastError();
 }
 cudaError_t launch_pack_w_collapsed(const float* w, bf16* out, int Co, int Co_pad, int Ci, int kt, int kh, int kw,
-                                    const int* mt, const int* mh, const int* mw, int kt2, int kh2, int kw2, cudaStream_t s) {
+                                    const int* mt, const int* mh, const int* mw, int kt2, int kh2, int kw2, cudaStream_t s,
+                                    bool split) {
   CollapseMap cm;
   for (int i = 0; i < 3; ++i) { cm.mt[i] = i < kt ? mt[i] : -1; cm.mh[i] = i < kh ? mh[i] : -1; cm.mw[i] = i < kw ? mw[i] : -1; }
-  pack_w_collapsed_kernel<<<grid_for((long long)Co_pad * kt2 * kh2 * kw2 * Ci), 256, 0, s>>>(w, out, Co, Co_pad, Ci, kt, kh, kw, cm, kt2, kh2, kw2);
+  pack_w_collapsed_kernel<<<grid_for((long long)Co_pad * kt2 * kh2 * kw2 * Ci), 256, 0, s>>>(w, out, Co, Co_pad, Ci, kt, kh, kw, cm, kt2, kh2, kw2, split ? 1 : 0);
   count_launch();
   return cudaGetLastError();
 }
-cudaError_t launch_pack_w_nk_bf16(const float* w, bf16* out, int Co, int Co_pad, int Ci, int taps, int Kpad, cudaStream_t s) {
-  pack_w_nk_bf16_kernel<<<grid_for((long long)Co_pad * Kpad), 256, 0, s>>>(w, out, Co, Co_pad, Ci, taps, Kpad);
+cudaError_t launch_pack_w_nk_bf16(const float* w, bf16* out, int Co, int Co_pad, int Ci, int taps, int Kpad, cudaStream_t s,
+                                  bool split) {
+  pack_w_nk_bf16_kernel<<<grid_for((long long)Co_pad * Kpad), 256, 0, s>>>(w, out, Co, Co_pad, Ci, taps, Kpad, split ? 1 : 0);
   count_launch();
   return cudaGetLastError();
 }
-cudaError_t launch_time_interp2x(DType t, const void* x, void* y, int B, int T, long long hwc, cudaStream_t s) {
+cudaError_t launch_time_interp2x(DType t, const void* x, void* y, int B, int T, long long hw, int C, cudaStream_t s) {
+  const long long hwc = hw * C;
   ProfScope _ps("time_interp2x", 0.0, 3.0 * B * T * hwc * (double)dtype_size(t), s);
+  if (t == DT_SPLIT) {
+    if (C % 8 != 0) return cudaErrorInvalidValue;
+    const long long tot = (long long)B * 2 * T * hw * (C / 8);
+    if (tot == 0) return cudaSuccess;
+    time_interp2x_split_kernel<<<grid_for(tot), 256, 0, s>>>((const bf16*)x, (bf16*)y, B, T, hw, C);
+    count_launch();
+    return cudaGetLastError();
+  }
   if (hwc % 4 != 0) return cudaErrorInvalidValue;
   const long long total = (long long)B * 2 * T * (hwc / 4);
   if (total == 0) return cudaSuccess;
@@ -810,11 +985,12 @@ cudaError_t launch_pack_w_tap_planes(const float* w, bf16* out, int Co, int Ci, 
   count_launch();
   return cudaGetLastError();
 }
-cudaError_t launch_transpose_bf16(const bf16* x, bf16* y, int batch, int rows, int cols, cudaStream_t s) {
+cudaError_t launch_transpose_bf16(const bf16* x, bf16* y, int batch, int rows, int cols, cudaStream_t s, bool split) {
   if (rows % 32 != 0 || cols % 32 != 0) return cudaErrorInvalidValue;
-  ProfScope _ps("transpose", 0.0, 4.0 * batch * rows * cols, s);
+  ProfScope _ps("transpose", 0.0, (split ? 8.0 : 4.0) * batch * rows * cols, s);
   dim3 grid(cols / 32, rows / 32, batch);
-  transpose_bf16_kernel<<<grid, 256, 0, s>>>(x, y, rows, cols);
+  if (split) transpose_split_kernel<<<grid, 256, 0, s>>>(x, y, rows, cols);
+  else transpose_bf16_kernel<<<grid, 256, 0, s>>>(x, y, rows, cols);
   count_launch();
   return cudaGetLastError();
 }
@@ -824,7 +1000,7 @@ cudaError_t launch_upsample_nearest(DType t, const void* x, void* y, int B, int 
   if (C % 4 != 0) return cudaErrorInvalidValue;
   const long long total = (long long)B * T * ut * H * uh * W * uw * (C / 4);
   if (total == 0) return cudaSuccess;
-  if (t == DT_F32) upsample_nearest_kernel<float><<<grid_for(total), 256, 0, s>>>((const float*)x, (float*)y, B, T, H, W, C / 4, ut, uh, uw);
+  if (t != DT_BF16) upsample_nearest_kernel<float><<<grid_for(total), 256, 0, s>>>((const float*)x, (float*)y, B, T, H, W, C / 4, ut, uh, uw);
   else upsample_nearest_kernel<bf16><<<grid_for(total), 256, 0, s>>>((const bf16*)x, (bf16*)y, B, T, H, W, C / 4, ut, uh, uw);
   count_launch();
   return cudaGetLastError();
@@ -834,6 +1010,7 @@ cudaError_t launch_ncdhw_to_cl(DType t, const float* x, void* y, int B, int C, i
   const long long total = (long long)B * (T + t_rep) * H * W * C;
   if (total == 0) return cudaSuccess;
   if (t == DT_F32) ncdhw_to_cl_kernel<float><<<grid_for(total), 256, 0, s>>>(x, (float*)y, B, C, T, (long long)H * W, t_rep);
+  else if (t == DT_SPLIT) ncdhw_to_cl_kernel<split16><<<grid_for(total), 256, 0, s>>>(x, (split16*)y, B, C, T, (long long)H * W, t_rep);
   else ncdhw_to_cl_kernel<bf16><<<grid_for(total), 256, 0, s>>>(x, (bf16*)y, B, C, T, (long long)H * W, t_rep);
   count_launch();
   return cudaGetLastError();
@@ -842,7 +1019,7 @@ cudaError_t launch_cache_update(DType t, const void* x, const void* old_cache, v
                                 int off, bool first, long long frame_elems, long long x_bs, cudaStream_t s) {
   const long long total = (long long)B * P * frame_elems;
   if (total == 0) return cudaSuccess;
-  if (t == DT_F32) cache_update_kernel<float><<<grid_for(total), 256, 0, s>>>((const float*)x, (const float*)old_cache, (float*)new_cache, B, Tc, P, off, first ? 1 : 0, frame_elems, x_bs);
+  if (t != DT_BF16) cache_update_kernel<float><<<grid_for(total), 256, 0, s>>>((const float*)x, (const float*)old_cache, (float*)new_cache, B, Tc, P, off, first ? 1 : 0, frame_elems, x_bs);
   else cache_update_kernel<bf16><<<grid_for(total), 256, 0, s>>>((const bf16*)x, (const bf16*)old_cache, (bf16*)new_cache, B, Tc, P, off, first ? 1 : 0, frame_elems, x_bs);
   count_launch();
   return cudaGetLastError();
@@ -851,8 +1028,21 @@ cudaError_t launch_copy_frames(DType t, const void* src, void* dst, int B, long 
                                long long n, cudaStream_t s) {
   const long long total = (long long)B * n;
   if (total == 0) return cudaSuccess;
-  if (t == DT_F32) copy_frames_kernel<float><<<grid_for(total), 256, 0, s>>>((const float*)src, (float*)dst, B, src_bs, dst_bs, n);
+  if (t != DT_BF16) copy_frames_kernel<float><<<grid_for(total), 256, 0, s>>>((const float*)src, (float*)dst, B, src_bs, dst_bs, n);
   else copy_frames_kernel<bf16><<<grid_for(total), 256, 0, s>>>((const bf16*)src, (bf16*)dst, B, src_bs, dst_bs, n);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_split_to_f32(const bf16* x, float* y, long long rows, int C, cudaStream_t s) {
+  if (rows * C == 0) return cudaSuccess;
+  split_to_f32_kernel<<<grid_for(rows * C), 256, 0, s>>>((const split16*)x, y, rows, C);
+  count_launch();
+  return cudaGetLastError();
+}
+cudaError_t launch_f32_to_split(const float* x, bf16* y, long long rows, int C, cudaStream_t s) {
+  if (rows * C == 0) return cudaSuccess;
+  f32_to_split_kernel<<<grid_for(rows * C), 256, 0, s>>>(x, (split16*)y, rows, C);
   count_launch();
   return cudaGetLastError();
 }

@@ -7,8 +7,11 @@
 
 namespace vt {
 
-enum DType { DT_F32 = 0, DT_BF16 = 1 };
-inline size_t dtype_size(DType t) { return t == DT_F32 ? 4 : 2; }
+// DT_SPLIT: fp32-class activations stored as two bf16 planes side by side in the channel dimension,
+// [..., hi(C) | lo(C)] with hi = bf16(v), lo = bf16(v - hi) (the operand format of the bf16x3 tcgen05 mode).
+// One logical element = 4 bytes; pointers to such tensors are bf16*, strides in ConvP count bf16 elements.
+enum DType { DT_F32 = 0, DT_BF16 = 1, DT_SPLIT = 2 };
+inline size_t dtype_size(DType t) { return t == DT_BF16 ? 2 : 4; }
 
 void prof_start();
 void prof_set_detail(bool on);
@@ -24,6 +27,8 @@ cudaError_t launch_gemm_simt(DType ta, DType tb, DType tc, const void* A, const 
 // elementwise.cu
 cudaError_t launch_layernorm(DType t, const void* x, const float* gamma, const float* beta, void* y, long long rows,
                              int C, bool silu, bool exact, cudaStream_t s);
+// Element counts / strides of the data-movement launchers (upsample_nearest, cache_update, copy_frames) are LOGICAL
+// elements; a DT_SPLIT element is moved as one 4-byte unit (whole rows keep their hi|lo layout).
 // stats: float2 [frames*32] scratch (per-frame mode)
 cudaError_t launch_groupnorm(DType t, const void* x, const float* gamma, const float* beta, void* y, long long frames,
                              long long pos_per_frame, int C, bool per_position, bool silu, bool exact, float* stats,
@@ -38,13 +43,16 @@ cudaError_t launch_fsq_indices_to_codes(const int* indices, int d, const int* le
 // weight repacking: w [Co][Ci][taps] (reference OIDHW flattened) -> [K = tap*Ci + ci][Co] fp32
 cudaError_t launch_pack_w_kn(const float* w, float* out, int Co, int Ci, int taps, cudaStream_t s);
 // -> [Co][K = tap*Ci + ci] bf16 (K-major rows for the tcgen05 B operand)
-cudaError_t launch_pack_w_nk_bf16(const float* w, bf16* out, int Co, int Co_pad, int Ci, int taps, int Kpad, cudaStream_t s);
+// split: rows are [hi(Kpad) | lo(Kpad)] (DT_SPLIT operand format)
+cudaError_t launch_pack_w_nk_bf16(const float* w, bf16* out, int Co, int Co_pad, int Ci, int taps, int Kpad, cudaStream_t s,
+                                  bool split = false);
 // phase-collapsed weights of "nearest-2x upsample then conv": original taps (a,b,c) of a kt x kh x kw kernel are
 // summed into tap (mt[a], mh[b], mw[c]) of a kt2 x kh2 x kw2 kernel; output [Co_pad][kt2*kh2*kw2*Ci] bf16
 cudaError_t launch_pack_w_collapsed(const float* w, bf16* out, int Co, int Co_pad, int Ci, int kt, int kh, int kw,
-                                    const int* mt, const int* mh, const int* mw, int kt2, int kh2, int kw2, cudaStream_t s);
+                                    const int* mt, const int* mh, const int* mw, int kt2, int kh2, int kw2, cudaStream_t s,
+                                    bool split = false);
 // trilinear (align_corners=False) 2x upsampling along T of channels-last x [B,T,HWC] -> [B,2T,HWC]
-cudaError_t launch_time_interp2x(DType t, const void* x, void* y, int B, int T, long long hwc, cudaStream_t s);
+cudaError_t launch_time_interp2x(DType t, const void* x, void* y, int B, int T, long long hw, int C, cudaStream_t s);
 cudaError_t launch_upsample_nearest(DType t, const void* x, void* y, int B, int T, int H, int W, int C, int ut, int uh,
                                     int uw, cudaStream_t s);
 cudaError_t launch_cache_update(DType t, const void* x, const void* old_cache, void* new_cache, int B, int Tc, int P,
@@ -53,6 +61,10 @@ cudaError_t launch_ncdhw_to_cl(DType t, const float* x, void* y, int B, int C, i
                                cudaStream_t s);
 cudaError_t launch_copy_frames(DType t, const void* src, void* dst, int B, long long src_bs, long long dst_bs,
                                long long n_per_batch, cudaStream_t s);
+
+// hi|lo split rows [rows][hi(C) | lo(C)] <-> fp32 rows [rows][C]
+cudaError_t launch_split_to_f32(const bf16* x, float* y, long long rows, int C, cudaStream_t s);
+cudaError_t launch_f32_to_split(const float* x, bf16* y, long long rows, int C, cudaStream_t s);
 
 // conv_tc.cu (tcgen05 / TMA implicit GEMM)
 // LayerNorm(+SiLU) of the output row fused into the conv epilogue (the row is complete in TMEM when Cout <= 256):
@@ -74,7 +86,7 @@ cudaError_t launch_tap_planes_gather(const bf16* P, const float* bias, float* ou
                                      int to_off, cudaStream_t s);
 cudaError_t launch_pack_w_tap_planes(const float* w, bf16* out, int Co, int Ci, int NP, cudaStream_t s);
 // x [batch][rows][cols] -> y [batch][cols][rows] (bf16), rows and cols multiples of 32
-cudaError_t launch_transpose_bf16(const bf16* x, bf16* y, int batch, int rows, int cols, cudaStream_t s);
+cudaError_t launch_transpose_bf16(const bf16* x, bf16* y, int batch, int rows, int cols, cudaStream_t s, bool split = false);
 const char* conv_tc_last_error();
 void conv_tc_set_pair(bool on);
 int conv_tc_cluster_query(int smem, char* msg, int cap);

@@ -307,11 +307,20 @@ struct ConvOpt {
   mutable Act ln2_act;            // filled when fused2 and no view was given
 };
 
+// effective precision of one stack: MIXED = encoder EXACT_TC, decoder BF16
+static inline int stack_prec(int precision, bool decoder) {
+  if (precision == VT_PREC_MIXED) return decoder ? VT_PREC_BF16 : VT_PREC_EXACT_TC;
+  return precision;
+}
+
 struct Exec {
   vt_model* m;
-  int prec;
-  DType ta;
-  bool exact;
+  int prec;          // FMA32 / BF16 / EXACT_TC (never MIXED: see stack_prec)
+  DType ta;          // activation storage: fp32 / bf16 / hi|lo split bf16
+  bool exact;        // full-precision activations functions (everything but BF16)
+  bool tcm;          // tensor-core modes (BF16, EXACT_TC)
+  bool split;        // ta == DT_SPLIT
+  int cw;            // storage elements per logical channel (2 for split rows)
   cudaStream_t s;
   Arena ar;
   bool dry;
@@ -319,8 +328,9 @@ struct Exec {
   int rc = VT_OK;
 
   Exec(vt_model* m_, int prec_, cudaStream_t s_, void* ws, size_t ws_bytes, bool dry_)
-      : m(m_), prec(prec_), ta(prec_ == VT_PREC_EXACT ? DT_F32 : DT_BF16), exact(prec_ == VT_PREC_EXACT), s(s_),
-        dry(dry_) {
+      : m(m_), prec(prec_), ta(prec_ == VT_PREC_FMA32 ? DT_F32 : (prec_ == VT_PREC_EXACT_TC ? DT_SPLIT : DT_BF16)),
+        exact(prec_ != VT_PREC_BF16), tcm(prec_ != VT_PREC_FMA32), split(prec_ == VT_PREC_EXACT_TC),
+        cw(prec_ == VT_PREC_EXACT_TC ? 2 : 1), s(s_), dry(dry_) {
     ar.reset(dry_ ? (void*)(uintptr_t)0x100000 : ws, ws_bytes, dry_);
   }
   bool ok() const { return rc == VT_OK; }
@@ -414,8 +424,10 @@ struct Exec {
     if (o.ext_in) {
       p.isC = (long long)in.T * in.H * in.W; p.isB = p.isC * in.C; p.isT = (long long)in.H * in.W; p.isH = in.W; p.isW = 1;
     } else {
-      p.isC = 1; p.isW = in.C; p.isH = (long long)in.W * in.C; p.isT = p.isH * in.H; p.isB = o.in_bs >= 0 ? o.in_bs : p.isT * in.T;
+      // (stride overrides in ConvOpt count storage elements: bf16 values for split rows)
+      p.isC = 1; p.isW = (long long)cw * in.C; p.isH = (long long)in.W * p.isW; p.isT = p.isH * in.H; p.isB = o.in_bs >= 0 ? o.in_bs : p.isT * in.T;
     }
+    p.split = split ? 1 : 0;
     p.kt = w.kt; p.kh = w.kh; p.kw = w.kw;
     p.st = o.st; p.sh = o.sh; p.sw = o.sw;
     p.ut = o.ut; p.uh = o.uh; p.uw = o.uw;
@@ -441,7 +453,7 @@ struct Exec {
     } else {
       out.p = alloc((size_t)out.elems() * dtype_size(ta));
       out.owned = true;
-      p.osC = 1; p.osW = p.Co; p.osH = (long long)p.Wo * p.Co; p.osT = p.osH * p.Ho; p.osB = p.osT * p.To;
+      p.osC = 1; p.osW = (long long)cw * p.Co; p.osH = (long long)p.Wo * p.osW; p.osT = p.osH * p.Ho; p.osB = p.osT * p.To;
     }
     if (!ok()) return out;
     // time padding mode
@@ -468,7 +480,7 @@ struct Exec {
     if (o.res_mode) {
       const Act& r = *o.res;
       p.res = r.p;
-      p.rsW = r.C; p.rsH = (long long)r.W * r.C; p.rsT = p.rsH * r.H; p.rsB = o.res_bs >= 0 ? o.res_bs : p.rsT * r.T;
+      p.rsW = (long long)cw * r.C; p.rsH = (long long)r.W * p.rsW; p.rsT = p.rsH * r.H; p.rsB = o.res_bs >= 0 ? o.res_bs : p.rsT * r.T;
       p.resT = r.T;
       if (r.C != w.Co) { rc = fail(VT_ERR_INVALID, "conv: residual channel mismatch"); return out; }
       if (o.res_mode == 3) {
@@ -486,10 +498,11 @@ struct Exec {
     }
     const DType tin = o.ext_in ? DT_F32 : ta;
     const DType tout = o.ext_out ? DT_F32 : ta;
-    const bool tc = (prec == VT_PREC_BF16) && !o.force_simt && !o.ext_in && w.Kpad > 0 && conv_tc_supported(p, tout, dry);
+    const bf16* wtc = split ? w.w_nk3 : w.w_nk;
+    const bool tc = tcm && !o.force_simt && !o.ext_in && w.Kpad > 0 && conv_tc_supported(p, tout, dry);
     // LayerNorm fusion into the epilogue: the planning (dry) pass and the real pass must take the same decision
     TcLnFusion lf;
-    if (tc && tout == DT_BF16 && m->desc.norm_type == VT_NORM_LAYERNORM && conv_tc_can_fuse_ln(p)) {
+    if (tc && tout != DT_F32 && m->desc.norm_type == VT_NORM_LAYERNORM && conv_tc_can_fuse_ln(p)) {
       if (o.ln1) {
         lf.mode = 1; lf.silu = o.ln1_silu; lf.gamma = o.ln1->gamma; lf.beta = o.ln1->beta;
         o.fused1 = true;
@@ -506,11 +519,12 @@ struct Exec {
       }
     }
     if (!dry) {
-      const bool stem = (prec == VT_PREC_BF16) && !o.force_simt && o.ext_in && !o.ext_out && !o.out_view && w.w_stem && conv_stem_supported(p);
+      const bf16* wst = split ? w.w_stem3 : w.w_stem;
+      const bool stem = tcm && !o.force_simt && o.ext_in && !o.ext_out && !o.out_view && wst && conv_stem_supported(p);
       if (tc) {
-        if (!cuda(launch_conv_tc(p, (const bf16*)in.p, w.w_nk, w.Kpad, out.p, tout, s, 1, 0, lf.mode ? &lf : nullptr), conv_tc_last_error())) return out;
+        if (!cuda(launch_conv_tc(p, (const bf16*)in.p, wtc, w.Kpad, out.p, tout, s, 1, 0, lf.mode ? &lf : nullptr), conv_tc_last_error())) return out;
       } else if (stem) {
-        if (!cuda(launch_conv_stem(p, o.ext_in, w.w_stem, (bf16*)out.p, s), "conv_stem")) return out;
+        if (!cuda(launch_conv_stem(p, o.ext_in, wst, (bf16*)out.p, s), "conv_stem")) return out;
       } else if (!w.w_kn) {
         rc = fail(VT_ERR_INVALID, "phase-collapsed conv rejected by the tcgen05 path: %s", conv_tc_last_error());
         return out;
@@ -521,7 +535,7 @@ struct Exec {
       if (cb) {
         const int nxt = cb->cur ^ 1;
         if (!cuda(launch_cache_update(tin, o.ext_in ? (const void*)o.ext_in : in.p, cb->buf[cb->cur], cb->buf[nxt], in.B, in.T,
-                                      p.pt, cache_off, ck->first, in.frame(), p.isB, s), "cache_update")) return out;
+                                      p.pt, cache_off, ck->first, in.frame(), o.ext_in ? p.isB : p.isB / cw, s), "cache_update")) return out;
         cb->cur = nxt;
         cb->valid = true;
       }
@@ -619,29 +633,31 @@ struct Exec {
   // Both products are the conv_tc GEMM with per-frame "weights": K of the frame for the scores, V^T for the output.
   bool attention_tc(const Act& q, const Act& k, const Act& v, Act& o) {
     const int frames = q.B * q.T, tokens = q.H * q.W, C = q.C;
-    if (prec != VT_PREC_BF16 || tokens % 64 != 0 || C % 64 != 0 || tokens % 32 != 0) return false;
+    if (!tcm || tokens % 64 != 0 || C % 64 != 0 || tokens % 32 != 0) return false;
     ConvP ps;
     memset(&ps, 0, sizeof(ps));
     ps.B = frames; ps.Ti = 1; ps.Hi = q.H; ps.Wi = q.W; ps.Ci = C;
-    ps.isC = 1; ps.isW = C; ps.isH = (long long)q.W * C; ps.isT = ps.isH * q.H; ps.isB = ps.isT;
+    ps.split = split ? 1 : 0;
+    ps.isC = 1; ps.isW = (long long)cw * C; ps.isH = (long long)q.W * ps.isW; ps.isT = ps.isH * q.H; ps.isB = ps.isT;
     ps.To = 1; ps.Ho = q.H; ps.Wo = q.W; ps.Co = tokens;
     ps.osC = 1; ps.osW = tokens; ps.osH = (long long)q.W * tokens; ps.osT = ps.osH * q.H; ps.osB = ps.osT;
     ps.kt = ps.kh = ps.kw = 1; ps.st = ps.sh = ps.sw = 1; ps.ut = ps.uh = ps.uw = 1;
     ps.ra = 0.f; ps.rb = 1.0f / sqrtf((float)C);
     ConvP pv = ps;
-    pv.Ci = tokens; pv.isW = tokens; pv.isH = (long long)q.W * tokens; pv.isT = pv.isH * q.H; pv.isB = pv.isT;
-    pv.Co = C; pv.osW = C; pv.osH = (long long)q.W * C; pv.osT = pv.osH * q.H; pv.osB = pv.osT;
+    pv.Ci = tokens; pv.isW = (long long)cw * tokens; pv.isH = (long long)q.W * pv.isW; pv.isT = pv.isH * q.H; pv.isB = pv.isT;
+    pv.Co = C; pv.osW = (long long)cw * C; pv.osH = (long long)q.W * pv.osW; pv.osT = pv.osH * q.H; pv.osB = pv.osT;
     pv.rb = 1.0f;
-    if (!dry && (!conv_tc_supported(ps, DT_F32) || !conv_tc_supported(pv, DT_BF16))) return false;
+    if (!dry && (!conv_tc_supported(ps, DT_F32) || !conv_tc_supported(pv, ta))) return false;
     o = new_act(q.B, q.T, q.H, q.W, C);
     float* S = (float*)alloc((size_t)frames * tokens * tokens * sizeof(float));
-    bf16* P = (bf16*)alloc((size_t)frames * tokens * tokens * sizeof(bf16));
-    bf16* Vt = (bf16*)alloc((size_t)frames * tokens * C * sizeof(bf16));
+    bf16* P = (bf16*)alloc((size_t)frames * tokens * tokens * dtype_size(ta));
+    bf16* Vt = (bf16*)alloc((size_t)frames * tokens * C * dtype_size(ta));
     if (ok() && !dry) {
-      cuda(launch_conv_tc(ps, (const bf16*)q.p, (const bf16*)k.p, C, S, DT_F32, s, frames, (long long)tokens * C), conv_tc_last_error());
-      cuda(launch_softmax_rows(DT_BF16, S, P, (long long)frames * tokens, tokens, s), "attn softmax");
-      cuda(launch_transpose_bf16((const bf16*)v.p, Vt, frames, tokens, C, s), "attn transpose V");
-      cuda(launch_conv_tc(pv, P, Vt, tokens, o.p, DT_BF16, s, frames, (long long)tokens * C), conv_tc_last_error());
+      // per-frame "weights": K of the frame ([tokens][C], split: [tokens][hi C | lo C]) and V^T ([C][tokens])
+      cuda(launch_conv_tc(ps, (const bf16*)q.p, (const bf16*)k.p, C, S, DT_F32, s, frames, (long long)tokens * C * cw), conv_tc_last_error());
+      cuda(launch_softmax_rows(ta, S, P, (long long)frames * tokens, tokens, s), "attn softmax");
+      cuda(launch_transpose_bf16((const bf16*)v.p, Vt, frames, tokens, C, s, split), "attn transpose V");
+      cuda(launch_conv_tc(pv, P, Vt, tokens, o.p, ta, s, frames, (long long)tokens * C * cw), conv_tc_last_error());
     }
     ar.release(Vt);
     ar.release(P);
@@ -655,6 +671,29 @@ struct Exec {
       if (attention_tc(q, k, v, o_tc)) return o_tc;
     }
     Act o = new_act(q.B, q.T, q.H, q.W, C);
+    if (split) {
+      // shapes the tcgen05 path does not take (tiny test models): join hi|lo to fp32, fp32 FMA GEMMs, split the result
+      const size_t nqc = (size_t)frames * tokens * C;
+      float* S = (float*)alloc((size_t)frames * tokens * tokens * sizeof(float));
+      float* P = (float*)alloc((size_t)frames * tokens * tokens * sizeof(float));
+      float* qf = (float*)alloc(nqc * sizeof(float));
+      float* kf = (float*)alloc(nqc * sizeof(float));
+      float* vf = (float*)alloc(nqc * sizeof(float));
+      float* of = (float*)alloc(nqc * sizeof(float));
+      if (ok() && !dry) {
+        const float scale = 1.0f / sqrtf((float)C);
+        const long long qs = (long long)tokens * C, ss = (long long)tokens * tokens, rows = (long long)frames * tokens;
+        cuda(launch_split_to_f32((const bf16*)q.p, qf, rows, C, s), "attn join q");
+        cuda(launch_split_to_f32((const bf16*)k.p, kf, rows, C, s), "attn join k");
+        cuda(launch_split_to_f32((const bf16*)v.p, vf, rows, C, s), "attn join v");
+        cuda(launch_gemm_simt(DT_F32, DT_F32, DT_F32, qf, kf, S, tokens, tokens, C, C, C, 1, tokens, frames, qs, qs, ss, scale, s), "attn QK^T");
+        cuda(launch_softmax_rows(DT_F32, S, P, rows, tokens, s), "attn softmax");
+        cuda(launch_gemm_simt(DT_F32, DT_F32, DT_F32, P, vf, of, tokens, C, tokens, tokens, 1, C, C, frames, ss, qs, qs, 1.0f, s), "attn PV");
+        cuda(launch_f32_to_split(of, (bf16*)o.p, rows, C, s), "attn split o");
+      }
+      ar.release(of); ar.release(vf); ar.release(kf); ar.release(qf); ar.release(P); ar.release(S);
+      return o;
+    }
     float* S = (float*)alloc((size_t)frames * tokens * tokens * sizeof(float));
     void* P = alloc((size_t)frames * tokens * tokens * dtype_size(ta));
     if (ok() && !dry) {
@@ -688,10 +727,10 @@ struct Exec {
     if (ok() && !dry) cuda(launch_upsample_nearest(ta, x.p, y.p, x.B, x.T, x.H, x.W, x.C, ut, uh, uw, s), "upsample_nearest");
     return y;
   }
-  bool fold_upsample() const { return prec == VT_PREC_EXACT; }
+  bool fold_upsample() const { return prec == VT_PREC_FMA32; }
 
   bool phase_ln_ok(int Co) const {
-    return prec == VT_PREC_BF16 && m->desc.norm_type == VT_NORM_LAYERNORM && Co % 32 == 0 && Co <= 256;
+    return tcm && m->desc.norm_type == VT_NORM_LAYERNORM && Co % 32 == 0 && Co <= 256;
   }
   // Downsample: pad (0,1,0,1) + conv3x3 stride 2 (model_3dcausal.py:223-227)
   void down(const LevelW& lv, Stream& st, const NormW* next, bool next_silu) {
@@ -716,7 +755,7 @@ struct Exec {
       ConvOpt o; o.uh = 2; o.uw = 2;
       Act y = conv(lv.resample, h, o);
       set_stream(st, y, o);
-    } else if (lv.has_up_phase && prec == VT_PREC_BF16) {
+    } else if (lv.has_up_phase && tcm) {
       // four parity classes of the 2x-upsampled output, each a 1x2x2 conv on the low-resolution input
       Act y = new_act(h.B, h.T, 2 * h.H, 2 * h.W, lv.resample.Co);
       const bool fuse = next && phase_ln_ok(lv.resample.Co);
@@ -730,7 +769,7 @@ struct Exec {
           o.ph0 = py == 0 ? 1 : 0; o.ph1 = 1 - o.ph0; o.pw0 = px == 0 ? 1 : 0; o.pw1 = 1 - o.pw0;
           const size_t off = (size_t)((py * Wo2 + px) * C) * dtype_size(ta);
           o.out_view = dry ? y.p : (void*)((char*)y.p + off);
-          o.ov_sW = 2 * C; o.ov_sH = 2 * Wo2 * C; o.ov_sT = Ho2 * Wo2 * C; o.ov_sB = o.ov_sT * h.T;
+          o.ov_sW = 2 * C * cw; o.ov_sH = 2 * Wo2 * C * cw; o.ov_sT = Ho2 * Wo2 * C * cw; o.ov_sB = o.ov_sT * h.T;
           if (fuse) { o.ln2 = next; o.ln2_silu = next_silu; o.ln2_view = dry ? n.p : (void*)((char*)n.p + off); }
           conv(lv.up_ph[py * 2 + px], h, o);
           if (fuse && ok() && !o.fused2) rc = fail(VT_ERR_INVALID, "upsample phase conv did not fuse its LayerNorm");
@@ -762,7 +801,7 @@ struct Exec {
         set_stream(st, out, o);
         return;
       }
-      if (lv.has_tup_phase && prec == VT_PREC_BF16) {
+      if (lv.has_tup_phase && tcm) {
         // even / odd output frames: 2x3x3 convs on the un-upsampled input, mixed with x[t/2] in the epilogue
         Act out = new_act(x.B, 2 * x.T, x.H, x.W, lv.tconv.Co);
         const bool fuse = next && phase_ln_ok(lv.tconv.Co);
@@ -774,7 +813,7 @@ struct Exec {
           op.ra = lv.alpha; op.rb = 1.f - lv.alpha; op.res_mode = 1; op.res = &x;
           const size_t off = (size_t)(pt * fr) * dtype_size(ta);
           op.out_view = dry ? out.p : (void*)((char*)out.p + off);
-          op.ov_sW = lv.tconv.Co; op.ov_sH = (long long)x.W * lv.tconv.Co; op.ov_sT = 2 * fr; op.ov_sB = 2 * fr * x.T;
+          op.ov_sW = (long long)lv.tconv.Co * cw; op.ov_sH = (long long)x.W * lv.tconv.Co * cw; op.ov_sT = 2 * fr * cw; op.ov_sB = 2 * fr * x.T * cw;
           if (fuse) { op.ln2 = next; op.ln2_silu = next_silu; op.ln2_view = dry ? n.p : (void*)((char*)n.p + off); }
           conv(lv.tup_ph[pt], x, op);
           if (fuse && ok() && !op.fused2) rc = fail(VT_ERR_INVALID, "time-upsample phase conv did not fuse its LayerNorm");
@@ -826,8 +865,8 @@ struct Exec {
         for (int b = 0; b < x.B && ok(); ++b) {
           const char* xb = (const char*)x.p + (size_t)b * x.T * fe * es;
           char* yb = (char*)xu.p + (size_t)b * 2 * x.T * fe * es;
-          cuda(launch_time_interp2x(ta, xb, yb, 1, na, fe, s), "time_interp2x");
-          if (nb > 0) cuda(launch_time_interp2x(ta, xb + (size_t)na * fe * es, yb + (size_t)2 * na * fe * es, 1, nb, fe, s), "time_interp2x");
+          cuda(launch_time_interp2x(ta, xb, yb, 1, na, (long long)x.H * x.W, x.C, s), "time_interp2x");
+          if (nb > 0) cuda(launch_time_interp2x(ta, xb + (size_t)na * fe * es, yb + (size_t)2 * na * fe * es, 1, nb, (long long)x.H * x.W, x.C, s), "time_interp2x");
         }
         if (cb) {  // cache = x[:, -n:]
           const int nxt = cb->cur ^ 1;
@@ -849,7 +888,7 @@ struct Exec {
           const int nxt = cb->cur ^ 1;
           cuda(launch_copy_frames(ta, (const char*)xc.p + (size_t)(x.T - n) * fe * es, cb->buf[nxt], x.B, (long long)(n + x.T) * fe, (long long)n * fe, (long long)n * fe, s), "up cache");
           cb->cur = nxt;
-          cuda(launch_time_interp2x(ta, xc.p, big.p, x.B, n + x.T, fe, s), "time_interp2x");
+          cuda(launch_time_interp2x(ta, xc.p, big.p, x.B, n + x.T, (long long)x.H * x.W, x.C, s), "time_interp2x");
         }
       }
       free_act(xc);
@@ -857,7 +896,7 @@ struct Exec {
       view.owned = false;
       view.p = (char*)big.p + (size_t)2 * n * fe * es;
       view.T = 2 * x.T;
-      bs = (long long)2 * (n + x.T) * fe;
+      bs = (long long)2 * (n + x.T) * fe * cw;
     }
     free_act(x);
     o.res_mode = 1; o.res = &view; o.in_bs = bs; o.res_bs = bs;
@@ -917,7 +956,8 @@ static void run_encoder(Exec& ex, const float* x_ext, int B, int T, int H, int W
   Act xin;
   xin.p = (void*)x_ext; xin.B = B; xin.T = T; xin.H = H; xin.W = W; xin.C = d.in_channels;
   Exec::Stream st;
-  if (d.version == 1 && ex.ck && ex.ck->persist && ex.prec == VT_PREC_BF16 && e.conv_in.w_stem && T + t_rep >= 2 &&
+  const bf16* stem_w = ex.split ? e.conv_in.w_stem3 : e.conv_in.w_stem;
+  if (d.version == 1 && ex.ck && ex.ck->persist && ex.tcm && stem_w && T + t_rep >= 2 &&
       e.conv_in.Ci * 27 <= 128) {
     // chunked v1.1 on the stem kernel: the causal cache (last two padded input frames, model_3dcausal_v1_1.py:230-233)
     // is kept in the caller's layout (fp32 [B,C,2,H,W]) and read by the kernel's patch loader
@@ -930,14 +970,15 @@ static void run_encoder(Exec& ex, const float* x_ext, int B, int T, int H, int W
       p.B = B; p.Ti = T; p.Hi = H; p.Wi = W; p.Ci = d.in_channels;
       p.isW = 1; p.isH = W; p.isT = (long long)H * W; p.isC = p.isT * T; p.isB = p.isC * p.Ci;
       p.To = T + t_rep; p.Ho = H; p.Wo = W; p.Co = e.conv_in.Co;
-      p.osC = 1; p.osW = p.Co; p.osH = (long long)W * p.Co; p.osT = p.osH * H; p.osB = p.osT * p.To;
+      p.split = ex.split ? 1 : 0;
+      p.osC = 1; p.osW = (long long)p.Co * ex.cw; p.osH = (long long)W * p.osW; p.osT = p.osH * H; p.osB = p.osT * p.To;
       p.kt = p.kh = p.kw = 3; p.st = p.sh = p.sw = 1; p.ut = p.uh = p.uw = 1;
       p.pt = 2; p.ph = 1; p.pw = 1; p.t_rep = t_rep;
       p.t_mode = ex.ck->first ? 1 : 2;
       p.cache = cb->buf[cb->cur]; p.cacheT = 2;
       p.bias = e.conv_in.bias;
       if (!conv_stem_supported(p)) { ex.rc = fail(VT_ERR_INVALID, "stem kernel rejected the chunk geometry"); return; }
-      ex.cuda(launch_conv_stem(p, x_ext, e.conv_in.w_stem, (bf16*)st.x.p, ex.s), "conv_stem");
+      ex.cuda(launch_conv_stem(p, x_ext, stem_w, (bf16*)st.x.p, ex.s), "conv_stem");
       const int nxt = cb->cur ^ 1;
       ex.cuda(launch_stem_cache_update(x_ext, (float*)cb->buf[nxt], B, d.in_channels, T, t_rep, H, W, ex.s), "stem cache");
       cb->cur = nxt;
@@ -1084,7 +1125,7 @@ using namespace vt;
 extern "C" {
 
 const char* vt_last_error(void) { return g_err.c_str(); }
-int32_t vt_abi_version(void) { return 1; }
+int32_t vt_abi_version(void) { return 2; }
 int64_t vt_launch_count(int32_t reset) {
   const long long v = g_launches;
   if (reset) g_launches = 0;
@@ -1121,6 +1162,7 @@ void vt_model_destroy(vt_model* m) {
   if (m->pool) cudaFree(m->pool);
   if (m->packed_kn) cudaFree(m->packed_kn);
   if (m->packed_nk) cudaFree(m->packed_nk);
+  if (m->packed_nk3) cudaFree(m->packed_nk3);
   if (m->packed_stem) cudaFree(m->packed_stem);
   if (m->packed_planes) cudaFree(m->packed_planes);
   if (m->kl_scratch) cudaFree(m->kl_scratch);
@@ -1201,6 +1243,7 @@ int32_t vt_model_finalize(vt_model* m, void* stream) {
   }
   if (!m->packed_kn) VT_CUDA(cudaMalloc(&m->packed_kn, kn * sizeof(float)));
   if (!m->packed_nk && nk) VT_CUDA(cudaMalloc(&m->packed_nk, nk * sizeof(bf16)));
+  if (!m->packed_nk3 && nk) VT_CUDA(cudaMalloc(&m->packed_nk3, 2 * nk * sizeof(bf16)));   // hi|lo copies (EXACT_TC)
   size_t okn = 0, onk = 0;
   for (ConvW* c : m->convs) {
     const int K = c->taps() * c->Ci;
@@ -1211,8 +1254,10 @@ int32_t vt_model_finalize(vt_model* m, void* stream) {
     VT_CUDA(launch_pack_w_kn(w, c->w_kn, c->Co, c->Ci, c->taps(), s));
     if (c->Kpad) {
       c->w_nk = m->packed_nk + onk;
+      c->w_nk3 = m->packed_nk3 + 2 * onk;
       onk += align_up((size_t)c->Co_pad * K, 512);
       VT_CUDA(launch_pack_w_nk_bf16(w, c->w_nk, c->Co, c->Co_pad, c->Ci, c->taps(), c->Kpad, s));
+      VT_CUDA(launch_pack_w_nk_bf16(w, c->w_nk3, c->Co, c->Co_pad, c->Ci, c->taps(), c->Kpad, s, true));
     }
   }
   for (auto& lv : m->dec.levels) {
@@ -1226,9 +1271,10 @@ int32_t vt_model_finalize(vt_model* m, void* stream) {
           ConvW& ph = lv.up_ph[py * 2 + px];
           ph = ConvW();
           ph.Co = c.Co; ph.Ci = c.Ci; ph.kt = 1; ph.kh = 2; ph.kw = 2; ph.Co_pad = c.Co; ph.Kpad = 4 * c.Ci;
-          ph.bias = c.bias; ph.w_nk = m->packed_nk + onk;
+          ph.bias = c.bias; ph.w_nk = m->packed_nk + onk; ph.w_nk3 = m->packed_nk3 + 2 * onk;
           onk += align_up((size_t)c.Co * 4 * c.Ci, 512);
           VT_CUDA(launch_pack_w_collapsed(w, ph.w_nk, c.Co, c.Co, c.Ci, 1, 3, 3, id1, py == 0 ? lo : hi, px == 0 ? lo : hi, 1, 2, 2, s));
+          VT_CUDA(launch_pack_w_collapsed(w, ph.w_nk3, c.Co, c.Co, c.Ci, 1, 3, 3, id1, py == 0 ? lo : hi, px == 0 ? lo : hi, 1, 2, 2, s, true));
         }
     }
     if (lv.has_tup_phase) {
@@ -1238,19 +1284,22 @@ int32_t vt_model_finalize(vt_model* m, void* stream) {
         ConvW& ph = lv.tup_ph[pt];
         ph = ConvW();
         ph.Co = c.Co; ph.Ci = c.Ci; ph.kt = 2; ph.kh = 3; ph.kw = 3; ph.Co_pad = c.Co; ph.Kpad = 18 * c.Ci;
-        ph.bias = c.bias; ph.w_nk = m->packed_nk + onk;
+        ph.bias = c.bias; ph.w_nk = m->packed_nk + onk; ph.w_nk3 = m->packed_nk3 + 2 * onk;
         onk += align_up((size_t)c.Co * 18 * c.Ci, 512);
         // even frames t'=2i read x'[2i-2..2i] = x[i-1],x[i-1],x[i]; odd frames read x[i-1],x[i],x[i]
         VT_CUDA(launch_pack_w_collapsed(w, ph.w_nk, c.Co, c.Co, c.Ci, 3, 3, 3, pt == 0 ? hi : lo, id3, id3, 2, 3, 3, s));
+        VT_CUDA(launch_pack_w_collapsed(w, ph.w_nk3, c.Co, c.Co, c.Ci, 3, 3, 3, pt == 0 ? hi : lo, id3, id3, 2, 3, 3, s, true));
       }
     }
   }
   {
     ConvW& c = m->enc.conv_in;
     if (c.Ci * 27 <= 128 && c.Co % 64 == 0 && c.Co <= 256 && c.kt == 3 && c.kh == 3 && c.kw == 3) {
-      if (!m->packed_stem) VT_CUDA(cudaMalloc(&m->packed_stem, (size_t)c.Co * 128 * sizeof(bf16)));
+      if (!m->packed_stem) VT_CUDA(cudaMalloc(&m->packed_stem, (size_t)c.Co * 128 * 3 * sizeof(bf16)));
       c.w_stem = m->packed_stem;
+      c.w_stem3 = m->packed_stem + (size_t)c.Co * 128;
       VT_CUDA(launch_pack_w_nk_bf16(m->pool + m->params[c.pw].offset, c.w_stem, c.Co, c.Co, c.Ci, 27, 128, s));
+      VT_CUDA(launch_pack_w_nk_bf16(m->pool + m->params[c.pw].offset, c.w_stem3, c.Co, c.Co, c.Ci, 27, 128, s, true));
     }
   }
   {
@@ -1301,15 +1350,21 @@ static int check_hw(const vt_model* m, int H, int W) {
   return VT_OK;
 }
 
+static int check_precision(int precision) {
+  if (precision < 0 || precision > VT_PREC_MIXED) return fail(VT_ERR_INVALID, "unknown precision mode %d", precision);
+  return VT_OK;
+}
+
 int64_t vt_workspace_bytes(const vt_model* m, int32_t precision, int32_t B, int32_t T, int32_t H, int32_t W) {
   if (!m || B <= 0 || T <= 0) { fail(VT_ERR_INVALID, "bad shape"); return -1; }
+  if (check_precision(precision)) return -1;
   if (check_hw(m, H, W)) return -1;
   vt_model* mm = const_cast<vt_model*>(m);
   int Tz, Hz, Wz;
   latent_shape(m, T, H, W, &Tz, &Hz, &Wz);
   size_t peak = 0;
   {
-    Exec ex(mm, precision, 0, nullptr, 0, true);
+    Exec ex(mm, stack_prec(precision, false), 0, nullptr, 0, true);
     vt_chunk_state one; one.m = mm; one.persist = false; one.first = true;
     if (m->desc.version == 1) ex.ck = &one;
     float* hpre = (float*)ex.alloc((size_t)B * (m->desc.double_z ? 2 : 1) * m->desc.z_channels * Tz * Hz * Wz * sizeof(float));
@@ -1319,7 +1374,7 @@ int64_t vt_workspace_bytes(const vt_model* m, int32_t precision, int32_t B, int3
     peak = std::max(peak, ex.ar.peak);
   }
   {
-    Exec ex(mm, precision, 0, nullptr, 0, true);
+    Exec ex(mm, stack_prec(precision, true), 0, nullptr, 0, true);
     vt_chunk_state one; one.m = mm; one.persist = false; one.first = true; one.is_decoder = true;
     if (m->desc.version == 1) ex.ck = &one;
     float* zc = (float*)ex.alloc((size_t)B * m->desc.z_channels * Tz * Hz * Wz * sizeof(float));  // codes from indices
@@ -1331,18 +1386,22 @@ int64_t vt_workspace_bytes(const vt_model* m, int32_t precision, int32_t B, int3
   return (int64_t)(peak + 4096);
 }
 
-int32_t vt_encode(vt_model* m, int32_t precision, const float* x, int32_t B, int32_t T, int32_t H, int32_t W,
+int32_t vt_encode(vt_model* m, int32_t precision, const float* x, int32_t B, int32_t C, int32_t T, int32_t H, int32_t W,
                   const float* noise, float* z, int32_t* indices, float* kl_loss, float* h_pre, void* workspace,
                   int64_t workspace_bytes, void* stream) {
   if (!m || !x || !z) return fail(VT_ERR_INVALID, "null argument");
   if (!m->finalized) return fail(VT_ERR_NOT_READY, "vt_model_finalize has not been called");
-  int rc = check_hw(m, H, W);
+  if (C != m->desc.in_channels) return fail(VT_ERR_INVALID, "input has %d channels, the model expects in_channels = %d", C, m->desc.in_channels);
+  if (B <= 0 || T <= 0) return fail(VT_ERR_INVALID, "bad shape");
+  int rc = check_precision(precision);
+  if (rc) return rc;
+  rc = check_hw(m, H, W);
   if (rc) return rc;
   VT_CUDA(cudaSetDevice(m->device));
   cudaStream_t s = (cudaStream_t)stream;
   int Tz, Hz, Wz;
   latent_shape(m, T, H, W, &Tz, &Hz, &Wz);
-  Exec ex(m, precision, s, workspace, (size_t)workspace_bytes, false);
+  Exec ex(m, stack_prec(precision, false), s, workspace, (size_t)workspace_bytes, false);
   vt_chunk_state one; one.m = m; one.persist = false; one.first = true;
   if (m->desc.version == 1) ex.ck = &one;
   const size_t hb = (size_t)B * (m->desc.double_z ? 2 : 1) * m->desc.z_channels * Tz * Hz * Wz * sizeof(float);
@@ -1353,13 +1412,16 @@ int32_t vt_encode(vt_model* m, int32_t precision, const float* x, int32_t B, int
   return regularize(m, hp, noise, B, Tz, Hz, Wz, z, indices, kl_loss, s);
 }
 
-int32_t vt_decode(vt_model* m, int32_t precision, const void* z, int32_t from_indices, int32_t B, int32_t Tz, int32_t Hz,
-                  int32_t Wz, float* x_out, void* workspace, int64_t workspace_bytes, void* stream) {
+int32_t vt_decode(vt_model* m, int32_t precision, const void* z, int32_t from_indices, int32_t B, int32_t Cz, int32_t Tz,
+                  int32_t Hz, int32_t Wz, float* x_out, void* workspace, int64_t workspace_bytes, void* stream) {
   if (!m || !z || !x_out) return fail(VT_ERR_INVALID, "null argument");
   if (!m->finalized) return fail(VT_ERR_NOT_READY, "vt_model_finalize has not been called");
+  if (!from_indices && Cz != m->desc.z_channels) return fail(VT_ERR_INVALID, "latent has %d channels, the model expects z_channels = %d", Cz, m->desc.z_channels);
+  if (B <= 0 || Tz <= 0 || Hz <= 0 || Wz <= 0) return fail(VT_ERR_INVALID, "bad shape");
+  if (check_precision(precision)) return VT_ERR_INVALID;
   VT_CUDA(cudaSetDevice(m->device));
   cudaStream_t s = (cudaStream_t)stream;
-  Exec ex(m, precision, s, workspace, (size_t)workspace_bytes, false);
+  Exec ex(m, stack_prec(precision, true), s, workspace, (size_t)workspace_bytes, false);
   vt_chunk_state one; one.m = m; one.persist = false; one.first = true; one.is_decoder = true;
   if (m->desc.version == 1) ex.ck = &one;
   const float* zf = (const float*)z;
@@ -1379,6 +1441,7 @@ int32_t vt_chunk_state_create(vt_model* m, int32_t precision, int32_t B, int32_t
                               int32_t use_overlap, vt_chunk_state** out) {
   if (!m || !out) return fail(VT_ERR_INVALID, "null argument");
   if (m->desc.version != 1) return fail(VT_ERR_INVALID, "temporal tiling exists only in the v1.1 model family");
+  if (check_precision(precision)) return VT_ERR_INVALID;
   vt_chunk_state* st = new vt_chunk_state();
   st->m = m; st->prec = precision; st->B = B; st->H = H; st->W = W;
   st->is_decoder = is_decoder != 0; st->use_overlap = use_overlap != 0;
@@ -1396,7 +1459,7 @@ int64_t vt_chunk_workspace_bytes(const vt_chunk_state* cs, int32_t Tc) {
   size_t peak = 0;
   for (int first = 0; first < 2; ++first) {
     tmp.first = first != 0;
-    Exec ex(cs->m, cs->prec, 0, nullptr, 0, true);
+    Exec ex(cs->m, stack_prec(cs->prec, cs->is_decoder), 0, nullptr, 0, true);
     ex.ck = &tmp;
     if (cs->is_decoder) {
       run_decoder(ex, (const float*)(uintptr_t)0x1000, cs->B, Tc, cs->H, cs->W, (float*)(uintptr_t)0x1000);
@@ -1412,19 +1475,20 @@ int64_t vt_chunk_workspace_bytes(const vt_chunk_state* cs, int32_t Tc) {
   return (int64_t)(peak + 4096);
 }
 
-int32_t vt_encode_chunk(vt_chunk_state* cs, int32_t is_first, const float* x_chunk, int32_t Tc, const float* noise,
+int32_t vt_encode_chunk(vt_chunk_state* cs, int32_t is_first, const float* x_chunk, int32_t C, int32_t Tc, const float* noise,
                         float* z, int32_t* indices, float* kl_loss, void* workspace, int64_t workspace_bytes,
                         void* stream) {
   if (!cs || !x_chunk || !z) return fail(VT_ERR_INVALID, "null argument");
   if (cs->is_decoder) return fail(VT_ERR_INVALID, "decoder state passed to vt_encode_chunk");
   vt_model* m = cs->m;
+  if (C != m->desc.in_channels) return fail(VT_ERR_INVALID, "input has %d channels, the model expects in_channels = %d", C, m->desc.in_channels);
   if (!m->finalized) return fail(VT_ERR_NOT_READY, "vt_model_finalize has not been called");
   VT_CUDA(cudaSetDevice(m->device));
   cudaStream_t s = (cudaStream_t)stream;
   cs->first = is_first != 0;
   int Tz, Hz, Wz;
   latent_shape(m, Tc, cs->H, cs->W, &Tz, &Hz, &Wz);
-  Exec ex(m, cs->prec, s, workspace, (size_t)workspace_bytes, false);
+  Exec ex(m, stack_prec(cs->prec, false), s, workspace, (size_t)workspace_bytes, false);
   ex.ck = cs;
   float* hp = (float*)ex.alloc((size_t)cs->B * (m->desc.double_z ? 2 : 1) * m->desc.z_channels * Tz * Hz * Wz * sizeof(float));
   if (!ex.ok()) return ex.rc;
@@ -1433,108 +1497,284 @@ int32_t vt_encode_chunk(vt_chunk_state* cs, int32_t is_first, const float* x_chu
   return regularize(m, hp, noise, cs->B, Tz, Hz, Wz, z, indices, kl_loss, s);
 }
 
-int32_t vt_decode_chunk(vt_chunk_state* cs, int32_t is_first, const float* z_chunk, int32_t Tzc, float* x_out,
+int32_t vt_decode_chunk(vt_chunk_state* cs, int32_t is_first, const float* z_chunk, int32_t Cz, int32_t Tzc, float* x_out,
                         void* workspace, int64_t workspace_bytes, void* stream) {
   if (!cs || !z_chunk || !x_out) return fail(VT_ERR_INVALID, "null argument");
   if (!cs->is_decoder) return fail(VT_ERR_INVALID, "encoder state passed to vt_decode_chunk");
   vt_model* m = cs->m;
+  if (Cz != m->desc.z_channels) return fail(VT_ERR_INVALID, "latent has %d channels, the model expects z_channels = %d", Cz, m->desc.z_channels);
   if (!m->finalized) return fail(VT_ERR_NOT_READY, "vt_model_finalize has not been called");
   VT_CUDA(cudaSetDevice(m->device));
   cs->first = is_first != 0;
-  Exec ex(m, cs->prec, (cudaStream_t)stream, workspace, (size_t)workspace_bytes, false);
+  Exec ex(m, stack_prec(cs->prec, true), (cudaStream_t)stream, workspace, (size_t)workspace_bytes, false);
   ex.ck = cs;
   run_decoder(ex, z_chunk, cs->B, Tzc, cs->H, cs->W, x_out);
   return ex.rc;
 }
 
 // ---- single operators (parity tests) -----------------------------------------------------------------
-int32_t vt_op_conv(int32_t precision, int32_t force_simt, const vt_conv_desc* d, const void* x, const float* w,
-                   const float* bias, const void* res, void* out, void* stream) {
+static inline DType act_type(int precision) {
+  return precision == VT_PREC_FMA32 ? DT_F32 : (precision == VT_PREC_EXACT_TC ? DT_SPLIT : DT_BF16);
+}
+
+// Shared body of vt_op_conv / vt_op_conv_ex: one convolution launch of the kernel the model path uses for that
+// precision, with temporary weight repacks.
+static int op_conv_impl(int precision, int force_simt, const vt_conv_desc* d, const vt_conv_ex* e, const void* x,
+                        const void* cache, const float* w, const float* bias, const void* res, const float* gamma,
+                        const float* beta, void* out, void* out2, cudaStream_t s) {
   if (!d || !x || !w || !out) return fail(VT_ERR_INVALID, "null argument");
-  cudaStream_t s = (cudaStream_t)stream;
-  const DType ta = precision == VT_PREC_EXACT ? DT_F32 : DT_BF16;
+  if (precision != VT_PREC_FMA32 && precision != VT_PREC_BF16 && precision != VT_PREC_EXACT_TC)
+    return fail(VT_ERR_INVALID, "operator precision must be FMA32, BF16 or EXACT_TC");
+  const DType ta = act_type(precision);
+  const long long cw = ta == DT_SPLIT ? 2 : 1;
   ConvP p;
   memset(&p, 0, sizeof(p));
+  p.split = ta == DT_SPLIT ? 1 : 0;
   p.B = d->B; p.Ti = d->Ti; p.Hi = d->Hi; p.Wi = d->Wi; p.Ci = d->Ci;
-  p.isC = 1; p.isW = d->Ci; p.isH = (long long)d->Wi * d->Ci; p.isT = p.isH * d->Hi; p.isB = p.isT * d->Ti;
+  p.isC = 1; p.isW = cw * d->Ci; p.isH = (long long)d->Wi * p.isW; p.isT = p.isH * d->Hi; p.isB = p.isT * d->Ti;
   p.kt = d->kt; p.kh = d->kh; p.kw = d->kw; p.st = d->st; p.sh = d->sh; p.sw = d->sw;
   p.ut = d->ut; p.uh = d->uh; p.uw = d->uw;
   p.pt = d->pt; p.ph = d->ph0; p.pw = d->pw0;
-  p.To = (d->ut * d->Ti + d->pt - d->kt) / d->st + 1;
+  p.to_off = e ? e->to_off : 0;
+  p.To = (d->ut * d->Ti + d->pt - d->kt) / d->st + 1 - p.to_off;
   p.Ho = (d->uh * d->Hi + d->ph0 + d->ph1 - d->kh) / d->sh + 1;
   p.Wo = (d->uw * d->Wi + d->pw0 + d->pw1 - d->kw) / d->sw + 1;
   p.Co = d->Co;
-  p.osC = 1; p.osW = p.Co; p.osH = (long long)p.Wo * p.Co; p.osT = p.osH * p.Ho; p.osB = p.osT * p.To;
+  if (p.To <= 0 || p.Ho <= 0 || p.Wo <= 0) return fail(VT_ERR_INVALID, "conv: empty output");
+  const bool out_f32 = e && e->out_f32_ncdhw;
+  if (out_f32) {   // external fp32 [B,Co,To,Ho,Wo] (the heads)
+    p.osC = (long long)p.To * p.Ho * p.Wo; p.osB = p.osC * p.Co; p.osT = (long long)p.Ho * p.Wo; p.osH = p.Wo; p.osW = 1;
+  } else {
+    p.osC = 1; p.osW = cw * p.Co; p.osH = (long long)p.Wo * p.osW; p.osT = p.osH * p.Ho; p.osB = p.osT * p.To;
+  }
+  if (e && e->t_mode) {
+    if (e->t_mode == 2 && (!cache || e->cacheT <= 0)) return fail(VT_ERR_INVALID, "t_mode 2 needs a cache of cacheT frames");
+    p.t_mode = e->t_mode; p.cache = cache; p.cacheT = e->cacheT;
+  }
   p.bias = bias;
   p.res_mode = d->res_mode;
   p.res = res;
+  if (d->res_mode && !res) return fail(VT_ERR_INVALID, "residual mode without residual tensor");
   if (d->res_mode == 1 || d->res_mode == 2) {
     const int rT = d->res_mode == 2 ? (p.To + 1) / 2 : p.To;
-    p.rsW = p.Co; p.rsH = (long long)p.Wo * p.Co; p.rsT = p.rsH * p.Ho; p.rsB = p.rsT * rT; p.resT = rT;
-    p.ra = d->res_mode == 2 ? d->alpha : 1.f; p.rb = d->res_mode == 2 ? 1.f - d->alpha : 1.f;
+    p.rsW = cw * p.Co; p.rsH = (long long)p.Wo * p.rsW; p.rsT = p.rsH * p.Ho; p.rsB = p.rsT * rT; p.resT = rT;
+    const bool mix = d->res_mode == 2 || (e && e->res_mix);
+    p.ra = mix ? d->alpha : 1.f; p.rb = mix ? 1.f - d->alpha : 1.f;
   } else if (d->res_mode == 3) {
-    p.rsW = p.Co; p.rsH = (long long)p.Wo * p.Co; p.rsT = p.rsH * p.Ho; p.rsB = p.rsT * d->Ti; p.resT = d->Ti;
+    p.rsW = cw * p.Co; p.rsH = (long long)p.Wo * p.rsW; p.rsT = p.rsH * p.Ho; p.rsB = p.rsT * d->Ti; p.resT = d->Ti;
     p.ra = d->alpha; p.rb = 1.f - d->alpha;
+    if (e) { p.res_t_mode = e->res_t_mode; p.res_cache = e->res_t_mode == 2 ? cache : nullptr; }
   } else {
     p.ra = 0.f; p.rb = 1.f;
   }
   const int taps = d->kt * d->kh * d->kw, K = taps * d->Ci;
+  const DType tout = out_f32 ? DT_F32 : ta;
+  TcLnFusion lf;
+  if (e && e->ln_mode) {
+    if (!gamma || !beta || (e->ln_mode == 2 && !out2)) return fail(VT_ERR_INVALID, "fused LayerNorm needs gamma, beta (and out2 for mode 2)");
+    if (precision == VT_PREC_FMA32 || force_simt) return fail(VT_ERR_INVALID, "the LayerNorm epilogue exists on the tcgen05 path only");
+    if (!conv_tc_can_fuse_ln(p)) return fail(VT_ERR_INVALID, "LayerNorm cannot be fused for this Cout");
+    lf.mode = e->ln_mode; lf.silu = e->ln_silu != 0; lf.gamma = gamma; lf.beta = beta; lf.out2 = out2;
+  }
   float* wkn = nullptr;
   bf16* wnk = nullptr;
-  VT_CUDA(cudaMalloc(&wkn, (size_t)K * d->Co * sizeof(float)));
-  VT_CUDA(launch_pack_w_kn(w, wkn, d->Co, d->Ci, taps, s));
-  cudaError_t e;
-  const bool tc = precision == VT_PREC_BF16 && !force_simt && d->Ci % 64 == 0 && conv_tc_supported(p, DT_BF16);
-  if (tc) {
+  cudaError_t er;
+  const bool want_tc = precision != VT_PREC_FMA32 && !force_simt;
+  if (want_tc) {
+    if (d->Ci % 64 != 0 || !conv_tc_supported(p, tout))
+      return fail(VT_ERR_INVALID, "tcgen05 conv does not support this geometry: %s", d->Ci % 64 ? "Cin % 64 != 0" : conv_tc_last_error());
     const int Co_pad = (d->Co + 31) / 32 * 32;
-    VT_CUDA(cudaMalloc(&wnk, (size_t)K * Co_pad * sizeof(bf16)));
-    VT_CUDA(launch_pack_w_nk_bf16(w, wnk, d->Co, Co_pad, d->Ci, taps, K, s));
-    e = launch_conv_tc(p, (const bf16*)x, wnk, K, out, DT_BF16, s);
+    VT_CUDA(cudaMalloc(&wnk, (size_t)K * Co_pad * sizeof(bf16) * cw));
+    VT_CUDA(launch_pack_w_nk_bf16(w, wnk, d->Co, Co_pad, d->Ci, taps, K, s, ta == DT_SPLIT));
+    er = launch_conv_tc(p, (const bf16*)x, wnk, K, out, tout, s, 1, 0, lf.mode ? &lf : nullptr);
   } else {
-    if (precision == VT_PREC_BF16 && !force_simt) {
-      cudaFree(wkn);
-      return fail(VT_ERR_INVALID, "tcgen05 conv does not support this geometry: %s", conv_tc_last_error());
-    }
-    e = launch_conv_simt(p, ta, ta, ta, x, wkn, out, s);
+    VT_CUDA(cudaMalloc(&wkn, (size_t)K * d->Co * sizeof(float)));
+    VT_CUDA(launch_pack_w_kn(w, wkn, d->Co, d->Ci, taps, s));
+    er = launch_conv_simt(p, ta, tout, ta, x, wkn, out, s);
   }
   cudaError_t e2 = cudaStreamSynchronize(s);
-  cudaFree(wkn);
+  if (wkn) cudaFree(wkn);
   if (wnk) cudaFree(wnk);
-  if (e != cudaSuccess) return fail(VT_ERR_CUDA, "conv launch: %s %s", cudaGetErrorString(e), conv_tc_last_error());
+  if (er != cudaSuccess) return fail(VT_ERR_CUDA, "conv launch: %s %s", cudaGetErrorString(er), conv_tc_last_error());
   if (e2 != cudaSuccess) return fail(VT_ERR_CUDA, "conv execution: %s", cudaGetErrorString(e2));
+  return VT_OK;
+}
+
+int32_t vt_op_conv(int32_t precision, int32_t force_simt, const vt_conv_desc* d, const void* x, const float* w,
+                   const float* bias, const void* res, void* out, void* stream) {
+  return op_conv_impl(precision, force_simt, d, nullptr, x, nullptr, w, bias, res, nullptr, nullptr, out, nullptr, (cudaStream_t)stream);
+}
+int32_t vt_op_conv_ex(int32_t precision, const vt_conv_ex* e, const void* x, const void* cache, const float* w,
+                      const float* bias, const void* res, const float* gamma, const float* beta, void* out, void* out2,
+                      void* stream) {
+  if (!e) return fail(VT_ERR_INVALID, "null argument");
+  return op_conv_impl(precision, e->force_simt, &e->d, e, x, cache, w, bias, res, gamma, beta, out, out2, (cudaStream_t)stream);
+}
+
+// Encoder stem (conv_in from the caller's fp32 [B,Ci,T,H,W] tensor) on the conv_stem kernel.
+int32_t vt_op_conv_stem(int32_t precision, const float* x, const float* w, const float* bias, void* out, int32_t B,
+                        int32_t Ci, int32_t T, int32_t H, int32_t W, int32_t Co, int32_t t_rep, void* stream) {
+  if (!x || !w || !out) return fail(VT_ERR_INVALID, "null argument");
+  if (precision != VT_PREC_BF16 && precision != VT_PREC_EXACT_TC) return fail(VT_ERR_INVALID, "the stem kernel is a tcgen05 kernel (BF16 / EXACT_TC)");
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool split = precision == VT_PREC_EXACT_TC;
+  ConvP p;
+  memset(&p, 0, sizeof(p));
+  p.split = split ? 1 : 0;
+  p.B = B; p.Ti = T; p.Hi = H; p.Wi = W; p.Ci = Ci;
+  p.isW = 1; p.isH = W; p.isT = (long long)H * W; p.isC = p.isT * T; p.isB = p.isC * Ci;
+  p.To = T + t_rep; p.Ho = H; p.Wo = W; p.Co = Co;
+  p.osC = 1; p.osW = (long long)Co * (split ? 2 : 1); p.osH = (long long)W * p.osW; p.osT = p.osH * H; p.osB = p.osT * p.To;
+  p.kt = p.kh = p.kw = 3; p.st = p.sh = p.sw = 1; p.ut = p.uh = p.uw = 1;
+  p.pt = 2; p.ph = 1; p.pw = 1; p.t_rep = t_rep;
+  p.bias = bias;
+  if (!conv_stem_supported(p)) return fail(VT_ERR_INVALID, "stem kernel does not take this geometry");
+  bf16* wpk = nullptr;
+  VT_CUDA(cudaMalloc(&wpk, (size_t)Co * 128 * 2 * sizeof(bf16)));
+  VT_CUDA(launch_pack_w_nk_bf16(w, wpk, Co, Co, Ci, 27, 128, s, split));
+  cudaError_t er = launch_conv_stem(p, x, wpk, (bf16*)out, s);
+  cudaError_t e2 = cudaStreamSynchronize(s);
+  cudaFree(wpk);
+  if (er != cudaSuccess || e2 != cudaSuccess) return fail(VT_ERR_CUDA, "conv_stem: %s", cudaGetErrorString(er != cudaSuccess ? er : e2));
+  return VT_OK;
+}
+
+// Decoder head (conv_out Cin -> Co <= 4, 3x3x3, v1.0 zero padding, first to_off output frames dropped) as the BF16 path
+// runs it: tap-planes GEMM + gather.  x bf16 channels-last [B,T,H,W,Ci]; out fp32 [B,Co,T - to_off,H,W].
+int32_t vt_op_head_planes(const void* x, const float* w, const float* bias, float* out, int32_t B, int32_t T, int32_t H,
+                          int32_t W, int32_t Ci, int32_t Co, int32_t to_off, void* stream) {
+  if (!x || !w || !bias || !out) return fail(VT_ERR_INVALID, "null argument");
+  if (Co > 4 || Ci % 64 != 0 || W % 8 != 0) return fail(VT_ERR_INVALID, "head planes need Co <= 4, Cin % 64 == 0, W % 8 == 0");
+  cudaStream_t s = (cudaStream_t)stream;
+  bf16 *wp = nullptr, *P = nullptr;
+  VT_CUDA(cudaMalloc(&wp, (size_t)128 * Ci * sizeof(bf16)));
+  VT_CUDA(cudaMalloc(&P, (size_t)B * T * H * W * 128 * sizeof(bf16)));
+  VT_CUDA(launch_pack_w_tap_planes(w, wp, Co, Ci, 128, s));
+  ConvP p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.Ti = T; p.Hi = H; p.Wi = W; p.Ci = Ci;
+  p.isC = 1; p.isW = Ci; p.isH = (long long)W * Ci; p.isT = p.isH * H; p.isB = p.isT * T;
+  p.To = T; p.Ho = H; p.Wo = W; p.Co = 128;
+  p.osC = 1; p.osW = 128; p.osH = (long long)W * 128; p.osT = p.osH * H; p.osB = p.osT * T;
+  p.kt = p.kh = p.kw = 1; p.st = p.sh = p.sw = 1; p.ut = p.uh = p.uw = 1;
+  p.ra = 0.f; p.rb = 1.f;
+  cudaError_t er = cudaSuccess;
+  if (!conv_tc_supported(p, DT_BF16)) er = cudaErrorInvalidValue;
+  if (er == cudaSuccess) er = launch_conv_tc(p, (const bf16*)x, wp, Ci, P, DT_BF16, s);
+  if (er == cudaSuccess) er = launch_tap_planes_gather(P, bias, out, B, T, H, W, 128, Co, to_off, s);
+  cudaError_t e2 = cudaStreamSynchronize(s);
+  cudaFree(wp); cudaFree(P);
+  if (er != cudaSuccess || e2 != cudaSuccess) return fail(VT_ERR_CUDA, "head planes: %s %s", cudaGetErrorString(er != cudaSuccess ? er : e2), conv_tc_last_error());
+  return VT_OK;
+}
+
+// "nearest 2x upsample, then conv" exactly as the tensor-core modes run it: phase-collapsed weights, one small conv per
+// output parity class, strided stores into the full-resolution tensor (Exec::up / Exec::time_up), optional fused
+// LayerNorm(+SiLU) of the result into out2.
+//   kind 0: Upsample (model_3dcausal.py:208-212): x [B,T,H,W,C] -> out [B,T,2H,2W,Co], w [Co,C,3,3]
+//   kind 1: TimeUpsampleResCausal2x, v1.0 (:267-273): out [B,2T,H,W,C] = alpha*x' + (1-alpha)*conv(x'), w [C,C,3,3,3]
+int32_t vt_op_upsample_conv(int32_t precision, int32_t kind, const void* x, const float* w, const float* bias, float alpha,
+                            const float* gamma, const float* beta, int32_t ln_silu, void* out, void* out2, int32_t B,
+                            int32_t T, int32_t H, int32_t W, int32_t Ci, int32_t Co, void* stream) {
+  if (!x || !w || !bias || !out) return fail(VT_ERR_INVALID, "null argument");
+  if (precision != VT_PREC_BF16 && precision != VT_PREC_EXACT_TC) return fail(VT_ERR_INVALID, "phase-collapsed convs exist in the tensor-core modes only");
+  if (Ci % 64 != 0 || Co % 32 != 0 || (kind == 1 && Ci != Co)) return fail(VT_ERR_INVALID, "unsupported channel counts");
+  cudaStream_t s = (cudaStream_t)stream;
+  vt_model dummy;
+  memset(&dummy.desc, 0, sizeof(dummy.desc));
+  dummy.desc.norm_type = VT_NORM_LAYERNORM;
+  dummy.desc.version = 0;
+  const bool split = precision == VT_PREC_EXACT_TC;
+  const int nph = kind == 0 ? 4 : 2, taps2 = kind == 0 ? 4 : 18;
+  bf16* wp = nullptr;
+  const size_t per = (size_t)Co * taps2 * Ci;
+  VT_CUDA(cudaMalloc(&wp, per * nph * (split ? 2 : 1) * sizeof(bf16)));
+  LevelW lv;
+  const int id3[3] = {0, 1, 2}, id1[3] = {0, 0, 0};
+  const int lo[3] = {0, 1, 1}, hi[3] = {0, 0, 1};
+  for (int i = 0; i < nph; ++i) {
+    ConvW& ph = kind == 0 ? lv.up_ph[i] : lv.tup_ph[i];
+    ph = ConvW();
+    ph.Co = Co; ph.Ci = Ci; ph.Co_pad = Co; ph.Kpad = taps2 * Ci; ph.bias = bias;
+    bf16* dst = wp + per * i * (split ? 2 : 1);
+    if (split) ph.w_nk3 = dst; else ph.w_nk = dst;
+    if (kind == 0) {
+      ph.kt = 1; ph.kh = 2; ph.kw = 2;
+      VT_CUDA(launch_pack_w_collapsed(w, dst, Co, Co, Ci, 1, 3, 3, id1, (i >> 1) == 0 ? lo : hi, (i & 1) == 0 ? lo : hi, 1, 2, 2, s, split));
+    } else {
+      ph.kt = 2; ph.kh = 3; ph.kw = 3;
+      VT_CUDA(launch_pack_w_collapsed(w, dst, Co, Co, Ci, 3, 3, 3, i == 0 ? hi : lo, id3, id3, 2, 3, 3, s, split));
+    }
+  }
+  lv.has_resample = kind == 0; lv.has_up_phase = kind == 0;
+  lv.has_tres = kind == 1; lv.has_tup_phase = kind == 1;
+  lv.resample.Co = Co; lv.resample.Ci = Ci; lv.tconv.Co = Co; lv.tconv.Ci = Ci;
+  lv.alpha = alpha;
+  lv.tkey = "op";
+  NormW nw;
+  nw.C = Co; nw.gamma = gamma; nw.beta = beta;
+  const bool want_ln = gamma && beta && out2;
+  const size_t esz = split ? 4 : 2;
+  const size_t in_bytes = (size_t)B * T * H * W * Ci * esz;
+  const size_t out_elems = kind == 0 ? (size_t)B * T * 4 * H * W * Co : (size_t)B * 2 * T * H * W * Co;
+  const size_t ws_bytes = in_bytes + 2 * out_elems * esz + (1 << 20);
+  void* ws = nullptr;
+  cudaError_t em = cudaMalloc(&ws, ws_bytes);
+  if (em != cudaSuccess) { cudaFree(wp); return fail(VT_ERR_CUDA, "cudaMalloc(workspace)"); }
+  int rc = VT_OK;
+  {
+    Exec ex(&dummy, precision, s, ws, ws_bytes, false);
+    Exec::Stream st;
+    st.x = ex.new_act(B, T, H, W, Ci);
+    if (ex.ok()) ex.cuda(cudaMemcpyAsync(st.x.p, x, in_bytes, cudaMemcpyDeviceToDevice, s), "copy in");
+    if (kind == 0) ex.up(lv, st, want_ln ? &nw : nullptr, ln_silu != 0);
+    else ex.time_up(lv, st, want_ln ? &nw : nullptr, ln_silu != 0);
+    if (ex.ok()) ex.cuda(cudaMemcpyAsync(out, st.x.p, out_elems * esz, cudaMemcpyDeviceToDevice, s), "copy out");
+    if (ex.ok() && want_ln) {
+      if (!st.n.p) ex.rc = fail(VT_ERR_INVALID, "the LayerNorm was not fused into the phase convolutions");
+      else ex.cuda(cudaMemcpyAsync(out2, st.n.p, out_elems * esz, cudaMemcpyDeviceToDevice, s), "copy out2");
+    }
+    rc = ex.rc;
+  }
+  cudaError_t e2 = cudaStreamSynchronize(s);
+  cudaFree(ws); cudaFree(wp);
+  if (rc) return rc;
+  if (e2 != cudaSuccess) return fail(VT_ERR_CUDA, "upsample conv: %s", cudaGetErrorString(e2));
   return VT_OK;
 }
 
 int32_t vt_op_layernorm(int32_t precision, const void* x, const float* gamma, const float* beta, void* y, int64_t rows,
                         int32_t C, int32_t apply_silu, void* stream) {
-  const DType ta = precision == VT_PREC_EXACT ? DT_F32 : DT_BF16;
-  VT_CUDA(launch_layernorm(ta, x, gamma, beta, y, rows, C, apply_silu != 0, precision == VT_PREC_EXACT, (cudaStream_t)stream));
+  VT_CUDA(launch_layernorm(act_type(precision), x, gamma, beta, y, rows, C, apply_silu != 0, precision != VT_PREC_BF16, (cudaStream_t)stream));
   return VT_OK;
 }
 int32_t vt_op_groupnorm(int32_t precision, const void* x, const float* gamma, const float* beta, void* y, int64_t frames,
                         int64_t ppf, int32_t C, int32_t per_position, int32_t apply_silu, void* workspace,
                         int64_t workspace_bytes, void* stream) {
-  const DType ta = precision == VT_PREC_EXACT ? DT_F32 : DT_BF16;
   if (!per_position && workspace_bytes < (int64_t)(frames * 32 * 2 * sizeof(float))) return fail(VT_ERR_WORKSPACE, "groupnorm stats need %lld bytes", (long long)(frames * 64 * sizeof(float)));
-  VT_CUDA(launch_groupnorm(ta, x, gamma, beta, y, frames, ppf, C, per_position != 0, apply_silu != 0, precision == VT_PREC_EXACT,
+  VT_CUDA(launch_groupnorm(act_type(precision), x, gamma, beta, y, frames, ppf, C, per_position != 0, apply_silu != 0, precision != VT_PREC_BF16,
                            (float*)workspace, (cudaStream_t)stream));
   return VT_OK;
 }
+// The attention core the model path runs for this precision and shape: tcgen05 GEMMs (per-frame K / V^T as the B
+// operand) when tokens and C are multiples of 64 in the tensor-core modes, fp32 FMA GEMMs otherwise.
 int32_t vt_op_attention(int32_t precision, const void* q, const void* k, const void* v, void* o, int32_t frames,
                         int32_t tokens, int32_t C, void* workspace, int64_t workspace_bytes, void* stream) {
-  const DType ta = precision == VT_PREC_EXACT ? DT_F32 : DT_BF16;
-  const size_t sb = align_up((size_t)frames * tokens * tokens * sizeof(float), 1024);
-  const size_t pb = (size_t)frames * tokens * tokens * dtype_size(ta);
-  if ((size_t)workspace_bytes < sb + pb) return fail(VT_ERR_WORKSPACE, "attention needs %zu workspace bytes", sb + pb);
-  float* S = (float*)workspace;
-  void* P = (char*)workspace + sb;
-  cudaStream_t s = (cudaStream_t)stream;
-  const float scale = 1.0f / sqrtf((float)C);
-  const long long qs = (long long)tokens * C, ss = (long long)tokens * tokens;
-  VT_CUDA(launch_gemm_simt(ta, ta, DT_F32, q, k, S, tokens, tokens, C, C, C, 1, tokens, frames, qs, qs, ss, scale, s));
-  VT_CUDA(launch_softmax_rows(ta, S, P, (long long)frames * tokens, tokens, s));
-  VT_CUDA(launch_gemm_simt(ta, ta, ta, P, v, o, tokens, C, tokens, tokens, 1, C, C, frames, ss, qs, qs, 1.0f, s));
-  return VT_OK;
+  if (!q || !k || !v || !o || !workspace) return fail(VT_ERR_INVALID, "null argument");
+  if (precision != VT_PREC_FMA32 && precision != VT_PREC_BF16 && precision != VT_PREC_EXACT_TC)
+    return fail(VT_ERR_INVALID, "operator precision must be FMA32, BF16 or EXACT_TC");
+  vt_model dummy;
+  memset(&dummy.desc, 0, sizeof(dummy.desc));
+  Exec ex(&dummy, precision, (cudaStream_t)stream, workspace, (size_t)workspace_bytes, false);
+  Act aq, ak, av;
+  aq.B = frames; aq.T = 1; aq.H = 1; aq.W = tokens; aq.C = C;
+  // the tcgen05 formulation tiles positions as (H, W) boxes: present the token axis as an 8-wide image when possible
+  if (tokens % 8 == 0) { aq.H = tokens / 8; aq.W = 8; }
+  ak = aq; av = aq;
+  aq.p = const_cast<void*>(q); ak.p = const_cast<void*>(k); av.p = const_cast<void*>(v);
+  Act ao = ex.attention_core(aq, ak, av);
+  if (ex.ok()) ex.cuda(cudaMemcpyAsync(o, ao.p, (size_t)frames * tokens * C * dtype_size(ex.ta), cudaMemcpyDeviceToDevice, ex.s), "copy out");
+  return ex.rc;
 }
 int32_t vt_op_fsq(const float* h, int32_t d, const int32_t* levels, int64_t P, int32_t B, float* codes, int32_t* indices,
                   void* stream) {

@@ -25,9 +25,11 @@ struct ConvW {
   int pw = -1, pb = -1;      // param indices (weight, bias)
   float* w_kn = nullptr;     // [K][Co] fp32
   bf16* w_nk = nullptr;      // [Co_pad][Kpad] bf16 (tcgen05 B operand), may be null
+  bf16* w_nk3 = nullptr;     // [Co_pad][hi(Kpad) | lo(Kpad)] bf16: split operand of the EXACT_TC (bf16x3) mode
   int Kpad = 0;
   int Co_pad = 0;            // Cout rounded up to 32 (zero rows)
   bf16* w_stem = nullptr;    // [Co][128] bf16 (conv_stem.cu), only for the Cin<=4 stem
+  bf16* w_stem3 = nullptr;   // [Co][hi 128 | lo 128] (EXACT_TC)
   const float* bias = nullptr;
   int taps() const { return kt * kh * kw; }
 };
@@ -96,7 +98,8 @@ struct vt_model {
   int64_t pool_elems = 0;
   float* packed_kn = nullptr;   // all [K][Co] fp32 repacks
   vt::bf16* packed_nk = nullptr;
-  vt::bf16* packed_stem = nullptr;
+  vt::bf16* packed_nk3 = nullptr;      // split (hi|lo) copies of every tcgen05 weight matrix
+  vt::bf16* packed_stem = nullptr;     // [Co][128] followed by the split copy [Co][256]
   vt::bf16* packed_planes = nullptr;   // decoder conv_out as 27x4 tap planes: [128][Cin] bf16
   vt::ConvW head_planes;               // 1x1x1 pseudo-conv Cin -> 128 using packed_planes
   bool finalized = false;

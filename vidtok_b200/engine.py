@@ -9,8 +9,17 @@ but every tensor operation runs in libvidtok_b200.so (hand-written sm_100a kerne
 include/vidtok_b200.h.  There is no PyTorch/CPU fallback: a model that is not on a CUDA device raises.
 
 Precision: the reference scripts run fp32 by default and bf16/fp16 under `--precision autocast`
-(scripts/inference_evaluate.py:77-79,137).  Mirroring that, the native precision is EXACT (fp32 FMA kernels)
-unless autocast is active or `model.precision = "bf16"` is set, which selects the tcgen05 bf16 kernels.
+(scripts/inference_evaluate.py:77-79,137).  Mirroring that, `model.precision = None` (default) selects
+  * "exact"  -- fp32-class results on the tcgen05 tensor cores (bf16x3 split operands, fp32 LayerNorm/SiLU): the
+                parity mode (1e-3 max-abs, FSQ codes equal), unless
+  * "bf16"   -- torch.autocast is active (bf16 activations/weights on tcgen05, fp32 accumulate: the throughput mode;
+                outputs are returned in the autocast dtype like the reference's; an fp16 autocast region also
+                computes in bf16).
+Explicit settings: "exact", "bf16", "mixed" (encoder exact, decoder bf16: bit-exact FSQ codes / 1e-3 latents with a
+bf16 decoder) and "fma" (fp32 FMA kernels without tensor cores, kept as a cross-check).
+
+Threading / streams: one workspace per model handle -- calls on one model must be issued on one CUDA stream at a time
+(the reference's modules are not re-entrant either: v1.1 keeps chunk caches on the modules).
 """
 from __future__ import annotations
 
@@ -175,6 +184,8 @@ class NativeModel:
 
     def encode(self, x: torch.Tensor, noise: Optional[torch.Tensor], precision: int, want_h: bool = False):
         B, Cin, T, H, W = x.shape
+        if Cin != self.spec.in_channels:
+            raise ValueError(f"input has {Cin} channels, the model expects in_channels = {self.spec.in_channels}")
         Tz, Hz, Wz = self.latent_shape(T, H, W)
         s = self.spec
         z = torch.empty((B, s.z_channels, Tz, Hz, Wz), dtype=torch.float32, device=x.device)
@@ -183,22 +194,29 @@ class NativeModel:
         h = torch.empty((B, (2 if s.double_z else 1) * s.z_channels, Tz, Hz, Wz), dtype=torch.float32,
                         device=x.device) if want_h else None
         ws = self.workspace_for(precision, B, T, H, W)
-        N.check(self.lib.vt_encode(self.handle, precision, _ptr(x), B, T, H, W, _ptr(noise), _ptr(z), _ptr(idx), _ptr(kl),
+        N.check(self.lib.vt_encode(self.handle, precision, _ptr(x), B, Cin, T, H, W, _ptr(noise), _ptr(z), _ptr(idx), _ptr(kl),
                                    _ptr(h), _ptr(ws), ws.numel(), _stream_ptr(x.device)))
         return z, idx, kl, h
 
     def decode(self, z: torch.Tensor, from_indices: bool, precision: int) -> torch.Tensor:
         if from_indices:
+            if z.dim() != 4:
+                raise ValueError("expected [B,T,H,W] token indices")
             B, Tz, Hz, Wz = z.shape
+            Cz = self.spec.z_channels
         else:
-            B, _, Tz, Hz, Wz = z.shape
+            if z.dim() != 5:
+                raise ValueError("expected a [B,C,T,H,W] latent")
+            B, Cz, Tz, Hz, Wz = z.shape
+            if Cz != self.spec.z_channels:
+                raise ValueError(f"latent has {Cz} channels, the model expects z_channels = {self.spec.z_channels}")
         f = self.spatial_factor()
         To = self.decoded_frames(Tz)
         out = torch.empty((B, self.spec.out_ch, To, Hz * f, Wz * f), dtype=torch.float32, device=z.device)
         T_in = max(To, 1)
         ws = self.workspace_for(precision, B, T_in if self.spec.version == 0 else Tz * self.spec.time_downsample_factor,
                                 Hz * f, Wz * f)
-        N.check(self.lib.vt_decode(self.handle, precision, _ptr(z), int(from_indices), B, Tz, Hz, Wz, _ptr(out), _ptr(ws),
+        N.check(self.lib.vt_decode(self.handle, precision, _ptr(z), int(from_indices), B, Cz, Tz, Hz, Wz, _ptr(out), _ptr(ws),
                                    ws.numel(), _stream_ptr(z.device)))
         return out
 
@@ -466,13 +484,21 @@ class _Runtime:
         self._sig = None
         self.precision_override: Optional[str] = None
 
+    _MODES = {"exact": N.PREC_EXACT_TC, "bf16": N.PREC_BF16, "mixed": N.PREC_MIXED, "fma": N.PREC_FMA32}
+
     def precision(self) -> int:
         p = self.precision_override
         if p is None:
-            return N.PREC_BF16 if torch.is_autocast_enabled() else N.PREC_EXACT
-        if p not in ("exact", "bf16"):
-            raise ValueError("precision must be None, 'exact' or 'bf16'")
-        return N.PREC_BF16 if p == "bf16" else N.PREC_EXACT
+            return N.PREC_BF16 if torch.is_autocast_enabled() else N.PREC_EXACT_TC
+        if p not in self._MODES:
+            raise ValueError("precision must be None, 'exact', 'bf16', 'mixed' or 'fma'")
+        return self._MODES[p]
+
+    def out_dtype(self) -> torch.dtype:
+        """Reference semantics: fp32 tensors, or the autocast dtype inside a torch.autocast region."""
+        if self.precision_override is None and torch.is_autocast_enabled():
+            return torch.get_autocast_dtype("cuda")
+        return torch.float32
 
     def _params(self):
         for prefix, mod in self.stacks.items():
@@ -639,12 +665,13 @@ class AutoencodingEngine(_EngineBase):
 
     def encode(self, x: Any, return_reg_log: bool = False) -> Any:
         z, idx, kl, _ = self._rt.encode_raw(x)
+        z = z.to(self._rt.out_dtype())
         if return_reg_log:
             return z, self._reg_log(idx, kl)
         return z
 
     def decode(self, z: Any, decode_from_indices: bool = False) -> torch.Tensor:
-        return self._rt.decode_raw(z, decode_from_indices)
+        return self._rt.decode_raw(z, decode_from_indices).to(self._rt.out_dtype())
 
     def forward(self, x: Any):
         z, reg_log = self.encode(x, return_reg_log=True)
@@ -681,6 +708,7 @@ class AutoencodingEngineV11(_EngineBase):
         else:
             z, idx, kl, _ = self._rt.encode_raw(x)
             reg_log = self._reg_log(idx, kl)
+        z = z.to(self._rt.out_dtype())
         if return_reg_log:
             return z, reg_log
         return z
@@ -690,7 +718,9 @@ class AutoencodingEngineV11(_EngineBase):
         rt = self._rt
         nat = rt.sync()
         x = rt._as_input(x)
-        B, _, T, H, W = x.shape
+        B, Cin, T, H, W = x.shape
+        if Cin != self.spec.in_channels:
+            raise ValueError(f"input has {Cin} channels, the model expects in_channels = {self.spec.in_channels}")
         prec = rt.precision()
         lib = nat.lib
         st = ChunkState(nat, prec, B, H, W, is_decoder=False, use_overlap=False)
@@ -705,7 +735,7 @@ class AutoencodingEngineV11(_EngineBase):
                 idx = torch.empty((B, Tz, Hz, Wz), dtype=torch.int32, device=x.device) if self.spec.regularizer == "fsq" else None
                 kl = torch.empty((), dtype=torch.float32, device=x.device) if self.spec.regularizer == "kl" else None
                 ws = st.workspace(Tc)
-                N.check(lib.vt_encode_chunk(st.handle, int(i == 0), _ptr(chunk), Tc, _ptr(noise), _ptr(z), _ptr(idx), _ptr(kl),
+                N.check(lib.vt_encode_chunk(st.handle, int(i == 0), _ptr(chunk), Cin, Tc, _ptr(noise), _ptr(z), _ptr(idx), _ptr(kl),
                                             _ptr(ws), ws.numel(), _stream_ptr(x.device)))
                 zs.append(z), idxs.append(idx), kls.append(kl)
         finally:
@@ -723,8 +753,8 @@ class AutoencodingEngineV11(_EngineBase):
         if decode_from_indices:
             z = self.indices_to_latent(z)
         if self.use_tiling:
-            return self.tile_decode(z)
-        return self._rt.decode_raw(z, False)
+            return self.tile_decode(z).to(self._rt.out_dtype())
+        return self._rt.decode_raw(z, False).to(self._rt.out_dtype())
 
     def tile_decode(self, z: Any) -> torch.Tensor:
         """autoencoder_v1_1.py:302-331: one look-ahead latent frame per chunk when use_overlap, tail frames dropped."""
@@ -732,8 +762,10 @@ class AutoencodingEngineV11(_EngineBase):
         nat = rt.sync()
         if not z.is_cuda:
             raise RuntimeError("vidtok_b200: inputs must be CUDA tensors; there is no CPU path")
+        if z.dim() != 5 or z.shape[1] != self.spec.z_channels:
+            raise ValueError(f"expected a [B,{self.spec.z_channels},T,H,W] latent, got {tuple(z.shape)}")
         z = z.detach().float().contiguous()
-        B, _, nf, Hz, Wz = z.shape
+        B, Cz, nf, Hz, Wz = z.shape
         tdf = self.encoder.time_downsample_factor
         if self.use_overlap:
             assert tdf in [2, 4, 8], "Only support 2x, 4x or 8x temporal downsampling now."
@@ -749,7 +781,7 @@ class AutoencodingEngineV11(_EngineBase):
                 To = nat.decoded_frames(Tzc)
                 out = torch.empty((B, self.spec.out_ch, To, Hz * f, Wz * f), dtype=torch.float32, device=z.device)
                 ws = st.workspace(Tzc)
-                N.check(nat.lib.vt_decode_chunk(st.handle, int(i == 0), _ptr(zc), Tzc, _ptr(out), _ptr(ws), ws.numel(),
+                N.check(nat.lib.vt_decode_chunk(st.handle, int(i == 0), _ptr(zc), Cz, Tzc, _ptr(out), _ptr(ws), ws.numel(),
                                                 _stream_ptr(z.device)))
                 outs.append(out[:, :, :-tdf] if look else out)
         finally:
