@@ -284,7 +284,7 @@ def run_b200_arm(args, c):
     copy_stream = torch.cuda.Stream(device=dev)
     in_bufs = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
 
-    def run_e2e(steps):
+    def run_e2e_clips(steps):
         main = torch.cuda.current_stream(dev)
         ready = [torch.cuda.Event(), torch.cuda.Event()]   # input buffer i holds its step's clip
         freed = [torch.cuda.Event(), torch.cuda.Event()]   # the step that read input buffer i has finished
@@ -309,6 +309,26 @@ def run_b200_arm(args, c):
                     out_host.copy_(dec, non_blocking=True)
         main.wait_stream(copy_stream)
         return dec
+
+    # Tiled long video: the library stages the chunks itself (vt_encode_video reads the pinned host video chunk by chunk on its
+    # copy stream while the previous chunk computes; vt_decode_video copies each decoded chunk to pinned host memory while the
+    # next one computes) -- the user-facing calls are model.encode(host_video) and model.tile_decode(z, out=host_buffer).
+    out_host_video = None
+
+    def run_e2e_video(steps):
+        nonlocal out_host_video
+        dec = None
+        with torch.no_grad():
+            for _ in range(steps):
+                zz = model.encode(x_host)
+                if out_host_video is None:
+                    nf = int(zz.shape[2])
+                    t_out = int(lib.vt_decode_video_frames(model._rt.sync().handle, nf, int(model.t_chunk_dec), int(bool(model.use_overlap))))
+                    out_host_video = torch.empty((B, 3, t_out, H, W), dtype=torch.float32).pin_memory()
+                dec = model.tile_decode(zz, out=out_host_video)
+        return dec[:, :, -T:].to(dev, non_blocking=True)
+
+    run_e2e = run_e2e_video if c["tiling"] else run_e2e_clips
 
     # the clock sampler starts BEFORE the warm-up: nvidia-smi takes ~1 s to initialise NVML, and doing that inside the
     # timed region cost the first steps ~10 % (profiles/notes_r1.md); its samples cover warm-up + timed steps, all under load
@@ -435,8 +455,11 @@ def run_b200_arm(args, c):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": nbytes + noise_bytes, "d2h_bytes_per_step": nbytes,
-                    "pipeline": "every step copies its clips from pinned host memory and its reconstruction back; the copies run on a "
-                                "second stream, double buffered against the previous / next step's kernels"},
+                    "pipeline": ("the library stages the pinned host video chunk by chunk on its copy stream while the previous chunk computes "
+                                 "and copies every decoded chunk back to pinned host memory while the next one computes (vt_encode_video / "
+                                 "vt_decode_video)") if c["tiling"] else
+                                ("every step copies its clips from pinned host memory and its reconstruction back; the copies run on a "
+                                 "second stream, double buffered against the previous / next step's kernels")},
             "gpu_launches": launches,
             "roofline": roof,
             "cpu_baseline": cpu,

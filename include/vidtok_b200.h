@@ -159,6 +159,38 @@ int32_t vt_encode_chunk(vt_chunk_state* s, int32_t is_first, const float* x_chun
 int32_t vt_decode_chunk(vt_chunk_state* s, int32_t is_first, const float* z_chunk, int32_t Cz, int32_t Tzc, float* x_out,
                         void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- whole-video tiling below the ABI (tile_encode / tile_decode, autoencoder_v1_1.py:218-228,244-264,302-331): the chunk
+ *      schedule, the causal caches and the chunk staging run inside the library -- one call per video, no host
+ *      synchronisation, no per-chunk allocation.  Chunk i+1 is staged on the library's own copy stream while chunk i
+ *      computes on the caller's stream (double buffering); with x_on_host / out_on_host the staging copies are the
+ *      host <-> device transfers themselves (pinned memory recommended).  The call returns with all work enqueued; the
+ *      caller's stream is made to wait for the copy stream. ---- */
+int64_t vt_encode_video_workspace_bytes(const vt_model* m, int32_t precision, int32_t B, int32_t T, int32_t H, int32_t W,
+                                        int32_t t_chunk_enc);
+/* x fp32 [B,C,T,H,W] (device, or host when x_on_host); noise device fp32 [B,z,Tz,Hz,Wz] = the per-chunk torch.randn draws
+ * concatenated along T (KL with sampling; else NULL); z / indices as vt_encode for the whole video (Tz = sum of the chunks'
+ * latent frames); kl_loss = mean of the per-chunk values (autoencoder_v1_1.py:261-264). */
+int32_t vt_encode_video(vt_model* m, int32_t precision, const float* x, int32_t x_on_host, int32_t B, int32_t C, int32_t T,
+                        int32_t H, int32_t W, int32_t t_chunk_enc, const float* noise, float* z, int32_t* indices,
+                        float* kl_loss, void* workspace, int64_t workspace_bytes, void* stream);
+int64_t vt_decode_video_workspace_bytes(const vt_model* m, int32_t precision, int32_t B, int32_t Tz, int32_t Hz, int32_t Wz,
+                                        int32_t t_chunk_dec, int32_t use_overlap);
+/* frames vt_decode_video writes (look-ahead tails dropped; the v1.1 forward then keeps the last T_in frames) */
+int32_t vt_decode_video_frames(const vt_model* m, int32_t Tz, int32_t t_chunk_dec, int32_t use_overlap);
+/* z device fp32 [B,Cz,Tz,Hz,Wz]; x_out fp32 [B,out_ch,vt_decode_video_frames(...),H,W] (device, or host when out_on_host) */
+int32_t vt_decode_video(vt_model* m, int32_t precision, const float* z, int32_t B, int32_t Cz, int32_t Tz, int32_t Hz, int32_t Wz,
+                        int32_t t_chunk_dec, int32_t use_overlap, float* x_out, int32_t out_on_host, void* workspace,
+                        int64_t workspace_bytes, void* stream);
+
+/* ---- video I/O adjacent steps (scripts/inference_reconstruct.py:41-47,71-82,231-239): the tokenizer runs at > 1000
+ *      frames/s, so the uint8 <-> float conversions around it belong on the device too ---- */
+/* frames: device uint8 [T,Hs,Ws,C] (decord's HWC frames); clip: device fp32 [C,T,H,W] = Normalize(.5,.5)(frames/255)
+ * of the crop window at (h0, w0) (CenterCrop; the optional Resize is not part of this entry point). */
+int32_t vt_video_u8_to_clip(const uint8_t* frames, float* clip, int32_t T, int32_t Hs, int32_t Ws, int32_t C, int32_t h0,
+                            int32_t w0, int32_t H, int32_t W, void* stream);
+/* clip: device fp32 [C,T,H,W]; frames: device uint8 [T,H,W,C] = uint8(255 * (clamp(clip,-1,1) + 1) / 2) (tensor_to_uint8). */
+int32_t vt_clip_to_video_u8(const float* clip, uint8_t* frames, int32_t C, int32_t T, int32_t H, int32_t W, void* stream);
+
 /* ---- single operators, exposed for the parity tests (same kernels the model path launches) ---- */
 typedef struct vt_conv_desc {
   int32_t B, Ti, Hi, Wi, Ci;        /* input, channels-last [B,Ti,Hi,Wi,Ci] */
@@ -194,6 +226,12 @@ typedef struct vt_conv_ex {
 int32_t vt_op_conv_ex(int32_t precision, const vt_conv_ex* e, const void* x, const void* cache, const float* w,
                       const float* bias, const void* res, const float* gamma, const float* beta, void* out, void* out2,
                       void* stream);
+/* Encoder conv_out with the KL / FSQ regularizer applied in the convolution's epilogue (regularizers.py:82-92,153-178,
+ * distributions.py:8-18): reg_mode 1 = KL (Co = 2*zc, zc in {4,8,16}; noise NULL = the mode), 2 = FSQ (Co = zc = len(levels)).
+ * h_out (fp32 [B,Co,T,H,W]) may be NULL; z fp32 [B,zc,T,H,W]; indices int32 [B,T,H,W] (FSQ); kl_loss 1 float (KL). */
+int32_t vt_op_conv_regularize(int32_t precision, const vt_conv_desc* d, const void* x, const float* w, const float* bias,
+                              int32_t reg_mode, int32_t zc, const int32_t* fsq_levels, const float* noise, float* h_out,
+                              float* z, int32_t* indices, float* kl_loss, void* stream);
 /* Encoder stem from the caller's fp32 [B,Ci,T,H,W] (t_rep replicated leading frames); out channels-last
  * [B,T+t_rep,H,W,Co] in the precision's activation type (BF16 / EXACT_TC). */
 int32_t vt_op_conv_stem(int32_t precision, const float* x, const float* w, const float* bias, void* out, int32_t B,
@@ -207,6 +245,12 @@ int32_t vt_op_head_planes(const void* x, const float* w, const float* bias, floa
 int32_t vt_op_upsample_conv(int32_t precision, int32_t kind, const void* x, const float* w, const float* bias, float alpha,
                             const float* gamma, const float* beta, int32_t ln_silu, void* out, void* out2, int32_t B,
                             int32_t T, int32_t H, int32_t W, int32_t Ci, int32_t Co, void* stream);
+/* ResnetCausalBlock1D (model_3dcausal.py:427-499) as the BF16 mode runs it for 128 channels (one fused launch):
+ * n1 = silu(LN1(x)) and x bf16 channels-last [B,T,H,W,C]; w1, w2 fp32 [C,C,3]; out = x + conv2(silu(LN2(conv1(n1))));
+ * optional out2 = act(LN3(out)) (g3/be3/out2 may be NULL). */
+int32_t vt_op_tblock(const void* n1, const void* x, const float* w1, const float* b1, const float* g2, const float* be2,
+                     const float* w2, const float* b2, const float* g3, const float* be3, int32_t out_silu, void* out,
+                     void* out2, int32_t B, int32_t T, int32_t H, int32_t W, int32_t C, void* stream);
 /* y = silu?(norm(x)) over channels-last x [rows, C]; groupnorm variants take frame geometry. */
 int32_t vt_op_layernorm(int32_t precision, const void* x, const float* gamma, const float* beta, void* y,
                         int64_t rows, int32_t C, int32_t apply_silu, void* stream);

@@ -167,7 +167,7 @@ def test_attention_core():
     ref = F.scaled_dot_product_attention(q.unsqueeze(0), k.unsqueeze(0), v.unsqueeze(0))[0]
     qd, kd, vd = q.cuda(), k.cuda(), v.cuda()
     o = torch.empty_like(qd)
-    ws = torch.empty(frames * tokens * tokens * 8 + 4096, dtype=torch.uint8, device="cuda")
+    ws = torch.empty(frames * tokens * (8 * tokens + 24 * C_) + 65536, dtype=torch.uint8, device="cuda")
     N.check(N.lib().vt_op_attention(N.PREC_FMA32, C.c_void_p(qd.data_ptr()), C.c_void_p(kd.data_ptr()), C.c_void_p(vd.data_ptr()),
                                     C.c_void_p(o.data_ptr()), frames, tokens, C_, C.c_void_p(ws.data_ptr()), ws.numel(), None))
     torch.cuda.synchronize()

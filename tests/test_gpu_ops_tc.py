@@ -3,8 +3,9 @@ bite"): every fused epilogue, padding mode and weight transformation of conv_tc 
 in BOTH tensor-core precisions, against fp64 torch statements of the reference op:
 
   * BF16     -- operands rounded to bf16 first; bound 2^-7*|ref| + 2e-2 (bf16 output rounding + fp32 accumulation)
-  * EXACT_TC -- fp32 operands as hi|lo bf16 planes (bf16x3 MMAs); bound 1e-4*(1 + |ref|): fp32-class, two orders of
-                magnitude below bf16 rounding, so a silent bf16 path or a wrong gamma/beta slice cannot pass.
+  * EXACT_TC -- fp32 operands as hi|lo bf16 planes (bf16x3 MMAs); bound 4e-4*(1 + |ref|).  Measured on B200: 2e-5 .. 2.3e-4
+                (the largest at K = 13824: dropped lo*lo terms plus the tensor core's fp32 accumulation), i.e. fp32-class and
+                ~50x below bf16 rounding, so a silent bf16 path or a wrong gamma/beta slice cannot pass.
 
 Reference lines: model_3dcausal.py:62-80 (LayerNorm), :26-27 (SiLU), :193-197 (CausalConv3d), :208-212 (Upsample),
 :267-273 (TimeUpsampleResCausal2x), :139-140 (attention); model_3dcausal_v1_1.py:216-236 (replicate / cache padding).
@@ -22,6 +23,7 @@ from vidtok_b200 import _native as N  # noqa: E402
 
 PRECS = [N.PREC_BF16, N.PREC_EXACT_TC]
 PIDS = ["bf16", "exact_tc"]
+X3_TOL = 4e-4
 
 
 def rnd(*shape, seed=0, scale=1.0):
@@ -40,7 +42,7 @@ def check(got, ref, precision, what="", slack=1.0):
     if precision == N.PREC_BF16:
         tol = slack * (2.0 ** -7 * ref.abs().double() + 2e-2)
     else:
-        tol = slack * 1e-4 * (1.0 + ref.abs().double())
+        tol = slack * X3_TOL * (1.0 + ref.abs().double())
     worst = float((err / tol).max())
     assert worst <= 1.0, f"{what}: max err {float(err.max()):.3e} (x{worst:.1f} the bound) at ref {float(ref.flatten()[(err / tol).argmax()]):.4f}"
     return float(err.max())
@@ -265,7 +267,7 @@ def test_conv_head_fp32_ncdhw_with_dropped_frames(precision):
         got, _ = op_conv_ex(x, w, b, precision=precision, to_off=to_off, out_f32=True)
         # fp32 output: no bf16 output rounding in BF16 mode either
         err = (got.double() - ref).abs()
-        assert float(err.max()) <= (2e-3 if precision == N.PREC_BF16 else 1e-4), float(err.max())
+        assert float(err.max()) <= (2e-3 if precision == N.PREC_BF16 else X3_TOL), float(err.max())
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -341,7 +343,7 @@ def test_attention_core_tcgen05(precision):
     got = from_act(o, precision)
     err = (got.double() - ref).abs()
     # P is rounded to bf16 in BF16 mode: 2^-8 relative on probabilities that sum to 1
-    assert float(err.max()) <= (3e-2 if precision == N.PREC_BF16 else 1e-4), float(err.max())
+    assert float(err.max()) <= (3e-2 if precision == N.PREC_BF16 else X3_TOL), float(err.max())
 
 
 @pytest.mark.parametrize("C_", [16, 128, 512])
@@ -354,9 +356,9 @@ def test_layernorm_split_rows(C_, silu):
     ref = F.layer_norm(x.double(), (C_,), g.double(), b.double(), eps=1e-6)
     if silu:
         ref = ref * torch.sigmoid(ref)
-    xd = split_rows(x.cuda())
+    xd, gd, bd = split_rows(x.cuda()), g.cuda(), b.cuda()
     y = torch.empty_like(xd)
-    N.check(N.lib().vt_op_layernorm(N.PREC_EXACT_TC, _p(xd), _p(g.cuda()), _p(b.cuda()), _p(y), rows, C_, int(silu), stream()))
+    N.check(N.lib().vt_op_layernorm(N.PREC_EXACT_TC, _p(xd), _p(gd), _p(bd), _p(y), rows, C_, int(silu), stream()))
     torch.cuda.synchronize()
     # the split input itself carries ~2^-17 relative error
     assert float((join_rows(y).cpu().double() - ref).abs().max()) < 1e-4
@@ -373,10 +375,132 @@ def test_groupnorm_split_rows(per_position):
     else:
         ref = F.group_norm(x, 32, g, b, eps=1e-6).permute(0, 2, 3, 1)
     ref = ref * torch.sigmoid(ref)
-    xd = split_rows(x.permute(0, 2, 3, 1).contiguous().cuda())
+    xd, gd, bd = split_rows(x.permute(0, 2, 3, 1).contiguous().cuda()), g.cuda(), b.cuda()
     y = torch.empty_like(xd)
     ws = torch.empty(frames * 64 * 4, dtype=torch.uint8, device="cuda")
-    N.check(N.lib().vt_op_groupnorm(N.PREC_EXACT_TC, _p(xd), _p(g.cuda()), _p(b.cuda()), _p(y), frames, H * W, C_,
+    N.check(N.lib().vt_op_groupnorm(N.PREC_EXACT_TC, _p(xd), _p(gd), _p(bd), _p(y), frames, H * W, C_,
                                     int(per_position), 1, _p(ws), ws.numel(), stream()))
     torch.cuda.synchronize()
-    assert float((join_rows(y).cpu() - ref).abs().max()) < 1e-4
+    # per-position statistics over C/32 = 2 channels amplify the 2^-17 relative error of the split input
+    assert float((join_rows(y).cpu() - ref).abs().max()) < (1e-3 if per_position else 1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# video I/O adjacent steps (scripts/inference_reconstruct.py:41-47,71-82)
+# ---------------------------------------------------------------------------------------------------------------
+def test_video_io_u8_to_clip_and_back_bit_exact():
+    import numpy as np
+    from torchvision import transforms
+    from vidtok_b200.video_io import clip_to_frames_u8, frames_to_clip
+    g = torch.Generator().manual_seed(0)
+    frames = torch.randint(0, 256, (5, 70, 90, 3), generator=g, dtype=torch.uint8)
+    H, W = 64, 80
+    tf = transforms.Compose([transforms.CenterCrop((H, W)), transforms.Normalize(mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5))])
+    ref = tf(frames.permute(0, 3, 1, 2).float() / 255.0).permute(1, 0, 2, 3)          # [C,T,H,W], reference statement
+    got = frames_to_clip(frames.cuda(), H, W)
+    assert tuple(got.shape) == (1, 3, 5, H, W) and torch.equal(got[0].cpu(), ref)
+    rec = ref * 1.3 + 0.05 * torch.randn(ref.shape, generator=g)                      # leaves [-1,1]: exercises the clamp
+    t = torch.clamp(rec, -1.0, 1.0)
+    ref_u8 = ((((t + 1.0) / 2.0).numpy() * 255).astype(np.uint8)).transpose(1, 2, 3, 0)   # tensor_to_uint8 + "t c h w -> t h w c"
+    got_u8 = clip_to_frames_u8(rec.cuda())
+    assert got_u8.dtype == torch.uint8 and np.array_equal(got_u8.cpu().numpy(), ref_u8)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fused temporal residual block (tblock_tc.cu)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("geom", [(1, 5, 8, 128), (2, 20, 16, 256), (1, 3, 64, 64), (3, 2, 8, 16)], ids=["w128", "w256_t20", "64x64", "w16"])
+@pytest.mark.parametrize("with_ln", [False, True], ids=["plain", "ln_out"])
+def test_fused_temporal_resblock(geom, with_ln):
+    """ResnetCausalBlock1D (model_3dcausal.py:473-499) for 128 channels as one launch: out = x + conv2(silu(LN2(conv1(n1)))),
+    optionally out2 = silu(LN3(out)).  Reference in fp64 on the bf16-rounded operands; the intermediate h is bf16 in the
+    kernel (as it is in the unfused BF16 path), hence the slack."""
+    from gpu_util import _p, cl, ncdhw, stream
+    B, T, H, W = geom
+    C_ = 128
+    n1 = rnd(B, C_, T, H, W, seed=1).to(torch.bfloat16).float()
+    x = rnd(B, C_, T, H, W, seed=2).to(torch.bfloat16).float()
+    w1 = rnd(C_, C_, 3, seed=3, scale=1 / math.sqrt(3 * C_)).to(torch.bfloat16).float()
+    w2 = rnd(C_, C_, 3, seed=4, scale=1 / math.sqrt(3 * C_)).to(torch.bfloat16).float()
+    b1, b2 = rnd(C_, seed=5), rnd(C_, seed=6)
+    g2, be2 = 1.0 + 0.5 * rnd(C_, seed=7), 0.3 * rnd(C_, seed=8) + torch.linspace(-0.5, 0.5, C_)
+    g3, be3 = 1.0 + 0.5 * rnd(C_, seed=9), 0.3 * rnd(C_, seed=10)
+    h = conv3d_ref(n1, w1[..., None, None], b1)
+    hn = ln_ref(h, g2, be2, True)
+    out = x.double() + conv3d_ref(hn.to(torch.bfloat16).double(), w2[..., None, None], b2)
+    out2 = ln_ref(out, g3, be3, True)
+    n1d, xd = cl(n1).to(torch.bfloat16).cuda(), cl(x).to(torch.bfloat16).cuda()
+    o = torch.empty_like(xd)
+    o2 = torch.empty_like(xd) if with_ln else None
+    dev = lambda t: t.contiguous().cuda()  # noqa: E731
+    w1d, w2d, b1d, b2d, g2d, be2d, g3d, be3d = map(dev, (w1, w2, b1, b2, g2, be2, g3, be3))
+    N.check(N.lib().vt_op_tblock(_p(n1d), _p(xd), _p(w1d), _p(b1d), _p(g2d), _p(be2d), _p(w2d), _p(b2d), _p(g3d), _p(be3d), 1,
+                                 _p(o), _p(o2), B, T, H, W, C_, stream()))
+    torch.cuda.synchronize()
+    check(ncdhw(o.float().cpu()), out, N.PREC_BF16, "tblock out", slack=2.0)
+    if with_ln:
+        check(ncdhw(o2.float().cpu()), out2, N.PREC_BF16, "tblock out2", slack=2.5)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# regularizers as the epilogue of the bottleneck convolution (encoder conv_out)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", PRECS, ids=PIDS)
+@pytest.mark.parametrize("zc", [4, 16])
+def test_conv_out_kl_epilogue(precision, zc):
+    """conv_out 512 -> 2z (k333) + DiagonalGaussianRegularizer in one launch: z = mean + exp(.5*clamp(logvar))*noise and
+    kl_loss = .5 * sum(mean^2 + var - 1 - logvar) / B (distributions.py:8-28, regularizers.py:82-92)."""
+    from gpu_util import _p, cl, conv_desc, stream, to_act
+    from oracle.vidtok_oracle import kl_regularize
+    B, Ci, T, H, W = 2, 512, 3, 16, 16
+    x = prep(rnd(B, Ci, T, H, W, seed=1), precision)
+    w = prep(rnd(2 * zc, Ci, 3, 3, 3, seed=2, scale=1 / math.sqrt(27 * Ci)), precision)
+    b = rnd(2 * zc, seed=3)
+    noise = rnd(B, zc, T, H, W, seed=4)
+    h_ref = conv3d_ref(x, w, b).float()
+    d, _ = conv_desc(x.shape, w.shape)
+    xd, wd, bd, nd = to_act(cl(x), precision), w.cuda(), b.cuda(), noise.cuda()
+    h = torch.empty((B, 2 * zc, T, H, W), device="cuda")
+    z = torch.empty((B, zc, T, H, W), device="cuda")
+    kl = torch.zeros((), device="cuda")
+    N.check(N.lib().vt_op_conv_regularize(precision, C.byref(d), _p(xd), _p(wd), _p(bd), 1, zc, None, _p(nd), _p(h), _p(z), None, _p(kl), stream()))
+    torch.cuda.synchronize()
+    tol = 2e-3 if precision == N.PREC_BF16 else X3_TOL
+    assert float((h.cpu() - h_ref).abs().max()) <= tol
+    # the regularizer itself is exact given the kernel's own h
+    z_ref, log = kl_regularize(h.cpu(), noise, True)
+    assert float((z.cpu() - z_ref).abs().max()) <= 1e-6 * max(1.0, float(z_ref.abs().max()))
+    assert abs(float(kl) - float(log["kl_loss"])) <= 1e-5 * abs(float(log["kl_loss"]))
+    # and without the optional h output
+    z2 = torch.empty_like(z)
+    N.check(N.lib().vt_op_conv_regularize(precision, C.byref(d), _p(xd), _p(wd), _p(bd), 1, zc, None, _p(nd), None, _p(z2), None, _p(kl), stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(z, z2)
+
+
+@pytest.mark.parametrize("precision", PRECS, ids=PIDS)
+def test_conv_out_fsq_epilogue(precision):
+    """conv_out 512 -> 5 + FSQ bound / round / index (regularizers.py:153-178) in one launch"""
+    from gpu_util import _p, cl, conv_desc, stream, to_act
+    from oracle.vidtok_oracle import fsq_regularize
+    B, Ci, T, H, W = 2, 512, 3, 16, 16
+    levels = (8, 8, 8, 8, 8)
+    x = prep(rnd(B, Ci, T, H, W, seed=1), precision)
+    w = prep(rnd(5, Ci, 3, 3, 3, seed=2, scale=1.5 / math.sqrt(27 * Ci)), precision)
+    b = rnd(5, seed=3)
+    d, _ = conv_desc(x.shape, w.shape)
+    xd, wd, bd = to_act(cl(x), precision), w.cuda(), b.cuda()
+    h = torch.empty((B, 5, T, H, W), device="cuda")
+    z = torch.empty((B, 5, T, H, W), device="cuda")
+    idx = torch.empty((B, T, H, W), dtype=torch.int32, device="cuda")
+    lv = (C.c_int32 * 5)(*levels)
+    N.check(N.lib().vt_op_conv_regularize(precision, C.byref(d), _p(xd), _p(wd), _p(bd), 2, 5, lv, None, _p(h), _p(z), _p(idx), None, stream()))
+    torch.cuda.synchronize()
+    codes_ref, log = fsq_regularize(h.cpu(), levels)      # bit-exact given the kernel's own h
+    assert torch.equal(idx.cpu(), log["indices"]) and torch.equal(z.cpu(), codes_ref)
+    if precision == N.PREC_EXACT_TC:                       # and against the fp64 conv: codes equal outside the tie band
+        _, log64 = fsq_regularize(conv3d_ref(x, w, b).float(), levels)
+        bad = idx.cpu() != log64["indices"]
+        pre = log64["pre_round"]
+        near = ((pre - pre.floor() - 0.5).abs() < 1e-4).any(dim=-1)
+        assert not (bad & ~near).any() and int(bad.sum()) <= 2

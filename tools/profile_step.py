@@ -1,4 +1,5 @@
-"""Per-layer timing of one B=8 17x256x256 bf16 forward (detailed profiler keys) -- run under gpurun."""
+"""Per-layer timing of one forward (detailed profiler keys) -- run under gpurun.
+  python tools/profile_step.py [B] [bf16|exact|mixed|fma] [kl488|fsq488|v11long|kl41616]"""
 import ctypes
 import json
 import os
@@ -18,12 +19,18 @@ from vidtok_b200.synth import synth_clip, synth_state_dict  # noqa: E402
 
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-    model = instantiate_from_config(bench.model_cfg())
+    prec = sys.argv[2] if len(sys.argv) > 2 else "bf16"
+    cfg_name = sys.argv[3] if len(sys.argv) > 3 else "kl488"
+    c = bench.CONFIGS[cfg_name]
+    model = instantiate_from_config(bench.model_cfg(c))
     sd = synth_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed=0)
     model.load_state_dict(sd)
     model = model.cuda().eval()
-    model.precision = "bf16"
-    x = synth_clip(B, 17, 256, 256).cuda()
+    model.precision = prec
+    if c["tiling"]:
+        model.use_tiling = True
+        model.t_chunk_enc, model.t_chunk_dec, model.use_overlap = c["tiling"]
+    x = synth_clip(B, c["T"], c["H"], c["W"]).cuda()
     with torch.no_grad():
         for _ in range(2):
             model(x)

@@ -63,6 +63,53 @@ __device__ __forceinline__ float silu_f(float x) {
 // accurate variant for the EXACT mode (expf, not the fast intrinsic)
 __device__ __forceinline__ float silu_exact(float x) { return x * (1.0f / (1.0f + expf(-x))); }
 
+// ---- regularizer arithmetic, shared by the stand-alone kernels (elementwise.cu) and the conv_out epilogue (conv_tc.cu) ----
+// FSQ (regularizers.py:153-178): bound = tanh(z + shift) * half_l - offset, round half-to-even, code = q / half_w,
+// index = sum_k (code_k * half_w_k + half_w_k) * basis_k -- fp32 op by op as torch evaluates it (no FMA contraction).
+struct FsqConst {
+  int d;
+  float half_l[VT_MAX_FSQ], offset[VT_MAX_FSQ], shift[VT_MAX_FSQ], half_w[VT_MAX_FSQ];
+  int levels[VT_MAX_FSQ], basis[VT_MAX_FSQ];
+};
+inline FsqConst make_fsq_const(int d, const int* levels) {
+  FsqConst c;
+  c.d = d;
+  int basis = 1;
+  for (int k = 0; k < VT_MAX_FSQ; ++k) { c.half_l[k] = c.offset[k] = c.shift[k] = c.half_w[k] = 0.f; c.levels[k] = c.basis[k] = 0; }
+  for (int k = 0; k < d; ++k) {
+    const int L = levels[k];
+    c.levels[k] = L;
+    c.basis[k] = basis;
+    basis *= L;
+    // regularizers.py:155-157, evaluated in fp32 like torch does for an int32 tensor times a python float
+    const float half_l = ((float)(L - 1) * (float)(1.0 + 1e-3)) / 2.0f;
+    const float offset = (L % 2 == 0) ? 0.5f : 0.0f;
+    c.half_l[k] = half_l;
+    c.offset[k] = offset;
+    c.shift[k] = atanhf(offset / half_l);
+    c.half_w[k] = (float)(L / 2);
+  }
+  return c;
+}
+// one channel of one token: returns the code, adds this digit's contribution to idx
+__device__ __forceinline__ float fsq_code(const FsqConst& c, int k, float zv, float& idx) {
+  const float t = (float)tanh((double)__fadd_rn(zv, c.shift[k]));
+  const float bounded = __fsub_rn(__fmul_rn(t, c.half_l[k]), c.offset[k]);
+  const float q = rintf(bounded);  // half-to-even, torch.round
+  const float code = __fdiv_rn(q, c.half_w[k]);
+  idx = __fadd_rn(idx, __fmul_rn(__fadd_rn(__fmul_rn(code, c.half_w[k]), c.half_w[k]), (float)c.basis[k]));
+  return code;
+}
+// KL (distributions.py:8-18, regularizers.py:82-92): z = mean + exp(.5 * clamp(logvar)) * noise; returns the element's
+// contribution mean^2 + var - 1 - logvar to the KL sum
+__device__ __forceinline__ float kl_sample_one(float mean, float logvar, float noise, int sample, float& z) {
+  logvar = fminf(fmaxf(logvar, -30.0f), 20.0f);
+  const float stdv = expf(0.5f * logvar);
+  const float var = expf(logvar);
+  z = sample ? __fadd_rn(mean, __fmul_rn(stdv, noise)) : mean;
+  return mean * mean + var - 1.0f - logvar;
+}
+
 // ---- generalized causal convolution geometry --------------------------------------------------------
 // One struct describes every convolution on the path:
 //   CausalConv3d / CausalConv1d (model_3dcausal.py:144-197), per-frame Conv2d of ResnetBlock (:296-306),

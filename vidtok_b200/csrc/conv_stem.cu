@@ -73,8 +73,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 
 // kSplit (EXACT_TC mode): the im2col rows and the weights are hi|lo bf16 pairs, every K=16 step issues hi*hi + lo*hi +
 // hi*lo into the same accumulator, and the output is written as hi | lo planes ([..., 2*Co]).
+// The bf16 variant (110 KB of shared memory, 2*Co = 256 TMEM columns for Co = 128) is sized so that TWO CTAs share an SM:
+// the phases of a tile (patch loads -> im2col -> MMA -> epilogue) are serialised inside a CTA by block barriers, and a
+// second resident CTA fills the bubbles.
 template <bool kSplit>
-__global__ void __launch_bounds__(256, 1) conv_stem_kernel(const StemParams p, const bf16* __restrict__ wpk /*[Co][128] or [Co][hi 128 | lo 128]*/) {
+__global__ void __launch_bounds__(256, kSplit ? 1 : 2) conv_stem_kernel(const StemParams p, const bf16* __restrict__ wpk /*[Co][128] or [Co][hi 128 | lo 128]*/) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -374,7 +377,10 @@ cudaError_t launch_conv_stem(const ConvP& p, const float* x, const bf16* wpk, bf
   char det[96] = "";
   if (prof_enabled()) snprintf(det, sizeof(det), "k333 %d->%d @%dx%dx%d", p.Ci, p.Co, p.To, p.Hi, p.Wi);
   ProfScope _ps(p.split ? "conv_stem3" : "conv_stem", 2.0 * M * 27 * p.Ci * p.Co, (double)p.B * p.Ci * p.Ti * p.Hi * p.Wi * 4.0 + M * p.Co * 2.0 * pl, s, det);
-  const unsigned grid = (unsigned)(t.num_tiles < num_sms ? t.num_tiles : num_sms);
+  // two CTAs per SM when both fit (shared memory and the 512 TMEM columns)
+  const int per_sm = (!p.split && 2 * (smem + 1024) <= 227 * 1024 && 2 * (int)t.tmem_cols <= 512) ? 2 : 1;
+  const long long slots = (long long)per_sm * num_sms;
+  const unsigned grid = (unsigned)(t.num_tiles < slots ? t.num_tiles : slots);
   if (p.split) conv_stem_kernel<true><<<grid, 256, smem, s>>>(t, wpk);
   else conv_stem_kernel<false><<<grid, 256, smem, s>>>(t, wpk);
   count_launch();

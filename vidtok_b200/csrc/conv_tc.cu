@@ -24,9 +24,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 
 #include "common.cuh"
 #include "kernels.h"
+#include "tc_ptx.cuh"
 
 namespace vt {
 
@@ -100,6 +102,13 @@ struct TcParams {
   // A_hi, A_lo, B_hi, B_lo and issues A_hi*B_hi + A_lo*B_hi + A_hi*B_lo into the same fp32 TMEM accumulator
   // (error ~2^-17 per product: fp32-class results on the bf16 tensor pipe).  Channel coordinate of the lo plane:
   int split, a_lo, b_lo, o_lo;   // = Cin, Kpad, Cout
+  // regularizer epilogue on the fp32 heads (TcRegFusion): the owner of a row holds every channel of its position
+  int reg_mode, reg_zc, reg_sample;
+  const float* reg_noise;
+  float* reg_z;
+  int* reg_idx;
+  double* reg_kl;
+  FsqConst reg_fsq;
 };
 
 struct TcMaps {
@@ -117,205 +126,7 @@ constexpr int kEpiWarp0 = 3;            // first epilogue warp (any 8 consecutiv
 constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;
 constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
 
-// ---------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 8000000000LL) __trap();
-  }
-}
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
-      ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-// same with an L2 evict-first policy: results far larger than L2 are not re-read before they would be evicted anyway, and
-// should not push the input frames that neighbouring taps / tiles still need out of the cache
-__device__ __forceinline__ void tma_store_5d_stream(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "{\n\t"
-      ".reg .b64 pol;\n\t"
-      "createpolicy.fractional.L2::evict_first.b64 pol, 1.0;\n\t"
-      "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5, %6}], [%1], pol;\n\t"
-      "}"
-      ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
-      ::"r"(bar), "r"(rank) : "memory");
-}
-// 2-CTA TMA loads: data lands in this CTA's shared memory, the transaction bytes are credited to the LEADER's barrier
-// (peer bit of the barrier address cleared, cute::Sm100MmaPeerBitMask)
-__device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                                int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"((uint16_t)3) : "memory");
-}
-__device__ __forceinline__ void umma_f16_2sm_lohi(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
-                                                  uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      ".reg .b64 da, db;\n\t"
-      "setp.ne.b32 p, %6, 0;\n\t"
-      "mov.b64 da, {%1, %2};\n\t"
-      "mov.b64 db, {%3, %4};\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t"
-      "}"
-      ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accum)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
-                                              uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      ".reg .b64 da, db;\n\t"
-      "setp.ne.b32 p, %6, 0;\n\t"
-      "mov.b64 da, {%1, %2};\n\t"
-      "mov.b64 db, {%3, %4};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
-      "}"
-      ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accum)
-      : "memory");
-}
-// one lane of the (converged) warp
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "elect.sync _|P1, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, P1;\n\t"
-      "}"
-      : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// Shared-memory matrix descriptors (cute::UMMA::SmemDescriptor), K-major SWIZZLE_128B, are built as two 32-bit words:
-//   lo = start >> 4 [0,14) | LBO >> 4 = 1 [16,30)        hi = SBO >> 4 [0,14) | version = 1 [14,16) | layout = 2 [29,32)
-// SBO = byte distance between 8-row groups: 1024 for a dense tile, hP * 128 for a tile inside a halo window.  The 128-byte
-// swizzle is a function of the absolute shared-memory address, so a tile may start at any 128-byte row of a window that
-// TMA wrote with the same swizzle (descriptor base offset stays 0; verified on B200, tests/test_gpu_ops.py tc_halo_*).
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
-__device__ __forceinline__ uint32_t make_idesc(int N, int M = 128) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    f[2 * i] = __low2float(h[i]);
-    f[2 * i + 1] = __high2float(h[i]);
-  }
-}
-// bf16 pair <-> fp32 through plain 32-bit registers (pointer punning would push the packed row into local memory)
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-// packed fp32 pairs (sm_100 FADD2 / FMUL2 / FFMA2): two lanes per issue slot in the epilogue arithmetic
-__device__ __forceinline__ uint64_t pk2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ float tanh_approx(float x) { float t; asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x)); return t; }
-__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
-__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+using namespace tcx;
 
 struct TileCoord {
   int b, t0, h0, w0, n0;
@@ -748,6 +559,42 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         }
       };
 
+      // regularizer on the complete fp32 row f[0..31] of this thread's position (heads with Cout <= 32: one 32-column
+      // chunk, tile n0 == 0).  Called by all 32 lanes (the KL partial sums are reduced across the warp).
+      auto regularize_row = [&](const float (&f)[32]) {
+        const long long plane = p.osC;                                  // T*H*W of the [B,C,T,H,W] tensors
+        const long long pos = ooff - (long long)tc.b * p.osB;
+        if (p.reg_mode == 1) {
+          float part = 0.f;
+          // z_channels is a compile-time constant inside each case: f[] stays in registers (no dynamic indexing)
+          auto kl_row = [&](auto ZC) {
+            constexpr int zc = decltype(ZC)::value;
+            const long long zb = (long long)tc.b * zc * plane + pos;
+#pragma unroll
+            for (int c = 0; c < zc; ++c) {
+              float zv;
+              part += kl_sample_one(f[c], f[zc + c], p.reg_sample ? p.reg_noise[zb + c * plane] : 0.f, p.reg_sample, zv);
+              p.reg_z[zb + c * plane] = zv;
+            }
+          };
+          if (valid) {
+            if (p.reg_zc == 4) kl_row(std::integral_constant<int, 4>());
+            else if (p.reg_zc == 8) kl_row(std::integral_constant<int, 8>());
+            else kl_row(std::integral_constant<int, 16>());
+          }
+          double dsum = (double)part;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+          if (lane == 0) atomicAdd(p.reg_kl, dsum);
+        } else if (valid) {
+          const long long zb = (long long)tc.b * p.reg_zc * plane + pos;
+          float idx = 0.f;
+#pragma unroll
+          for (int c = 0; c < VT_MAX_FSQ; ++c)
+            if (c < p.reg_zc) p.reg_z[zb + c * plane] = fsq_code(p.reg_fsq, c, f[c], idx);
+          if (p.reg_idx) p.reg_idx[(long long)tc.b * plane + pos] = (int)idx;
+        }
+      };
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * p.MT + mt) * p.BN);
@@ -863,7 +710,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
               }
               if (p.out_f32) {
                 // external fp32 heads / attention scores: direct stores, only the real output channels
-                if (valid) {
+                if (p.reg_mode) regularize_row(f);
+                if (valid && optr) {
                   float* of = reinterpret_cast<float*>(optr) + ooff;
                   if (p.osC == 1 && tc.n0 + jj + 32 <= p.Co_real) {
 #pragma unroll
@@ -953,7 +801,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           }
           if (p.out_f32) {
             // external fp32 heads (never fused with LayerNorm): direct stores, only the real output channels
-            if (valid) {
+            if (p.reg_mode) regularize_row(f);
+            if (valid && p.out) {
               float* of = reinterpret_cast<float*>(p.out) + ooff;
               if (p.osC == 1 && tc.n0 + jj + 32 <= p.Co_real) {
 #pragma unroll
@@ -1202,7 +1051,7 @@ bool conv_tc_supported(const ConvP& p, DType tout, bool planning) {
 
 // w_nk: [Co_pad][Kpad] bf16 with Co_pad = roundup(Co, 32) (rows >= Co are zero).
 cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int Kpad, void* out, DType tout, cudaStream_t s,
-                           int w_batches, long long w_batch_stride, const TcLnFusion* ln) {
+                           int w_batches, long long w_batch_stride, const TcLnFusion* ln, const TcRegFusion* reg) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { g_tc_err = "cuTensorMapEncodeTiled unavailable"; return cudaErrorNotSupported; }
   const bool split = p.split != 0;
@@ -1222,10 +1071,11 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   int bn_local = 0;
   // Tile geometry + shared-memory plan.  Split operands double every operand tile: when the preferred geometry (halo
   // windows, two M tiles) leaves fewer than 2 pipeline stages, fall back to the next simpler one.
-  auto plan = [&](bool allow_halo, bool allow_mt2) -> int {
+  auto plan = [&](bool allow_halo, bool allow_mt2, bool allow_tma_store, int bn_cap) -> int {
   const int mt_cap = allow_mt2 ? mt_env : 1;
   t.halo = 0; t.hP = 0; t.a_stages = 0; t.halo_bytes = 0;
   t.BN = choose_bn(Co_pad);
+  if (bn_cap && t.BN > bn_cap && Co_pad % bn_cap == 0) t.BN = bn_cap;
   // two M tiles per CTA tile when the N tile is narrow: one B (weight) tile then feeds 256 output rows, which halves
   // the weight bytes per FLOP (the N<=128 layers are operand-bandwidth bound otherwise)
   t.MT = 1;
@@ -1288,6 +1138,7 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
     int ntaps_eff = p.kt * p.kh * p.kw;
     if (ntaps_eff * (p.Ci / 64) >= 48) t.tma_store = 0;
   }
+  if (!allow_tma_store) t.tma_store = 0;
   bn_local = t.pair ? t.BN / 2 : t.BN;
   const size_t stage_bytes = (size_t)cw * ((t.halo ? 0 : (size_t)t.MT * kABytes) + (size_t)bn_local * 128);
   const size_t budget = 222 * 1024;
@@ -1320,9 +1171,15 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   return 0;
   };
   {
-    int rc = plan(true, true);
-    if (rc == 1) rc = plan(false, true);
-    if (rc == 1) rc = plan(false, false);
+    // preference order; the later entries only matter for split operands (every operand tile doubled): give up the halo
+    // windows, the second M tile, the store staging buffers, and finally (when no LayerNorm needs the whole row) the wide N tile
+    const bool need_row = ln && ln->mode;
+    int rc = plan(true, true, true, 0);
+    if (rc == 1) rc = plan(false, true, true, 0);
+    if (rc == 1) rc = plan(false, false, true, 0);
+    if (rc == 1) rc = plan(false, false, false, 0);
+    if (rc == 1 && !need_row) rc = plan(false, false, true, 128);
+    if (rc == 1 && !need_row) rc = plan(false, false, false, 128);
     if (rc == 1) g_tc_err = "not enough shared memory for 2 stages";
     if (rc != 0) return cudaErrorInvalidValue;
   }
@@ -1340,6 +1197,20 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   if (ln && ln->mode) {
     if (t.BN != p.Co || !out_bf16) { g_tc_err = "fused LayerNorm needs one N tile covering Cout and bf16 output"; return cudaErrorInvalidValue; }
     t.ln_mode = ln->mode; t.ln_silu = ln->silu ? 1 : 0; t.ln_gamma = ln->gamma; t.ln_beta = ln->beta; t.out2 = ln->out2;
+  }
+  if (reg && reg->mode) {
+    const int need = reg->mode == 1 ? 2 * reg->zc : reg->zc;
+    if (tout != DT_F32 || Co_pad != 32 || t.BN != 32 || need > p.Co || (reg->mode == 1 ? (reg->zc != 4 && reg->zc != 8 && reg->zc != 16) : reg->zc > VT_MAX_FSQ) || !reg->z ||
+        (reg->mode == 1 && (!reg->kl_acc || (reg->sample && !reg->noise))) || p.osW != 1) {
+      g_tc_err = "regularizer epilogue needs an fp32 [B,C,T,H,W] head with Cout <= 32 holding all latent channels";
+      return cudaErrorInvalidValue;
+    }
+    t.reg_mode = reg->mode; t.reg_zc = reg->zc; t.reg_sample = reg->sample; t.reg_noise = reg->noise; t.reg_z = reg->z;
+    t.reg_idx = reg->indices; t.reg_kl = reg->kl_acc;
+    if (reg->mode == 2) t.reg_fsq = make_fsq_const(reg->zc, reg->fsq_levels);
+  } else if (!out) {
+    g_tc_err = "null output";
+    return cudaErrorInvalidValue;
   }
   t.w_batched = w_batches > 1 ? 1 : 0;
   if (t.w_batched && w_batches != p.B) { g_tc_err = "batched weights need one weight matrix per batch element"; return cudaErrorInvalidValue; }

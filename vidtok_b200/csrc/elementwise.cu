@@ -454,13 +454,9 @@ __global__ void __launch_bounds__(256) kl_kernel(const float* __restrict__ h, co
   double local = 0.0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long b = i / (zc * P), r = i % (zc * P);
-    const float mean = h[b * 2 * zc * P + r];
-    float logvar = h[b * 2 * zc * P + zc * P + r];
-    logvar = fminf(fmaxf(logvar, -30.0f), 20.0f);
-    const float stdv = expf(0.5f * logvar);
-    const float var = expf(logvar);
-    z[i] = sample ? __fadd_rn(mean, __fmul_rn(stdv, noise[i])) : mean;
-    local += (double)(mean * mean + var - 1.0f - logvar);
+    float zv;
+    local += (double)kl_sample_one(h[b * 2 * zc * P + r], h[b * 2 * zc * P + zc * P + r], sample ? noise[i] : 0.f, sample, zv);
+    z[i] = zv;
   }
   __shared__ double red[8];
   for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
@@ -475,11 +471,6 @@ __global__ void __launch_bounds__(256) kl_kernel(const float* __restrict__ h, co
 __global__ void kl_finish_kernel(const double* acc, int B, float* out) { *out = (float)(0.5 * acc[0] / B); }
 
 // ---- FSQ: bound -> round -> index (regularizers.py:153-178,206-262) --------------------------------------
-struct FsqConst {
-  int d;
-  float half_l[VT_MAX_FSQ], offset[VT_MAX_FSQ], shift[VT_MAX_FSQ], half_w[VT_MAX_FSQ];
-  int levels[VT_MAX_FSQ], basis[VT_MAX_FSQ];
-};
 __global__ void __launch_bounds__(256) fsq_kernel(const float* __restrict__ h, FsqConst c, long long P, int B,
                                                   float* __restrict__ codes, int* __restrict__ indices) {
   const long long total = (long long)B * P;
@@ -487,14 +478,7 @@ __global__ void __launch_bounds__(256) fsq_kernel(const float* __restrict__ h, F
     const long long b = i / P, pos = i % P;
     float idx = 0.f;
     for (int k = 0; k < c.d; ++k) {
-      const float zv = h[(b * c.d + k) * P + pos];
-      // fp32 op-by-op as the reference: tanh(z + shift) * half_l - offset, no FMA contraction
-      const float t = (float)tanh((double)__fadd_rn(zv, c.shift[k]));
-      const float bounded = __fsub_rn(__fmul_rn(t, c.half_l[k]), c.offset[k]);
-      const float q = rintf(bounded);  // half-to-even, torch.round
-      const float code = __fdiv_rn(q, c.half_w[k]);
-      codes[(b * c.d + k) * P + pos] = code;
-      idx = __fadd_rn(idx, __fmul_rn(__fadd_rn(__fmul_rn(code, c.half_w[k]), c.half_w[k]), (float)c.basis[k]));
+      codes[(b * c.d + k) * P + pos] = fsq_code(c, k, h[(b * c.d + k) * P + pos], idx);
     }
     if (indices) indices[i] = (int)idx;
   }
@@ -512,26 +496,6 @@ __global__ void __launch_bounds__(256) fsq_i2c_kernel(const int* __restrict__ in
     }
   }
 }
-FsqConst make_fsq_const(int d, const int* levels) {
-  FsqConst c;
-  c.d = d;
-  int basis = 1;
-  for (int k = 0; k < d; ++k) {
-    const int L = levels[k];
-    c.levels[k] = L;
-    c.basis[k] = basis;
-    basis *= L;
-    // regularizers.py:155-157, evaluated in fp32 like torch does for an int32 tensor times a python float
-    const float half_l = ((float)(L - 1) * (float)(1.0 + 1e-3)) / 2.0f;
-    const float offset = (L % 2 == 0) ? 0.5f : 0.0f;
-    c.half_l[k] = half_l;
-    c.offset[k] = offset;
-    c.shift[k] = atanhf(offset / half_l);
-    c.half_w[k] = (float)(L / 2);
-  }
-  return c;
-}
-
 // ---- weight repacking -------------------------------------------------------------------------------------
 __global__ void pack_w_kn_kernel(const float* __restrict__ w, float* __restrict__ out, int Co, int Ci, int taps) {
   const long long total = (long long)Co * Ci * taps;
@@ -800,6 +764,39 @@ __global__ void __launch_bounds__(256) f32_to_split_kernel(const float* __restri
     RowAcc<split16>::st(y + (i / C) * 2 * C, C, (int)(i % C), x[i]);
 }
 
+// ---- video I/O adjacent steps (scripts/inference_reconstruct.py:41-47,71-75 and :78-82,231-239) ------------------------
+// decoded frames uint8 [T,Hs,Ws,3] (decord's HWC layout) -> centre-cropped, normalised clip fp32 [3,T,H,W] in [-1,1]:
+// frames.float() / 255.0, then Normalize(mean .5, std .5) = (v - .5) / .5, op by op as torch evaluates them
+__global__ void __launch_bounds__(256) u8_frames_to_clip_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, int T,
+                                                                int Hs, int Ws, int C, int h0, int w0, int H, int W) {
+  const long long total = (long long)C * T * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    long long r = i / W;
+    const int h = (int)(r % H); r /= H;
+    const int t = (int)(r % T);
+    const int c = (int)(r / T);
+    const float v = __fdiv_rn((float)src[(((long long)t * Hs + h0 + h) * Ws + w0 + w) * C + c], 255.0f);
+    dst[i] = __fdiv_rn(__fsub_rn(v, 0.5f), 0.5f);
+  }
+}
+// reconstruction fp32 [C,T,H,W] -> uint8 frames [T,H,W,C]: clamp(-1,1), (x+1)/2, *255, truncate (numpy astype(uint8))
+__global__ void __launch_bounds__(256) clip_to_u8_frames_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, int C,
+                                                                int T, int H, int W) {
+  const long long total = (long long)T * H * W * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H);
+    const int t = (int)(r / H);
+    float v = src[(((long long)c * T + t) * H + h) * W + w];
+    v = fminf(fmaxf(v, -1.0f), 1.0f);
+    v = __fmul_rn(__fdiv_rn(__fadd_rn(v, 1.0f), 2.0f), 255.0f);
+    dst[i] = (uint8_t)v;
+  }
+}
+
 inline int grid_for(long long total, int block = 256) {
   long long g = (total + block - 1) / block;
   const long long cap = 148LL * 16;
@@ -910,6 +907,15 @@ cudaError_t launch_kl(const float* h, const float* noise, int zc, long long P, i
     kl_finish_kernel<<<1, 1, 0, s>>>(scratch, B, kl_loss);
     count_launch();
   }
+  return cudaGetLastError();
+}
+
+// fused KL (conv_out epilogue accumulates into `scratch`): clear before, finish after
+cudaError_t launch_kl_clear(double* scratch, cudaStream_t s) { return cudaMemsetAsync(scratch, 0, sizeof(double), s); }
+cudaError_t launch_kl_finish(const double* scratch, int B, float* kl_loss, cudaStream_t s) {
+  if (!kl_loss) return cudaSuccess;
+  kl_finish_kernel<<<1, 1, 0, s>>>(scratch, B, kl_loss);
+  count_launch();
   return cudaGetLastError();
 }
 
@@ -1034,6 +1040,23 @@ cudaError_t launch_copy_frames(DType t, const void* src, void* dst, int B, long 
   return cudaGetLastError();
 }
 
+cudaError_t launch_u8_frames_to_clip(const uint8_t* src, float* dst, int T, int Hs, int Ws, int C, int h0, int w0, int H, int W,
+                                    cudaStream_t s) {
+  const long long total = (long long)C * T * H * W;
+  if (total == 0) return cudaSuccess;
+  ProfScope _ps("u8_frames_to_clip", 0.0, 5.0 * total, s);
+  u8_frames_to_clip_kernel<<<grid_for(total), 256, 0, s>>>(src, dst, T, Hs, Ws, C, h0, w0, H, W);
+  count_launch();
+  return cudaGetLastError();
+}
+cudaError_t launch_clip_to_u8_frames(const float* src, uint8_t* dst, int C, int T, int H, int W, cudaStream_t s) {
+  const long long total = (long long)C * T * H * W;
+  if (total == 0) return cudaSuccess;
+  ProfScope _ps("clip_to_u8_frames", 0.0, 5.0 * total, s);
+  clip_to_u8_frames_kernel<<<grid_for(total), 256, 0, s>>>(src, dst, C, T, H, W);
+  count_launch();
+  return cudaGetLastError();
+}
 cudaError_t launch_split_to_f32(const bf16* x, float* y, long long rows, int C, cudaStream_t s) {
   if (rows * C == 0) return cudaSuccess;
   split_to_f32_kernel<<<grid_for(rows * C), 256, 0, s>>>((const split16*)x, y, rows, C);

@@ -62,6 +62,10 @@ cudaError_t launch_ncdhw_to_cl(DType t, const float* x, void* y, int B, int C, i
 cudaError_t launch_copy_frames(DType t, const void* src, void* dst, int B, long long src_bs, long long dst_bs,
                                long long n_per_batch, cudaStream_t s);
 
+// video I/O adjacent steps: decoded uint8 frames [T,Hs,Ws,C] -> cropped normalised clip fp32 [C,T,H,W]; clip -> uint8 frames
+cudaError_t launch_u8_frames_to_clip(const uint8_t* src, float* dst, int T, int Hs, int Ws, int C, int h0, int w0, int H, int W,
+                                    cudaStream_t s);
+cudaError_t launch_clip_to_u8_frames(const float* src, uint8_t* dst, int C, int T, int H, int W, cudaStream_t s);
 // hi|lo split rows [rows][hi(C) | lo(C)] <-> fp32 rows [rows][C]
 cudaError_t launch_split_to_f32(const bf16* x, float* y, long long rows, int C, cudaStream_t s);
 cudaError_t launch_f32_to_split(const float* x, bf16* y, long long rows, int C, cudaStream_t s);
@@ -76,11 +80,28 @@ struct TcLnFusion {
   const float* beta = nullptr;
   void* out2 = nullptr;
 };
+// Regularizer fused into the epilogue of the encoder's conv_out (fp32 heads, Cout <= 32: the thread that owns an output
+// position holds all of its channels): KL reparameterisation (distributions.py:8-18) or FSQ bound/round/index
+// (regularizers.py:153-178), written straight to the caller's z / indices tensors ([B,zc,T,H,W] / [B,T,H,W]).
+struct TcRegFusion {
+  int mode = 0;                  // 0 none, 1 KL, 2 FSQ
+  int zc = 0;
+  int sample = 1;                // KL: z = mean + std * noise (else the mode)
+  const float* noise = nullptr;  // KL, [B,zc,T,H,W]
+  float* z = nullptr;
+  int* indices = nullptr;        // FSQ (may be null)
+  double* kl_acc = nullptr;      // KL: sum over all elements of mean^2 + var - 1 - logvar (cleared by the caller)
+  int fsq_levels[VT_MAX_FSQ] = {0};
+};
 bool conv_tc_can_fuse_ln(const ConvP& p);
 // planning = true: geometry-only answer (workspace dry runs: no device pointers, possibly no driver)
 bool conv_tc_supported(const ConvP& p, DType tout, bool planning = false);
+// out may be null when a regularizer epilogue consumes the result (reg != nullptr)
 cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int Kpad, void* out, DType tout, cudaStream_t s,
-                           int w_batches = 1, long long w_batch_stride = 0, const TcLnFusion* ln = nullptr);
+                           int w_batches = 1, long long w_batch_stride = 0, const TcLnFusion* ln = nullptr,
+                           const TcRegFusion* reg = nullptr);
+cudaError_t launch_kl_clear(double* scratch, cudaStream_t s);
+cudaError_t launch_kl_finish(const double* scratch, int B, float* kl_loss, cudaStream_t s);
 // decoder head through per-tap partial outputs (see elementwise.cu)
 cudaError_t launch_tap_planes_gather(const bf16* P, const float* bias, float* out, int B, int Ti, int H, int W, int NP, int Co,
                                      int to_off, cudaStream_t s);
@@ -90,6 +111,14 @@ cudaError_t launch_transpose_bf16(const bf16* x, bf16* y, int batch, int rows, i
 const char* conv_tc_last_error();
 void conv_tc_set_pair(bool on);
 int conv_tc_cluster_query(int smem, char* msg, int cap);
+
+// tblock_tc.cu: fused ResnetCausalBlock1D (k311 conv -> LayerNorm -> SiLU -> k311 conv + residual) for C = 128, v1.0 padding
+bool tblock_tc_supported(int B, int T, int H, int W, int C, bool planning = false);
+cudaError_t launch_tblock_tc(const bf16* n1, const bf16* x, const bf16* w1, const float* bias1, const float* gamma2,
+                             const float* beta2, const bf16* w2, const float* bias2, bf16* out, bf16* out2,
+                             const float* gamma_out, const float* beta_out, bool out_silu, int B, int T, int H, int W,
+                             cudaStream_t s);
+const char* tblock_tc_last_error();
 
 // conv_stem.cu (thread-built im2col A tile + tcgen05 for the Cin=3 stem)
 bool conv_stem_supported(const ConvP& p);

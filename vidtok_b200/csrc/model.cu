@@ -305,6 +305,10 @@ struct ConvOpt {
   void* ln2_view = nullptr;       // with out_view: where the normalised copy goes (same strides)
   mutable bool fused1 = false, fused2 = false;
   mutable Act ln2_act;            // filled when fused2 and no view was given
+  // regularizer (KL / FSQ) fused into the epilogue of an fp32 head (encoder conv_out); honoured on the tcgen05 path only
+  const TcRegFusion* reg = nullptr;
+  bool reg_only = false;          // nobody reads the head's own output (h_pre): skip its stores when the regularizer is fused
+  mutable bool fused_reg = false;
 };
 
 // effective precision of one stack: MIXED = encoder EXACT_TC, decoder BF16
@@ -518,11 +522,17 @@ struct Exec {
         if (!ok()) return out;
       }
     }
+    // regularizer epilogue: same decision in the planning pass and the real pass (geometry only)
+    const bool reg_fuse = tc && o.reg && o.reg->mode && tout == DT_F32 && w.Co_pad == 32 &&
+                          (o.reg->mode == 1 ? (o.reg->zc == 4 || o.reg->zc == 8 || o.reg->zc == 16) : o.reg->zc <= VT_MAX_FSQ);
+    o.fused_reg = reg_fuse;
     if (!dry) {
       const bf16* wst = split ? w.w_stem3 : w.w_stem;
       const bool stem = tcm && !o.force_simt && o.ext_in && !o.ext_out && !o.out_view && wst && conv_stem_supported(p);
       if (tc) {
-        if (!cuda(launch_conv_tc(p, (const bf16*)in.p, wtc, w.Kpad, out.p, tout, s, 1, 0, lf.mode ? &lf : nullptr), conv_tc_last_error())) return out;
+        void* optr = (reg_fuse && o.reg_only) ? nullptr : out.p;
+        if (!cuda(launch_conv_tc(p, (const bf16*)in.p, wtc, w.Kpad, optr, tout, s, 1, 0, lf.mode ? &lf : nullptr, reg_fuse ? o.reg : nullptr),
+                  conv_tc_last_error())) return out;
       } else if (stem) {
         if (!cuda(launch_conv_stem(p, o.ext_in, wst, (bf16*)out.p, s), "conv_stem")) return out;
       } else if (!w.w_kn) {
@@ -604,8 +614,30 @@ struct Exec {
   // ResnetBlock (2D, model_3dcausal.py:317-337), ResnetCausalBlock1D (:473-499; GroupNorm statistics per position, see
   // the oracle) and ResnetCausalBlock (3D, :400-424) share one shape: LN,SiLU,conv1,LN,SiLU,conv2,+skip.
   // `next`: the norm the FOLLOWING stage applies to this block's output (fused into conv2's epilogue when possible).
+  // ResnetCausalBlock1D as ONE launch (tblock_tc.cu): BF16 mode, v1.0 zero padding, LayerNorm, 128 channels
+  bool resblock1d_fused(const ResBlockW& r, Stream& st, const NormW* next, bool next_silu) {
+    if (prec != VT_PREC_BF16 || m->desc.version != 0 || m->desc.norm_type != VT_NORM_LAYERNORM) return false;
+    if (r.c1.Ci != 128 || r.c1.Co != 128 || r.c2.Co != 128 || !r.c1.w_nk || !r.c2.w_nk || r.c1.kt != 3 || r.c1.kh != 1) return false;
+    if (!tblock_tc_supported(st.x.B, st.x.T, st.x.H, st.x.W, st.x.C, dry)) return false;
+    Act n1 = take_norm(st, r.n1, true, true);
+    Act out = new_act(st.x.B, st.x.T, st.x.H, st.x.W, 128);
+    Act out2;
+    if (next) out2 = new_act(st.x.B, st.x.T, st.x.H, st.x.W, 128);
+    if (ok() && !dry)
+      cuda(launch_tblock_tc((const bf16*)n1.p, (const bf16*)st.x.p, r.c1.w_nk, r.c1.bias, r.n2.gamma, r.n2.beta, r.c2.w_nk, r.c2.bias,
+                            (bf16*)out.p, next ? (bf16*)out2.p : nullptr, next ? next->gamma : nullptr, next ? next->beta : nullptr,
+                            next_silu, st.x.B, st.x.T, st.x.H, st.x.W, s), tblock_tc_last_error());
+    free_act(n1);
+    if (st.n.p) free_act(st.n);
+    free_act(st.x);
+    st.x = out;
+    st.n = out2;
+    st.n_of = next ? next : nullptr;
+    return true;
+  }
   void resblock(const ResBlockW& r, Stream& st, int kind /*2,1,3*/, const NormW* next, bool next_silu) {
     const bool pp = kind == 1;
+    if (kind == 1 && resblock1d_fused(r, st, next, next_silu)) return;
     const std::string k1 = r.key + ".conv1", k2 = r.key + ".conv2";
     Act n1 = take_norm(st, r.n1, true, pp);
     ConvOpt o1;
@@ -945,8 +977,11 @@ static void run_stages(Exec& ex, Exec::Stream& st, const std::vector<Stage>& sta
   }
 }
 
-// x_ext: fp32 [B,Cin,T,H,W]; h_out: fp32 [B,Cz,Tz,Hz,Wz]
-static void run_encoder(Exec& ex, const float* x_ext, int B, int T, int H, int W, float* h_out) {
+// x_ext: fp32 [B,Cin,T,H,W]; h_out: fp32 [B,Cz,Tz,Hz,Wz].  reg (optional): regularizer outputs; when conv_out runs on the
+// tcgen05 path it is applied in that kernel's epilogue (reg_done = true) and h_out is only written if want_h.
+static void run_encoder(Exec& ex, const float* x_ext, int B, int T, int H, int W, float* h_out, const TcRegFusion* reg = nullptr,
+                        bool want_h = true, bool* reg_done = nullptr) {
+  if (reg_done) *reg_done = false;
   vt_model* m = ex.m;
   const vt_model_desc& d = m->desc;
   const StackW& e = m->enc;
@@ -1016,7 +1051,9 @@ static void run_encoder(Exec& ex, const float* x_ext, int B, int T, int H, int W
   Act n = ex.take_norm(st, e.norm_out, true, false);
   ex.free_act(st.x);
   ConvOpt o; o.ext_out = h_out; o.cache_key = "encoder.conv_out";
+  o.reg = reg; o.reg_only = !want_h;
   ex.conv(e.conv_out, n, o);
+  if (reg_done) *reg_done = o.fused_reg;
   ex.free_act(n);
 }
 
@@ -1102,6 +1139,27 @@ static void decoded_shape(const vt_model* m, int Tz, int Hz, int Wz, int* T, int
   *T = t; *H = h; *W = w;
 }
 
+// the fused form of `regularize`: request for the conv_out epilogue (KL: the accumulator is cleared here)
+static int make_reg_fusion(vt_model* m, const float* noise, float* z, int32_t* indices, cudaStream_t s, TcRegFusion* rf) {
+  const vt_model_desc& d = m->desc;
+  *rf = TcRegFusion();
+  rf->zc = d.z_channels;
+  rf->z = z;
+  if (d.regularizer == VT_REG_KL) {
+    if (d.kl_sample && !noise) return fail(VT_ERR_INVALID, "KL regularizer with sample=True needs the noise tensor");
+    rf->mode = 1; rf->sample = d.kl_sample != 0; rf->noise = noise; rf->kl_acc = m->kl_scratch;
+    VT_CUDA(launch_kl_clear(m->kl_scratch, s));
+  } else {
+    rf->mode = 2; rf->indices = indices;
+    for (int i = 0; i < VT_MAX_FSQ && i < d.fsq_num_levels; ++i) rf->fsq_levels[i] = d.fsq_levels[i];
+  }
+  return VT_OK;
+}
+static int finish_reg_fusion(vt_model* m, int B, float* kl_loss, cudaStream_t s) {
+  if (m->desc.regularizer == VT_REG_KL) VT_CUDA(launch_kl_finish(m->kl_scratch, B, kl_loss, s));
+  return VT_OK;
+}
+
 static int regularize(vt_model* m, const float* h_pre, const float* noise, int B, int Tz, int Hz, int Wz, float* z,
                       int32_t* indices, float* kl_loss, cudaStream_t s) {
   const vt_model_desc& d = m->desc;
@@ -1167,6 +1225,14 @@ void vt_model_destroy(vt_model* m) {
   if (m->packed_planes) cudaFree(m->packed_planes);
   if (m->kl_scratch) cudaFree(m->kl_scratch);
   for (auto& kv : m->cache_pool) cudaFree(kv.second);
+  if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+  for (int i = 0; i < 2; ++i) {
+    if (m->ev_ready[i]) cudaEventDestroy(m->ev_ready[i]);
+    if (m->ev_free[i]) cudaEventDestroy(m->ev_free[i]);
+    if (m->ev_done[i]) cudaEventDestroy(m->ev_done[i]);
+    if (m->ev_drained[i]) cudaEventDestroy(m->ev_drained[i]);
+  }
+  if (m->ev_join) cudaEventDestroy(m->ev_join);
   delete m;
 }
 
@@ -1407,8 +1473,13 @@ int32_t vt_encode(vt_model* m, int32_t precision, const float* x, int32_t B, int
   const size_t hb = (size_t)B * (m->desc.double_z ? 2 : 1) * m->desc.z_channels * Tz * Hz * Wz * sizeof(float);
   float* hp = h_pre ? h_pre : (float*)ex.alloc(hb);
   if (!ex.ok()) return ex.rc;
-  run_encoder(ex, x, B, T, H, W, hp);
+  TcRegFusion rf;
+  rc = make_reg_fusion(m, noise, z, indices, s, &rf);
+  if (rc) return rc;
+  bool reg_done = false;
+  run_encoder(ex, x, B, T, H, W, hp, &rf, h_pre != nullptr, &reg_done);
   if (!ex.ok()) return ex.rc;
+  if (reg_done) return finish_reg_fusion(m, B, kl_loss, s);
   return regularize(m, hp, noise, B, Tz, Hz, Wz, z, indices, kl_loss, s);
 }
 
@@ -1492,8 +1563,13 @@ int32_t vt_encode_chunk(vt_chunk_state* cs, int32_t is_first, const float* x_chu
   ex.ck = cs;
   float* hp = (float*)ex.alloc((size_t)cs->B * (m->desc.double_z ? 2 : 1) * m->desc.z_channels * Tz * Hz * Wz * sizeof(float));
   if (!ex.ok()) return ex.rc;
-  run_encoder(ex, x_chunk, cs->B, Tc, cs->H, cs->W, hp);
+  TcRegFusion rf;
+  int rc = make_reg_fusion(m, noise, z, indices, s, &rf);
+  if (rc) return rc;
+  bool reg_done = false;
+  run_encoder(ex, x_chunk, cs->B, Tc, cs->H, cs->W, hp, &rf, false, &reg_done);
   if (!ex.ok()) return ex.rc;
+  if (reg_done) return finish_reg_fusion(m, cs->B, kl_loss, s);
   return regularize(m, hp, noise, cs->B, Tz, Hz, Wz, z, indices, kl_loss, s);
 }
 
@@ -1512,6 +1588,262 @@ int32_t vt_decode_chunk(vt_chunk_state* cs, int32_t is_first, const float* z_chu
   return ex.rc;
 }
 
+// ---- whole-video temporal tiling in the library (autoencoder_v1_1.py:218-228,244-264,302-331) ------------------------------
+// The chunk schedule, the per-layer caches and the chunk staging all live below the ABI: one call per video, no host
+// synchronisation, no per-chunk allocation.  Chunk i+1 is staged (host -> device, or a strided device copy) into the second
+// staging buffer on the library's copy stream while chunk i computes on the caller's stream (double buffering); decoded
+// chunks leave the same way.
+namespace {
+struct ChunkSpan { int s, e; };
+// build_chunk_start_end (autoencoder_v1_1.py:218-228): [0,1], then steps of `step`
+std::vector<ChunkSpan> chunk_schedule(int t, int step) {
+  std::vector<ChunkSpan> v;
+  v.push_back({0, 1});
+  int start = 1, end = 1;
+  while (start < t) {
+    end = std::min(t, end + step);
+    v.push_back({start, end});
+    start = end;
+  }
+  return v;
+}
+int ensure_copy_stream(vt_model* m) {
+  if (m->copy_stream) return VT_OK;
+  VT_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    VT_CUDA(cudaEventCreateWithFlags(&m->ev_ready[i], cudaEventDisableTiming));
+    VT_CUDA(cudaEventCreateWithFlags(&m->ev_free[i], cudaEventDisableTiming));
+    VT_CUDA(cudaEventCreateWithFlags(&m->ev_done[i], cudaEventDisableTiming));
+    VT_CUDA(cudaEventCreateWithFlags(&m->ev_drained[i], cudaEventDisableTiming));
+  }
+  VT_CUDA(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+  return VT_OK;
+}
+__global__ void mean_kernel(const float* v, int n, float* out) {
+  float s = 0.f;
+  for (int i = 0; i < n; ++i) s += v[i];
+  *out = s / (float)n;
+}
+// frames [t0, t0+n) of a [rows, T, frame] tensor <-> a dense [rows, n, frame] chunk (one strided 2-D copy)
+cudaError_t copy_frames_2d(void* dst, size_t dst_T, size_t dst_t0, const void* src, size_t src_T, size_t src_t0, size_t rows, size_t n,
+                           size_t frame_bytes, cudaMemcpyKind kind, cudaStream_t s) {
+  if (rows == 0 || n == 0) return cudaSuccess;
+  return cudaMemcpy2DAsync((char*)dst + dst_t0 * frame_bytes, dst_T * frame_bytes, (const char*)src + src_t0 * frame_bytes,
+                           src_T * frame_bytes, n * frame_bytes, rows, kind, s);
+}
+size_t up1k(size_t n) { return (n + 1023) / 1024 * 1024; }
+}  // namespace
+
+static int64_t video_workspace(const vt_model* m, int precision, int B, int T, int H, int W, int t_chunk, bool decoder, bool overlap) {
+  // staging + dense per-chunk outputs + the largest chunk workspace.  T/H/W: input video (encoder) or latent geometry (decoder).
+  vt_chunk_state tmp;
+  tmp.m = const_cast<vt_model*>(m); tmp.prec = precision; tmp.B = B; tmp.H = H; tmp.W = W;
+  tmp.is_decoder = decoder; tmp.use_overlap = overlap; tmp.persist = true;
+  const vt_model_desc& d = m->desc;
+  size_t fixed = 0, peak = 0;
+  std::vector<int> lens;
+  for (const ChunkSpan& c : chunk_schedule(T, t_chunk)) {
+    int n = c.e - c.s + ((decoder && overlap && c.e + 1 <= T) ? 1 : 0);
+    if (std::find(lens.begin(), lens.end(), n) == lens.end()) lens.push_back(n);
+  }
+  int max_len = *std::max_element(lens.begin(), lens.end());
+  if (!decoder) {
+    int Tz, Hz, Wz;
+    latent_shape(m, max_len, H, W, &Tz, &Hz, &Wz);
+    fixed += 2 * up1k((size_t)B * d.in_channels * max_len * H * W * 4);           // input staging x 2
+    fixed += 2 * up1k((size_t)B * d.z_channels * Tz * Hz * Wz * 4) + up1k((size_t)B * Tz * Hz * Wz * 4);   // noise, z, indices (dense chunk)
+    fixed += up1k(4096);                                                            // per-chunk kl values
+  } else {
+    int To, Ho, Wo;
+    decoded_shape(m, max_len, H, W, &To, &Ho, &Wo);
+    fixed += up1k((size_t)B * d.z_channels * max_len * H * W * 4);                 // dense latent chunk
+    fixed += 2 * up1k((size_t)B * d.out_ch * To * Ho * Wo * 4);                    // decoded chunk x 2
+  }
+  for (int n : lens) {
+    const int64_t w = vt_chunk_workspace_bytes(&tmp, n);
+    if (w < 0) return -1;
+    peak = std::max(peak, (size_t)w);
+  }
+  return (int64_t)(fixed + peak + 8192);
+}
+
+int64_t vt_encode_video_workspace_bytes(const vt_model* m, int32_t precision, int32_t B, int32_t T, int32_t H, int32_t W,
+                                        int32_t t_chunk_enc) {
+  if (!m || B <= 0 || T <= 0 || t_chunk_enc <= 0) { fail(VT_ERR_INVALID, "bad shape"); return -1; }
+  if (m->desc.version != 1) { fail(VT_ERR_INVALID, "temporal tiling exists only in the v1.1 model family"); return -1; }
+  if (check_precision(precision) || check_hw(m, H, W)) return -1;
+  return video_workspace(m, precision, B, T, H, W, t_chunk_enc, false, false);
+}
+int64_t vt_decode_video_workspace_bytes(const vt_model* m, int32_t precision, int32_t B, int32_t Tz, int32_t Hz, int32_t Wz,
+                                        int32_t t_chunk_dec, int32_t use_overlap) {
+  if (!m || B <= 0 || Tz <= 0 || t_chunk_dec <= 0) { fail(VT_ERR_INVALID, "bad shape"); return -1; }
+  if (m->desc.version != 1) { fail(VT_ERR_INVALID, "temporal tiling exists only in the v1.1 model family"); return -1; }
+  if (check_precision(precision)) return -1;
+  return video_workspace(m, precision, B, Tz, Hz, Wz, t_chunk_dec, true, use_overlap != 0);
+}
+// frames vt_decode_video writes: per chunk vt_decoded_frames(len) minus the dropped look-ahead tail (autoencoder_v1_1.py:327-328)
+int32_t vt_decode_video_frames(const vt_model* m, int32_t Tz, int32_t t_chunk_dec, int32_t use_overlap) {
+  if (!m || Tz <= 0 || t_chunk_dec <= 0) return -1;
+  const int tdf = m->desc.time_downsample_factor;
+  int total = 0;
+  for (const ChunkSpan& c : chunk_schedule(Tz, t_chunk_dec)) {
+    const bool look = use_overlap && c.e + 1 <= Tz;
+    total += vt_decoded_frames(m, c.e - c.s + (look ? 1 : 0)) - (look ? tdf : 0);
+  }
+  return total;
+}
+
+int32_t vt_encode_video(vt_model* m, int32_t precision, const float* x, int32_t x_on_host, int32_t B, int32_t C, int32_t T,
+                        int32_t H, int32_t W, int32_t t_chunk_enc, const float* noise, float* z, int32_t* indices,
+                        float* kl_loss, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!m || !x || !z || !workspace) return fail(VT_ERR_INVALID, "null argument");
+  if (m->desc.version != 1) return fail(VT_ERR_INVALID, "temporal tiling exists only in the v1.1 model family");
+  if (!m->finalized) return fail(VT_ERR_NOT_READY, "vt_model_finalize has not been called");
+  if (C != m->desc.in_channels) return fail(VT_ERR_INVALID, "input has %d channels, the model expects in_channels = %d", C, m->desc.in_channels);
+  if (B <= 0 || T <= 0 || t_chunk_enc <= 0) return fail(VT_ERR_INVALID, "bad shape");
+  int rc = check_precision(precision);
+  if (rc) return rc;
+  rc = check_hw(m, H, W);
+  if (rc) return rc;
+  VT_CUDA(cudaSetDevice(m->device));
+  rc = ensure_copy_stream(m);
+  if (rc) return rc;
+  const vt_model_desc& d = m->desc;
+  cudaStream_t s = (cudaStream_t)stream, cs = m->copy_stream;
+  const std::vector<ChunkSpan> chunks = chunk_schedule(T, t_chunk_enc);
+  int max_len = 0, TzTot = 0;
+  std::vector<int> tz_of(chunks.size());
+  int Hz = 0, Wz = 0;
+  for (size_t i = 0; i < chunks.size(); ++i) {
+    max_len = std::max(max_len, chunks[i].e - chunks[i].s);
+    latent_shape(m, chunks[i].e - chunks[i].s, H, W, &tz_of[i], &Hz, &Wz);
+    TzTot += tz_of[i];
+  }
+  if ((int)chunks.size() > 1024) return fail(VT_ERR_INVALID, "too many chunks");
+  int TzMax, hz_, wz_;
+  latent_shape(m, max_len, H, W, &TzMax, &hz_, &wz_);
+  // carve the workspace
+  char* w = (char*)workspace;
+  const size_t stage_b = up1k((size_t)B * C * max_len * H * W * 4), lat_b = up1k((size_t)B * d.z_channels * TzMax * Hz * Wz * 4);
+  float* stage[2] = {(float*)w, (float*)(w + stage_b)};
+  w += 2 * stage_b;
+  float* noise_c = (float*)w; w += lat_b;
+  float* z_c = (float*)w; w += lat_b;
+  int32_t* idx_c = (int32_t*)w; w += up1k((size_t)B * TzMax * Hz * Wz * 4);
+  float* kl_c = (float*)w; w += up1k(4096);
+  const int64_t ws_left = workspace_bytes - (w - (char*)workspace);
+  if (ws_left <= 0) return fail(VT_ERR_WORKSPACE, "workspace too small for the chunk staging buffers");
+  const size_t fr_in = (size_t)H * W * 4, fr_z = (size_t)Hz * Wz * 4;
+  const cudaMemcpyKind in_kind = x_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  // the copy stream must not start staging before the caller's stream has produced x / released the workspace
+  VT_CUDA(cudaEventRecord(m->ev_join, s));
+  VT_CUDA(cudaStreamWaitEvent(cs, m->ev_join, 0));
+  vt_chunk_state* st = nullptr;
+  rc = vt_chunk_state_create(m, precision, B, H, W, 0, 0, &st);
+  if (rc) return rc;
+  auto stage_chunk = [&](size_t i) -> cudaError_t {
+    const int n = chunks[i].e - chunks[i].s;
+    cudaError_t e = copy_frames_2d(stage[i & 1], n, 0, x, T, chunks[i].s, (size_t)B * C, n, fr_in, in_kind, cs);
+    if (e == cudaSuccess) e = cudaEventRecord(m->ev_ready[i & 1], cs);
+    return e;
+  };
+  cudaError_t ce = stage_chunk(0);
+  int tz0 = 0;
+  for (size_t i = 0; i < chunks.size() && ce == cudaSuccess && rc == VT_OK; ++i) {
+    const int cur = (int)(i & 1), n = chunks[i].e - chunks[i].s, tzc = tz_of[i];
+    if (i + 1 < chunks.size()) {
+      if (i >= 1) ce = cudaStreamWaitEvent(cs, m->ev_free[cur ^ 1], 0);   // chunk i-1 (which read that buffer) has finished
+      if (ce == cudaSuccess) ce = stage_chunk(i + 1);
+    }
+    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(s, m->ev_ready[cur], 0);
+    if (ce == cudaSuccess && noise)
+      ce = copy_frames_2d(noise_c, tzc, 0, noise, TzTot, tz0, (size_t)B * d.z_channels, tzc, fr_z, cudaMemcpyDeviceToDevice, s);
+    if (ce != cudaSuccess) break;
+    rc = vt_encode_chunk(st, i == 0, stage[cur], C, n, noise ? noise_c : nullptr, z_c, indices ? idx_c : nullptr,
+                         d.regularizer == VT_REG_KL ? kl_c + i : nullptr, w, ws_left, stream);
+    if (rc) break;
+    ce = cudaEventRecord(m->ev_free[cur], s);
+    if (ce == cudaSuccess) ce = copy_frames_2d(z, TzTot, tz0, z_c, tzc, 0, (size_t)B * d.z_channels, tzc, fr_z, cudaMemcpyDeviceToDevice, s);
+    if (ce == cudaSuccess && indices)
+      ce = copy_frames_2d(indices, TzTot, tz0, idx_c, tzc, 0, (size_t)B, tzc, fr_z, cudaMemcpyDeviceToDevice, s);
+    tz0 += tzc;
+  }
+  if (ce == cudaSuccess && rc == VT_OK && d.regularizer == VT_REG_KL && kl_loss) {
+    mean_kernel<<<1, 1, 0, s>>>(kl_c, (int)chunks.size(), kl_loss);   // torch.mean(torch.stack(kls)), autoencoder_v1_1.py:261-264
+    count_launch();
+    ce = cudaGetLastError();
+  }
+  // the caller's stream owns the workspace again only after the copy stream has drained
+  cudaEventRecord(m->ev_join, cs);
+  cudaStreamWaitEvent(s, m->ev_join, 0);
+  vt_chunk_state_destroy(st);
+  if (rc) return rc;
+  if (ce != cudaSuccess) return fail(VT_ERR_CUDA, "vt_encode_video: %s", cudaGetErrorString(ce));
+  return VT_OK;
+}
+
+int32_t vt_decode_video(vt_model* m, int32_t precision, const float* z, int32_t B, int32_t Cz, int32_t Tz, int32_t Hz, int32_t Wz,
+                        int32_t t_chunk_dec, int32_t use_overlap, float* x_out, int32_t out_on_host, void* workspace,
+                        int64_t workspace_bytes, void* stream) {
+  if (!m || !z || !x_out || !workspace) return fail(VT_ERR_INVALID, "null argument");
+  if (m->desc.version != 1) return fail(VT_ERR_INVALID, "temporal tiling exists only in the v1.1 model family");
+  if (!m->finalized) return fail(VT_ERR_NOT_READY, "vt_model_finalize has not been called");
+  if (Cz != m->desc.z_channels) return fail(VT_ERR_INVALID, "latent has %d channels, the model expects z_channels = %d", Cz, m->desc.z_channels);
+  if (B <= 0 || Tz <= 0 || t_chunk_dec <= 0) return fail(VT_ERR_INVALID, "bad shape");
+  int rc = check_precision(precision);
+  if (rc) return rc;
+  const vt_model_desc& d = m->desc;
+  const int tdf = d.time_downsample_factor;
+  if (use_overlap && tdf != 2 && tdf != 4 && tdf != 8) return fail(VT_ERR_INVALID, "use_overlap supports 2x, 4x or 8x temporal downsampling only");
+  VT_CUDA(cudaSetDevice(m->device));
+  rc = ensure_copy_stream(m);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream, cs = m->copy_stream;
+  const std::vector<ChunkSpan> chunks = chunk_schedule(Tz, t_chunk_dec);
+  int max_len = 0;
+  for (const ChunkSpan& c : chunks) max_len = std::max(max_len, c.e - c.s + ((use_overlap && c.e + 1 <= Tz) ? 1 : 0));
+  int ToMax, Ho, Wo;
+  decoded_shape(m, max_len, Hz, Wz, &ToMax, &Ho, &Wo);
+  const int T_out = vt_decode_video_frames(m, Tz, t_chunk_dec, use_overlap);
+  char* w = (char*)workspace;
+  float* z_c = (float*)w; w += up1k((size_t)B * Cz * max_len * Hz * Wz * 4);
+  const size_t out_b = up1k((size_t)B * d.out_ch * ToMax * Ho * Wo * 4);
+  float* out_c[2] = {(float*)w, (float*)(w + out_b)};
+  w += 2 * out_b;
+  const int64_t ws_left = workspace_bytes - (w - (char*)workspace);
+  if (ws_left <= 0) return fail(VT_ERR_WORKSPACE, "workspace too small for the chunk staging buffers");
+  const size_t fr_z = (size_t)Hz * Wz * 4, fr_o = (size_t)Ho * Wo * 4;
+  const cudaMemcpyKind out_kind = out_on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  vt_chunk_state* st = nullptr;
+  rc = vt_chunk_state_create(m, precision, B, Hz, Wz, 1, use_overlap, &st);
+  if (rc) return rc;
+  cudaError_t ce = cudaSuccess;
+  int t0 = 0;
+  for (size_t i = 0; i < chunks.size() && ce == cudaSuccess && rc == VT_OK; ++i) {
+    const int cur = (int)(i & 1);
+    const bool look = use_overlap && chunks[i].e + 1 <= Tz;
+    const int n = chunks[i].e - chunks[i].s + (look ? 1 : 0);
+    const int To = vt_decoded_frames(m, n), keep = To - (look ? tdf : 0);
+    ce = copy_frames_2d(z_c, n, 0, z, Tz, chunks[i].s, (size_t)B * Cz, n, fr_z, cudaMemcpyDeviceToDevice, s);
+    if (ce == cudaSuccess && i >= 2) ce = cudaStreamWaitEvent(s, m->ev_drained[cur], 0);   // chunk i-2 has left this buffer
+    if (ce != cudaSuccess) break;
+    rc = vt_decode_chunk(st, i == 0, z_c, Cz, n, out_c[cur], w, ws_left, stream);
+    if (rc) break;
+    // the decoded chunk leaves on the copy stream (device -> host, or into the caller's device tensor) while the next one computes
+    ce = cudaEventRecord(m->ev_done[cur], s);
+    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(cs, m->ev_done[cur], 0);
+    if (ce == cudaSuccess) ce = copy_frames_2d(x_out, T_out, t0, out_c[cur], To, 0, (size_t)B * d.out_ch, keep, fr_o, out_kind, cs);
+    if (ce == cudaSuccess) ce = cudaEventRecord(m->ev_drained[cur], cs);
+    t0 += keep;
+  }
+  cudaEventRecord(m->ev_join, cs);
+  cudaStreamWaitEvent(s, m->ev_join, 0);
+  vt_chunk_state_destroy(st);
+  if (rc) return rc;
+  if (ce != cudaSuccess) return fail(VT_ERR_CUDA, "vt_decode_video: %s", cudaGetErrorString(ce));
+  return VT_OK;
+}
+
 // ---- single operators (parity tests) -----------------------------------------------------------------
 static inline DType act_type(int precision) {
   return precision == VT_PREC_FMA32 ? DT_F32 : (precision == VT_PREC_EXACT_TC ? DT_SPLIT : DT_BF16);
@@ -1521,8 +1853,8 @@ static inline DType act_type(int precision) {
 // precision, with temporary weight repacks.
 static int op_conv_impl(int precision, int force_simt, const vt_conv_desc* d, const vt_conv_ex* e, const void* x,
                         const void* cache, const float* w, const float* bias, const void* res, const float* gamma,
-                        const float* beta, void* out, void* out2, cudaStream_t s) {
-  if (!d || !x || !w || !out) return fail(VT_ERR_INVALID, "null argument");
+                        const float* beta, void* out, void* out2, cudaStream_t s, const TcRegFusion* reg = nullptr) {
+  if (!d || !x || !w || (!out && !reg)) return fail(VT_ERR_INVALID, "null argument");
   if (precision != VT_PREC_FMA32 && precision != VT_PREC_BF16 && precision != VT_PREC_EXACT_TC)
     return fail(VT_ERR_INVALID, "operator precision must be FMA32, BF16 or EXACT_TC");
   const DType ta = act_type(precision);
@@ -1586,7 +1918,7 @@ static int op_conv_impl(int precision, int force_simt, const vt_conv_desc* d, co
     const int Co_pad = (d->Co + 31) / 32 * 32;
     VT_CUDA(cudaMalloc(&wnk, (size_t)K * Co_pad * sizeof(bf16) * cw));
     VT_CUDA(launch_pack_w_nk_bf16(w, wnk, d->Co, Co_pad, d->Ci, taps, K, s, ta == DT_SPLIT));
-    er = launch_conv_tc(p, (const bf16*)x, wnk, K, out, tout, s, 1, 0, lf.mode ? &lf : nullptr);
+    er = launch_conv_tc(p, (const bf16*)x, wnk, K, out, tout, s, 1, 0, lf.mode ? &lf : nullptr, reg);
   } else {
     VT_CUDA(cudaMalloc(&wkn, (size_t)K * d->Co * sizeof(float)));
     VT_CUDA(launch_pack_w_kn(w, wkn, d->Co, d->Ci, taps, s));
@@ -1609,6 +1941,42 @@ int32_t vt_op_conv_ex(int32_t precision, const vt_conv_ex* e, const void* x, con
                       void* stream) {
   if (!e) return fail(VT_ERR_INVALID, "null argument");
   return op_conv_impl(precision, e->force_simt, &e->d, e, x, cache, w, bias, res, gamma, beta, out, out2, (cudaStream_t)stream);
+}
+
+// Encoder conv_out with the regularizer in its epilogue, as the model path runs it: x channels-last activation,
+// h_out (optional) fp32 [B,Co,T,H,W]; KL: Co = 2*zc, noise/z fp32 [B,zc,T,H,W], kl_loss = 0.5 * sum / B;
+// FSQ: Co = zc = number of levels, z = codes, indices int32 [B,T,H,W].
+int32_t vt_op_conv_regularize(int32_t precision, const vt_conv_desc* d, const void* x, const float* w, const float* bias,
+                              int32_t reg_mode, int32_t zc, const int32_t* fsq_levels, const float* noise, float* h_out,
+                              float* z, int32_t* indices, float* kl_loss, void* stream) {
+  if (!d || !z) return fail(VT_ERR_INVALID, "null argument");
+  if (precision != VT_PREC_BF16 && precision != VT_PREC_EXACT_TC) return fail(VT_ERR_INVALID, "the regularizer epilogue exists on the tcgen05 path only");
+  cudaStream_t s = (cudaStream_t)stream;
+  vt_conv_ex e;
+  memset(&e, 0, sizeof(e));
+  e.d = *d;
+  e.out_f32_ncdhw = 1;
+  TcRegFusion rf;
+  rf.mode = reg_mode; rf.zc = zc; rf.z = z; rf.noise = noise; rf.indices = indices; rf.sample = noise ? 1 : 0;
+  double* acc = nullptr;
+  if (reg_mode == 1) {
+    VT_CUDA(cudaMalloc(&acc, sizeof(double)));
+    VT_CUDA(launch_kl_clear(acc, s));
+    rf.kl_acc = acc;
+  } else if (reg_mode == 2) {
+    if (!fsq_levels) return fail(VT_ERR_INVALID, "FSQ needs the level list");
+    for (int i = 0; i < zc && i < VT_MAX_FSQ; ++i) rf.fsq_levels[i] = fsq_levels[i];
+  } else {
+    return fail(VT_ERR_INVALID, "reg_mode must be 1 (KL) or 2 (FSQ)");
+  }
+  int rc = op_conv_impl(precision, 0, d, &e, x, nullptr, w, bias, nullptr, nullptr, nullptr, h_out, nullptr, s, &rf);
+  if (rc == VT_OK && reg_mode == 1 && kl_loss) {
+    cudaError_t er = launch_kl_finish(acc, d->B, kl_loss, s);
+    if (er == cudaSuccess) er = cudaStreamSynchronize(s);
+    if (er != cudaSuccess) rc = fail(VT_ERR_CUDA, "kl finish: %s", cudaGetErrorString(er));
+  }
+  if (acc) cudaFree(acc);
+  return rc;
 }
 
 // Encoder stem (conv_in from the caller's fp32 [B,Ci,T,H,W] tensor) on the conv_stem kernel.
@@ -1743,6 +2111,26 @@ int32_t vt_op_upsample_conv(int32_t precision, int32_t kind, const void* x, cons
   return VT_OK;
 }
 
+// Fused temporal residual block (BF16, C = 128) exactly as the model path launches it.
+int32_t vt_op_tblock(const void* n1, const void* x, const float* w1, const float* b1, const float* g2, const float* be2,
+                     const float* w2, const float* b2, const float* g3, const float* be3, int32_t out_silu, void* out,
+                     void* out2, int32_t B, int32_t T, int32_t H, int32_t W, int32_t C, void* stream) {
+  if (!n1 || !x || !w1 || !b1 || !g2 || !be2 || !w2 || !b2 || !out) return fail(VT_ERR_INVALID, "null argument");
+  if (!tblock_tc_supported(B, T, H, W, C)) return fail(VT_ERR_INVALID, "fused temporal block does not take this geometry: %s", tblock_tc_last_error());
+  cudaStream_t s = (cudaStream_t)stream;
+  bf16* wp = nullptr;
+  const size_t per = (size_t)C * 3 * C;
+  VT_CUDA(cudaMalloc(&wp, 2 * per * sizeof(bf16)));
+  VT_CUDA(launch_pack_w_nk_bf16(w1, wp, C, C, C, 3, 3 * C, s));
+  VT_CUDA(launch_pack_w_nk_bf16(w2, wp + per, C, C, C, 3, 3 * C, s));
+  cudaError_t er = launch_tblock_tc((const bf16*)n1, (const bf16*)x, wp, b1, g2, be2, wp + per, b2, (bf16*)out, (bf16*)out2,
+                                    out2 ? g3 : nullptr, out2 ? be3 : nullptr, out_silu != 0, B, T, H, W, s);
+  cudaError_t e2 = cudaStreamSynchronize(s);
+  cudaFree(wp);
+  if (er != cudaSuccess || e2 != cudaSuccess) return fail(VT_ERR_CUDA, "tblock: %s %s", cudaGetErrorString(er != cudaSuccess ? er : e2), tblock_tc_last_error());
+  return VT_OK;
+}
+
 int32_t vt_op_layernorm(int32_t precision, const void* x, const float* gamma, const float* beta, void* y, int64_t rows,
                         int32_t C, int32_t apply_silu, void* stream) {
   VT_CUDA(launch_layernorm(act_type(precision), x, gamma, beta, y, rows, C, apply_silu != 0, precision != VT_PREC_BF16, (cudaStream_t)stream));
@@ -1776,6 +2164,21 @@ int32_t vt_op_attention(int32_t precision, const void* q, const void* k, const v
   if (ex.ok()) ex.cuda(cudaMemcpyAsync(o, ao.p, (size_t)frames * tokens * C * dtype_size(ex.ta), cudaMemcpyDeviceToDevice, ex.s), "copy out");
   return ex.rc;
 }
+// ---- video I/O adjacent steps ---------------------------------------------------------------------------
+int32_t vt_video_u8_to_clip(const uint8_t* frames, float* clip, int32_t T, int32_t Hs, int32_t Ws, int32_t C, int32_t h0,
+                            int32_t w0, int32_t H, int32_t W, void* stream) {
+  if (!frames || !clip) return fail(VT_ERR_INVALID, "null argument");
+  if (T <= 0 || C <= 0 || H <= 0 || W <= 0 || h0 < 0 || w0 < 0 || h0 + H > Hs || w0 + W > Ws) return fail(VT_ERR_INVALID, "crop window outside the frame");
+  VT_CUDA(launch_u8_frames_to_clip(frames, clip, T, Hs, Ws, C, h0, w0, H, W, (cudaStream_t)stream));
+  return VT_OK;
+}
+int32_t vt_clip_to_video_u8(const float* clip, uint8_t* frames, int32_t C, int32_t T, int32_t H, int32_t W, void* stream) {
+  if (!frames || !clip) return fail(VT_ERR_INVALID, "null argument");
+  if (T <= 0 || C <= 0 || H <= 0 || W <= 0) return fail(VT_ERR_INVALID, "bad shape");
+  VT_CUDA(launch_clip_to_u8_frames(clip, frames, C, T, H, W, (cudaStream_t)stream));
+  return VT_OK;
+}
+
 int32_t vt_op_fsq(const float* h, int32_t d, const int32_t* levels, int64_t P, int32_t B, float* codes, int32_t* indices,
                   void* stream) {
   VT_CUDA(launch_fsq(h, d, levels, P, B, codes, indices, (cudaStream_t)stream));

@@ -111,4 +111,12 @@ struct vt_model {
   // device buffers of finished chunk states, reused by the next video (cudaMalloc/cudaFree per cache per video would
   // dominate the tiled path: ~100 caches per direction)
   std::multimap<size_t, void*> cache_pool;
+  // whole-video tiling (vt_encode_video / vt_decode_video): the library's own copy stream and the events that order chunk
+  // staging (stream `copy`) against chunk compute (the caller's stream)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_ready[2] = {nullptr, nullptr};   // staging buffer i holds its chunk           (copy -> compute)
+  cudaEvent_t ev_free[2] = {nullptr, nullptr};    // the chunk that read staging buffer i is done (compute -> copy)
+  cudaEvent_t ev_done[2] = {nullptr, nullptr};    // output buffer i holds its decoded chunk      (compute -> copy)
+  cudaEvent_t ev_drained[2] = {nullptr, nullptr}; // output buffer i has been copied out          (copy -> compute)
+  cudaEvent_t ev_join = nullptr;
 };

@@ -714,37 +714,41 @@ class AutoencodingEngineV11(_EngineBase):
         return z
 
     def tile_encode(self, x: Any) -> Any:
-        """autoencoder_v1_1.py:244-264: first frame alone, then chunks of t_chunk_enc, causal caches carried over."""
+        """autoencoder_v1_1.py:244-264: first frame alone, then chunks of t_chunk_enc, causal caches carried over.  One
+        native call per video (vt_encode_video): the chunk loop, the caches and the double-buffered chunk staging live in
+        the library.  `x` may be a CUDA tensor or a (pinned) host tensor -- then the chunks are staged host -> device on the
+        library's copy stream while the previous chunk computes."""
         rt = self._rt
         nat = rt.sync()
-        x = rt._as_input(x)
+        if x.dim() != 5:
+            raise ValueError("expected a [B,C,T,H,W] tensor")
+        on_host = not x.is_cuda
+        x = x.detach().to(torch.float32).contiguous()
+        dev = nat.device
         B, Cin, T, H, W = x.shape
         if Cin != self.spec.in_channels:
             raise ValueError(f"input has {Cin} channels, the model expects in_channels = {self.spec.in_channels}")
         prec = rt.precision()
         lib = nat.lib
-        st = ChunkState(nat, prec, B, H, W, is_decoder=False, use_overlap=False)
-        zs, idxs, kls = [], [], []
-        try:
-            for i, (s, e) in enumerate(self.build_chunk_start_end(T)):
-                chunk = x[:, :, s:e].contiguous()
-                Tc = e - s
-                Tz, Hz, Wz = nat.latent_shape(Tc, H, W)
-                noise = rt.draw_noise((B, self.spec.z_channels, Tz, Hz, Wz), x.device)
-                z = torch.empty((B, self.spec.z_channels, Tz, Hz, Wz), dtype=torch.float32, device=x.device)
-                idx = torch.empty((B, Tz, Hz, Wz), dtype=torch.int32, device=x.device) if self.spec.regularizer == "fsq" else None
-                kl = torch.empty((), dtype=torch.float32, device=x.device) if self.spec.regularizer == "kl" else None
-                ws = st.workspace(Tc)
-                N.check(lib.vt_encode_chunk(st.handle, int(i == 0), _ptr(chunk), Cin, Tc, _ptr(noise), _ptr(z), _ptr(idx), _ptr(kl),
-                                            _ptr(ws), ws.numel(), _stream_ptr(x.device)))
-                zs.append(z), idxs.append(idx), kls.append(kl)
-        finally:
-            torch.cuda.current_stream(x.device).synchronize()
-            st.close()
-        z = torch.cat(zs, dim=2)
+        chunks = self.build_chunk_start_end(T)
+        shapes = [nat.latent_shape(e - s, H, W) for s, e in chunks]
+        Hz, Wz = shapes[0][1], shapes[0][2]
+        Tz = sum(sh[0] for sh in shapes)
+        noise = None
+        if self.spec.regularizer == "kl" and self.spec.kl_sample:
+            # one torch.randn per chunk, in chunk order, exactly the draws the reference makes (distributions.py:17)
+            noise = torch.cat([torch.randn((B, self.spec.z_channels, sh[0], Hz, Wz)) for sh in shapes], dim=2).to(dev)
+        z = torch.empty((B, self.spec.z_channels, Tz, Hz, Wz), dtype=torch.float32, device=dev)
+        idx = torch.empty((B, Tz, Hz, Wz), dtype=torch.int32, device=dev) if self.spec.regularizer == "fsq" else None
+        kl = torch.empty((), dtype=torch.float32, device=dev) if self.spec.regularizer == "kl" else None
+        ws = nat._workspace(int(lib.vt_encode_video_workspace_bytes(nat.handle, prec, B, T, H, W, int(self.t_chunk_enc))))
+        N.check(lib.vt_encode_video(nat.handle, prec, _ptr(x), int(on_host), B, Cin, T, H, W, int(self.t_chunk_enc), _ptr(noise), _ptr(z),
+                                    _ptr(idx), _ptr(kl), _ptr(ws), ws.numel(), _stream_ptr(dev)))
+        if on_host:
+            torch.cuda.current_stream(dev).synchronize()   # the host tensor must outlive the staged copies
         if self.spec.regularizer == "kl":
-            return z, {"kl_loss": torch.mean(torch.stack(kls))}
-        return z, {"aux_loss": torch.zeros((), device=x.device), "indices": torch.cat(idxs, dim=1)}
+            return z, {"kl_loss": kl}
+        return z, {"aux_loss": torch.zeros((), device=dev), "indices": idx}
 
     def tile_indices_to_latent(self, token_indices: torch.Tensor) -> torch.Tensor:
         return self.indices_to_latent(token_indices)
@@ -756,8 +760,10 @@ class AutoencodingEngineV11(_EngineBase):
             return self.tile_decode(z).to(self._rt.out_dtype())
         return self._rt.decode_raw(z, False).to(self._rt.out_dtype())
 
-    def tile_decode(self, z: Any) -> torch.Tensor:
-        """autoencoder_v1_1.py:302-331: one look-ahead latent frame per chunk when use_overlap, tail frames dropped."""
+    def tile_decode(self, z: Any, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """autoencoder_v1_1.py:302-331: one look-ahead latent frame per chunk when use_overlap, tail frames dropped.  One
+        native call per video (vt_decode_video).  `out` (optional): a pre-allocated fp32 [B,C,T',H,W] tensor, CUDA or pinned
+        host memory -- decoded chunks are then copied out on the library's copy stream while the next chunk computes."""
         rt = self._rt
         nat = rt.sync()
         if not z.is_cuda:
@@ -771,23 +777,20 @@ class AutoencodingEngineV11(_EngineBase):
             assert tdf in [2, 4, 8], "Only support 2x, 4x or 8x temporal downsampling now."
         prec = rt.precision()
         f = nat.spatial_factor()
-        st = ChunkState(nat, prec, B, Hz, Wz, is_decoder=True, use_overlap=bool(self.use_overlap))
-        outs = []
-        try:
-            for i, (s, e) in enumerate(self.build_chunk_start_end(nf, decoder_mode=True)):
-                look = bool(self.use_overlap) and e + 1 <= nf
-                zc = (z[:, :, s:e + 1] if look else z[:, :, s:e]).contiguous()
-                Tzc = zc.shape[2]
-                To = nat.decoded_frames(Tzc)
-                out = torch.empty((B, self.spec.out_ch, To, Hz * f, Wz * f), dtype=torch.float32, device=z.device)
-                ws = st.workspace(Tzc)
-                N.check(nat.lib.vt_decode_chunk(st.handle, int(i == 0), _ptr(zc), Cz, Tzc, _ptr(out), _ptr(ws), ws.numel(),
-                                                _stream_ptr(z.device)))
-                outs.append(out[:, :, :-tdf] if look else out)
-        finally:
+        lib = nat.lib
+        tcd, ov = int(self.t_chunk_dec), int(bool(self.use_overlap))
+        T_out = int(lib.vt_decode_video_frames(nat.handle, nf, tcd, ov))
+        shape = (B, self.spec.out_ch, T_out, Hz * f, Wz * f)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float32, device=z.device)
+        elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous fp32 tensor of shape {shape}")
+        ws = nat._workspace(int(lib.vt_decode_video_workspace_bytes(nat.handle, prec, B, nf, Hz, Wz, tcd, ov)))
+        N.check(lib.vt_decode_video(nat.handle, prec, _ptr(z), B, Cz, nf, Hz, Wz, tcd, ov, _ptr(out), int(not out.is_cuda), _ptr(ws),
+                                    ws.numel(), _stream_ptr(z.device)))
+        if not out.is_cuda:
             torch.cuda.current_stream(z.device).synchronize()
-            st.close()
-        return torch.cat(outs, dim=2)
+        return out
 
     def forward(self, x: Any):
         z, reg_log = self.encode(x, return_reg_log=True)
