@@ -11,7 +11,7 @@ N > 1).  `value` is timed with CUDA events with the inputs already resident in H
 
 configs (BASELINE.json `configs`):
   kl488    [1] vidtok_kl_causal_488_4chn, 8 clips 17x256x256 per GPU, bf16 (default: the metric BASELINE.json is quoted on)
-  fsq488   [2] vidtok_fsq_causal_488_32768, 8 clips 17x256x256 per GPU, "mixed" = encoder bf16x3 (bit-exact codes), decoder bf16
+  fsq488   [2] vidtok_fsq_causal_488_32768, 8 clips 17x256x256 per GPU, "mixed" = encoder fp16x3 split operands (bit-exact codes), decoder bf16
   v11long  [3] vidtok_kl_causal_488_16chn v1.1, one 129x256x256 video per GPU, tiled t_chunk_enc=16 with overlap, bf16
   kl41616  [4] vidtok_kl_causal_41616_4chn, 4 clips 17x512x512 per GPU (32 clips over 8 GPUs), bf16
 """
@@ -47,7 +47,7 @@ CONFIGS = {
                     version="v1_0", reg="kl", z=4, ch_mult=(1, 2, 4, 4, 4), T=17, H=512, W=512, batch=4, flops=85.627e12,
                     precision="bf16", tiling=None),
 }
-DTYPE_OF = {"bf16": "bf16", "exact": "bf16x3 (hi|lo split bf16 operands, fp32-class results)", "mixed": "encoder bf16x3, decoder bf16",
+DTYPE_OF = {"bf16": "bf16", "exact": "fp16x3 (hi|lo split fp16 operands, 3 MMAs per K step, fp32-class results)", "mixed": "encoder fp16x3, decoder bf16",
             "fma": "f32"}
 
 
@@ -404,7 +404,7 @@ def run_b200_arm(args, c):
                     "frac": ach / peak, "traffic": traffic, "launches_per_step": d["launches"],
                     "avg_launch_ms": d["ms"] / max(d["launches"], 1), "share_of_step": d["ms"] / tot_ms,
                     "algorithmic_flops_per_step": d["flops"], "peak_source": peaks["source"],
-                    "note": ("achieved = algorithmic FLOPs of the kernel's launches / their summed durations; conv_tc3 (bf16x3) executes "
+                    "note": ("achieved = algorithmic FLOPs of the kernel's launches / their summed durations; conv_tc3 (split operands) executes "
                              "3 tensor-core MACs per algorithmic MAC, so its ceiling against the bf16 peak is 1/3"),
                     "whole_path": {"achieved": c["flops"] * B * args.steps / (ms / 1e3) / 1e12, "unit": "TFLOP/s per GPU (algorithmic)",
                                    "frac": c["flops"] * B * args.steps / (ms / 1e3) / 1e12 / peaks["tflops"]},

@@ -40,8 +40,9 @@ typedef enum {
 
 /* Precision modes.
  * EXACT_TC (the parity mode): fp32-class results on the tcgen05 tensor cores.  Activations and weights are kept as
- *   two bf16 planes (hi = bf16(v), lo = bf16(v - hi)); every K step issues hi*hi + lo*hi + hi*lo into the fp32 TMEM
- *   accumulator ("bf16x3"), LayerNorm / SiLU / regularizers in fp32.  Gate: 1e-3 max-abs, FSQ codes equal.
+ *   two fp16 planes (hi = fp16(v), lo = fp16(v - hi): 11 + 11 mantissa bits); every K step issues hi*hi + lo*hi + hi*lo
+ *   into the fp32 TMEM accumulator ("fp16x3": products good to ~2^-21), LayerNorm / SiLU / regularizers in fp32.
+ *   Gate: 1e-3 max-abs, FSQ codes equal.
  * BF16 (the throughput mode): bf16 activations / weights, fp32 accumulation.  Gate: PSNR within 0.01 dB.
  * MIXED: encoder in EXACT_TC (bit-exact FSQ codes / 1e-3 latents), decoder in BF16.
  * FMA32 (VT_PREC_EXACT, kept for cross-checks): fp32 activations on fp32 FMA kernels, no tensor cores. */

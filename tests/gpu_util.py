@@ -15,9 +15,10 @@ def stream():
 
 
 def split_rows(x):
-    """fp32 [..., C] -> the EXACT_TC activation format [..., hi(C) | lo(C)] bf16 (value = hi + lo)."""
-    hi = x.to(torch.bfloat16)
-    lo = (x - hi.float()).to(torch.bfloat16)
+    """fp32 [..., C] -> the EXACT_TC activation format [..., hi(C) | lo(C)]: two fp16 planes, value = hi + lo
+    (11 + 11 mantissa bits; saturating at the fp16 range)."""
+    hi = x.clamp(-65504.0, 65504.0).to(torch.float16)
+    lo = (x - hi.float()).clamp(-65504.0, 65504.0).to(torch.float16)
     return torch.cat([hi, lo], dim=-1).contiguous()
 
 
@@ -27,7 +28,7 @@ def join_rows(y):
 
 
 def act_dtype(precision):
-    return torch.float32 if precision == N.PREC_FMA32 else torch.bfloat16
+    return {N.PREC_FMA32: torch.float32, N.PREC_BF16: torch.bfloat16, N.PREC_EXACT_TC: torch.float16}[precision]
 
 
 def to_act(x_cl, precision):

@@ -2,7 +2,7 @@
 (vidtok.models.autoencoder[_v1_1].AutoencodingEngine resolved from the YAML target strings) against the golden
 fixtures produced by the unmodified reference, and against the oracle.
 
-Gates (BASELINE.json north_star): "exact" mode -- bf16x3 split operands on the tcgen05 tensor cores -- max-abs <= 1e-3 on
+Gates (BASELINE.json north_star): "exact" mode -- fp16 hi|lo split operands (3 MMAs per K step) on the tcgen05 tensor cores -- max-abs <= 1e-3 on
 latents and reconstructions, FSQ indices equal (0 mismatches outside a 1e-4 guard band around rounding ties, raw count
 reported); the same gates for the fp32-FMA cross-check mode ("fma"); BF16 mode PSNR within 0.01 dB."""
 import numpy as np
@@ -190,7 +190,7 @@ def test_autocast_selects_bf16_and_default_is_exact():
 
 @pytest.mark.parametrize("case", ["mid_fsq_v10", "cfg1_fsq_488_32768", "mid_kl_v10"])
 def test_mixed_mode_exact_encoder_bf16_decoder(case):
-    """precision="mixed": encoder on bf16x3 (codes / latents at the exact gate), decoder on bf16 (PSNR gate)."""
+    """precision="mixed": encoder on fp16x3 (codes / latents at the exact gate), decoder on bf16 (PSNR gate)."""
     d, meta = load_golden(case)
     sd, x = synth_weights(meta, d), synth_inputs(meta, d)
     model = build_model(meta, sd)

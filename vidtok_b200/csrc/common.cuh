@@ -1,6 +1,7 @@
 // Shared device/host definitions for the vidtok_b200 kernels.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -62,6 +63,28 @@ __device__ __forceinline__ float silu_f(float x) {
 }
 // accurate variant for the EXACT mode (expf, not the fast intrinsic)
 __device__ __forceinline__ float silu_exact(float x) { return x * (1.0f / (1.0f + expf(-x))); }
+
+// ---- DT_SPLIT planes: v = hi + lo with hi = fp16(v), lo = fp16(v - hi): 11 + 11 mantissa bits, so a product of two split
+// numbers that drops lo*lo is good to ~2^-21 (fp32-class).  (bf16 planes would give 8 + 8 bits: products good to 2^-17 only,
+// measured 3e-4 on the latents -- too coarse for bit-exact FSQ codes.)  The planes are stored through bf16-typed pointers
+// (16-bit elements; TMA and the data-movement kernels do not care), hence the reinterpretations.  Values beyond the fp16
+// range saturate instead of becoming inf.
+__device__ __forceinline__ float split_sat(float v) { return fminf(fmaxf(v, -65504.0f), 65504.0f); }
+__device__ __forceinline__ void split_store(bf16* hi_p, bf16* lo_p, float v) {
+  const __half h = __float2half_rn(split_sat(v));
+  *reinterpret_cast<__half*>(hi_p) = h;
+  *reinterpret_cast<__half*>(lo_p) = __float2half_rn(split_sat(v - __half2float(h)));
+}
+__device__ __forceinline__ float split_load(const bf16* hi_p, const bf16* lo_p) {
+  return __half2float(*reinterpret_cast<const __half*>(hi_p)) + __half2float(*reinterpret_cast<const __half*>(lo_p));
+}
+// 4 consecutive fp16 values (8-byte aligned) as floats
+__device__ __forceinline__ void load4h(const bf16* p, float (&o)[4]) {
+  const uint2 v = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
 
 // ---- regularizer arithmetic, shared by the stand-alone kernels (elementwise.cu) and the conv_out epilogue (conv_tc.cu) ----
 // FSQ (regularizers.py:153-178): bound = tanh(z + shift) * half_l - offset, round half-to-even, code = q / half_w,
@@ -143,9 +166,17 @@ struct ConvP {
   int res_t_mode;                     // mode 3 front pad: 0 zero (v1.0), 1 replicate frame 0, 2 res_cache (1 frame)
   const void* res_cache;              // [B,1,H,W,C]
   float ra, rb;
-  // activations (input, cache, residual, bf16-class output) are hi|lo split bf16 planes (DT_SPLIT): every position holds
+  // activations (input, cache, residual, bf16-class output) are hi|lo split fp16 planes (DT_SPLIT): every position holds
   // 2*C bf16 values, the strides above count bf16 elements (isW = 2*Ci for a dense tensor), channel c's lo part is at c + C
   int split;
+  // split mode: the packed weights were multiplied by a power of two (so that their lo plane stays in fp16's normal range);
+  // the epilogue multiplies the accumulator by acc_scale = 2^-s before the bias (0 is read as 1)
+  float acc_scale;
+  // decode_from_indices in the producer of the decoder's conv_in (autoencoder.py:205-217, regularizers.py:180-198): the
+  // "input" is the int32 token tensor [B,T,H,W] (strides as an fp32 tensor without the channel dimension, isC = 0) and
+  // channel ci of a position is the FSQ code digit ((idx / basis_ci) % L_ci - L_ci/2) / (L_ci/2).  0 = off.
+  int fsq_d;
+  int fsq_levels[VT_MAX_FSQ];
 };
 
 struct ConvLaunch {  // host-side convenience

@@ -40,20 +40,24 @@ __device__ __forceinline__ const TIn* gather_ptr(const ConvP& p, const TIn* __re
 template <typename T>
 __device__ __forceinline__ void ld4s(const ConvP& p, const T* q, int C, int ncount, float (&t)[4]) {
   t[0] = t[1] = t[2] = t[3] = 0.f;
+  if constexpr (std::is_same<T, bf16>::value) {
+    if (p.split) {   // fp16 hi | lo planes behind the 16-bit pointer
+      if (ncount == 4) {
+        float u[4];
+        load4h(q, t);
+        load4h(q + C, u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t[j] += u[j];
+      } else {
+        for (int j = 0; j < ncount; ++j) t[j] = split_load(q + j, q + C + j);
+      }
+      return;
+    }
+  }
   if (ncount == 4) {
     load4(q, t);
   } else {
     for (int j = 0; j < ncount; ++j) t[j] = to_f(q[j]);
-  }
-  if (std::is_same<T, bf16>::value && p.split) {
-    float u[4] = {0.f, 0.f, 0.f, 0.f};
-    if (ncount == 4) {
-      load4(q + C, u);
-    } else {
-      for (int j = 0; j < ncount; ++j) u[j] = to_f(q[C + j]);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) t[j] += u[j];
   }
 }
 
@@ -167,7 +171,23 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvP p, const TIn
             int t2 = tap / p.kw;
             int bb = t2 % p.kh, a = t2 / p.kh;
             const TIn* q = gather_ptr<TIn>(p, x, rb[i], rt[i], rh[i], rw[i], a, bb, c);
-            if (q) ra[i][j] = to_f(q[(long long)ci * p.isC]) + ((std::is_same<TIn, bf16>::value && p.split) ? to_f(q[(long long)(ci + p.Ci) * p.isC]) : 0.f);
+            if (q) {
+              if (std::is_same<TIn, float>::value && p.fsq_d) {
+                // token index -> code digit ci (same arithmetic as fsq_i2c_kernel)
+                const int id = *reinterpret_cast<const int*>(q);
+                int basis = 1;
+                for (int k2 = 0; k2 < ci; ++k2) basis *= p.fsq_levels[k2];
+                const int L = p.fsq_levels[ci], hw = L / 2;
+                ra[i][j] = (float)((id / basis) % L - hw) / (float)hw;
+              } else {
+                if constexpr (std::is_same<TIn, bf16>::value) {
+                  ra[i][j] = p.split ? split_load(reinterpret_cast<const bf16*>(q) + (long long)ci * p.isC, reinterpret_cast<const bf16*>(q) + (long long)(ci + p.Ci) * p.isC)
+                                     : to_f(q[(long long)ci * p.isC]);
+                } else {
+                  ra[i][j] = to_f(q[(long long)ci * p.isC]);
+                }
+              }
+            }
           }
         }
       }
@@ -255,11 +275,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvP p, const TIn
               (long long)n * p.osC;
     if (std::is_same<TOut, bf16>::value && p.split) {
       // hi | lo planes (TOut = bf16, osC == 1)
-      for (int j = 0; j < ncount; ++j) {
-        const TOut h = from_f<TOut>(v[j]);
-        o[j] = h;
-        o[p.Co + j] = from_f<TOut>(v[j] - to_f(h));
-      }
+      for (int j = 0; j < ncount; ++j) split_store(reinterpret_cast<bf16*>(o) + j, reinterpret_cast<bf16*>(o) + p.Co + j, v[j]);
     } else if (vecO) {
       store4(o, v);
     } else {
@@ -275,7 +291,7 @@ cudaError_t launch_typed(const ConvP& p, const void* x, const float* w, void* ou
   if (prof_enabled()) snprintf(det, sizeof(det), "k%d%d%d s%d%d%d u%d%d%d %d->%d @%dx%dx%d", p.kt, p.kh, p.kw, p.st, p.sh, p.sw, p.ut, p.uh, p.uw, p.Ci, p.Co, p.To, p.Ho, p.Wo);
   ProfScope _ps("conv_simt", 2.0 * M * p.kt * p.kh * p.kw * p.Ci * p.Co,
                 (double)p.B * p.Ti * p.Hi * p.Wi * p.Ci * sizeof(TIn) + (double)M * p.Co * sizeof(TOut), s, det);
-  const bool veca = (p.Ci % 4 == 0) && (p.isC == 1) && (p.isW % 4 == 0) && (p.isH % 4 == 0) && (p.isT % 4 == 0) &&
+  const bool veca = !p.fsq_d && (p.Ci % 4 == 0) && (p.isC == 1) && (p.isW % 4 == 0) && (p.isH % 4 == 0) && (p.isT % 4 == 0) &&
                     (p.isB % 4 == 0);
   const TIn* xi = reinterpret_cast<const TIn*>(x);
   TOut* o = reinterpret_cast<TOut*>(out);
@@ -300,7 +316,7 @@ cudaError_t launch_typed(const ConvP& p, const void* x, const float* w, void* ou
 
 }  // namespace
 
-// DT_SPLIT tensors are bf16 planes: the caller sets p.split when the bf16-typed operands (input / residual / output)
+// DT_SPLIT tensors are 16-bit (fp16) planes behind bf16-typed pointers: the caller sets p.split when the bf16-typed operands (input / residual / output)
 // are split; fp32 external tensors (tin / tout == DT_F32) are unaffected by the flag.
 cudaError_t launch_conv_simt(const ConvP& p, DType tin, DType tout, DType tres, const void* x, const float* w,
                              void* out, cudaStream_t s) {

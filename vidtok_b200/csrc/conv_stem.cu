@@ -26,6 +26,7 @@ struct StemParams {
   long long num_tiles;
   int tilesW, tilesH;
   uint32_t tmem_cols;
+  float acc_scale;   // split: 2^-s of the pre-scaled weights (1 otherwise)
 };
 
 constexpr int BW = 16, BH = 8;
@@ -71,7 +72,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr) : "memory");
 }
 
-// kSplit (EXACT_TC mode): the im2col rows and the weights are hi|lo bf16 pairs, every K=16 step issues hi*hi + lo*hi +
+// kSplit (EXACT_TC mode): the im2col rows and the weights are hi|lo fp16 pairs, every K=16 step issues hi*hi + lo*hi +
 // hi*lo into the same accumulator, and the output is written as hi | lo planes ([..., 2*Co]).
 // The bf16 variant (110 KB of shared memory, 2*Co = 256 TMEM columns for Co = 128) is sized so that TWO CTAs share an SM:
 // the phases of a tile (patch loads -> im2col -> MMA -> epilogue) are serialised inside a CTA by block barriers, and a
@@ -129,7 +130,8 @@ __global__ void __launch_bounds__(256, kSplit ? 1 : 2) conv_stem_kernel(const St
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + offBar + 16);
-  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Co >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  constexpr uint32_t kFmt = kSplit ? 0u : 1u;   // operand format: bf16, or fp16 for the split planes
+  const uint32_t idesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((uint32_t)(p.Co >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
   auto decode = [&](long long tile, int& b, int& t, int& h0, int& w0) {
     const int tw = (int)(tile % p.tilesW);
@@ -197,12 +199,19 @@ __global__ void __launch_bounds__(256, kSplit ? 1 : 2) conv_stem_kernel(const St
         f[e] = off >= 0 ? prow[off] : 0.f;
       }
       uint4 pk, pl;
-      __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
-      __nv_bfloat162* l2 = reinterpret_cast<__nv_bfloat162*>(&pl);
+      if constexpr (kSplit) {
+        __half2* h2 = reinterpret_cast<__half2*>(&pk);
+        __half2* l2 = reinterpret_cast<__half2*>(&pl);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        h2[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
-        if constexpr (kSplit) l2[e] = __floats2bfloat162_rn(f[2 * e] - __low2float(h2[e]), f[2 * e + 1] - __high2float(h2[e]));
+        for (int e = 0; e < 4; ++e) {
+          h2[e] = __floats2half2_rn(split_sat(f[2 * e]), split_sat(f[2 * e + 1]));
+          const float2 hf = __half22float2(h2[e]);
+          l2[e] = __floats2half2_rn(f[2 * e] - hf.x, f[2 * e + 1] - hf.y);
+        }
+      } else {
+        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
       }
       const int kc = u >> 3, uu = u & 7;
       *reinterpret_cast<uint4*>(arow + kc * (128 * 128) + ((uu ^ (row & 7)) << 4)) = pk;
@@ -253,15 +262,22 @@ __global__ void __launch_bounds__(256, kSplit ? 1 : 2) conv_stem_kernel(const St
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 pk, pl;
-          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
-          __nv_bfloat162* l2 = reinterpret_cast<__nv_bfloat162*>(&pl);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int c = j + g * 8 + 2 * e;
-            const float f0 = __uint_as_float(v[g * 8 + 2 * e]) + sbias[half * ncols + c];
-            const float f1 = __uint_as_float(v[g * 8 + 2 * e + 1]) + sbias[half * ncols + c + 1];
-            h2[e] = __floats2bfloat162_rn(f0, f1);
-            if constexpr (kSplit) l2[e] = __floats2bfloat162_rn(f0 - __low2float(h2[e]), f1 - __high2float(h2[e]));
+            if constexpr (kSplit) {
+              const float f0 = fmaf(__uint_as_float(v[g * 8 + 2 * e]), p.acc_scale, sbias[half * ncols + c]);
+              const float f1 = fmaf(__uint_as_float(v[g * 8 + 2 * e + 1]), p.acc_scale, sbias[half * ncols + c + 1]);
+              __half2* h2 = reinterpret_cast<__half2*>(&pk);
+              __half2* l2 = reinterpret_cast<__half2*>(&pl);
+              h2[e] = __floats2half2_rn(split_sat(f0), split_sat(f1));
+              const float2 hf = __half22float2(h2[e]);
+              l2[e] = __floats2half2_rn(split_sat(f0 - hf.x), split_sat(f1 - hf.y));
+            } else {
+              const float f0 = __uint_as_float(v[g * 8 + 2 * e]) + sbias[half * ncols + c];
+              const float f1 = __uint_as_float(v[g * 8 + 2 * e + 1]) + sbias[half * ncols + c + 1];
+              reinterpret_cast<__nv_bfloat162*>(&pk)[e] = __floats2bfloat162_rn(f0, f1);
+            }
           }
           *reinterpret_cast<uint4*>(orow + j + g * 8) = pk;
           if constexpr (kSplit) *reinterpret_cast<uint4*>(orow + p.Co + j + g * 8) = pl;
@@ -351,6 +367,7 @@ cudaError_t launch_conv_stem(const ConvP& p, const float* x, const bf16* wpk, bf
   t.cache = (const float*)p.cache;
   t.x = x; t.B = p.B; t.Ci = p.Ci; t.T = p.Ti; t.H = p.Hi; t.W = p.Wi; t.To = p.To; t.t_rep = p.t_rep; t.t_mode = p.t_mode;
   t.Co = p.Co; t.bias = p.bias; t.out = out;
+  t.acc_scale = (p.split && p.acc_scale != 0.f) ? p.acc_scale : 1.0f;
   t.tilesW = (p.Wi + BW - 1) / BW; t.tilesH = (p.Hi + BH - 1) / BH;
   t.num_tiles = (long long)p.B * p.To * t.tilesH * t.tilesW;
   uint32_t cols = 32;

@@ -97,11 +97,17 @@ struct TcParams {
   // group stride (SBO) = hP rows, and hP % 8 == 0 keeps the swizzle phase of every group equal (= descriptor base offset).
   int halo, hP, a_stages;
   uint32_t halo_bytes;
-  // split operands (EXACT_TC mode, kernel template kSplit): activations and weights are stored as two bf16 planes
-  // hi = bf16(v), lo = bf16(v - hi) side by side in the channel dimension ([..., hi(C) | lo(C)]); every K step loads
+  // split operands (EXACT_TC mode, kernel template kSplit): activations and weights are stored as two fp16 planes
+  // hi = fp16(v), lo = fp16(v - hi) side by side in the channel dimension ([..., hi(C) | lo(C)]); every K step loads
   // A_hi, A_lo, B_hi, B_lo and issues A_hi*B_hi + A_lo*B_hi + A_hi*B_lo into the same fp32 TMEM accumulator
-  // (error ~2^-17 per product: fp32-class results on the bf16 tensor pipe).  Channel coordinate of the lo plane:
+  // (error ~2^-21 per product: fp32-class results on the 16-bit tensor pipe).  Channel coordinate of the lo plane:
   int split, a_lo, b_lo, o_lo;   // = Cin, Kpad, Cout
+  float acc_scale;               // split: accumulator scale 2^-s of the pre-scaled weights
+  // split, long K: the tensor core's fp32 accumulation is the dominant error there (it grows with the number of chained
+  // MMAs: measured 2e-4 at K = 13824 against 1e-5 at K = 200), so the K steps of a tile are dealt round-robin onto `kparts`
+  // partial accumulators in TMEM which the epilogue adds in fp32 (round-to-nearest); the accumulator is then not double
+  // buffered across tiles (acc_stages = 1)
+  int kparts, acc_stages;
   // regularizer epilogue on the fp32 heads (TcRegFusion): the owner of a row holds every channel of its position
   int reg_mode, reg_zc, reg_sample;
   const float* reg_noise;
@@ -362,7 +368,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     // ===================== MMA issuer =====================
     if (rank == 0) {
       const bool el = elect_one();
-      const uint32_t idesc = make_idesc(p.BN, kPair ? 256 : 128);
+      const uint32_t idesc = make_idesc(p.BN, kPair ? 256 : 128, kSplit);   // split planes are fp16
       const int MT = p.MT;
       const uint32_t BNu = (uint32_t)p.BN;
       // descriptor words: lo = start >> 4 | LBO(1) << 16 ; hi = SBO >> 4 | version 1 << 14 | SWIZZLE_128B (2) << 29
@@ -393,15 +399,23 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         }
       };
       // one K step (64 channels): A tile(s) at descriptor word a_lo against the B tile of the current stage
+      uint32_t ks = 0;                                          // K steps issued for the current tile
+      const uint32_t kparts = kSplit ? (uint32_t)p.kparts : 1u;
+      const uint32_t part_cols = (uint32_t)MT * BNu;
       auto kstep = [&](uint32_t a_lo, uint32_t acc, bool res) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         if (el) {
           const uint32_t b_lo = (((b_addr0 + stage * stage_bytes) & 0x3FFFFu) >> 4) | 0x10000u;
-          mma64(tmem_d, a_lo, b_lo, acc, res);
-          if (MT == 2) mma64(tmem_d + BNu, a_lo + mt_step, b_lo, acc, res);
+          uint32_t d = tmem_d;
+          if constexpr (kSplit) {
+            if (kparts > 1) { d += (ks % kparts) * part_cols; acc = ks >= kparts ? 1u : 0u; }
+          }
+          mma64(d, a_lo, b_lo, acc, res);
+          if (MT == 2) mma64(d + BNu, a_lo + mt_step, b_lo, acc, res);
           if constexpr (kPair) umma_commit_2sm(empty_bar(stage)); else umma_commit(empty_bar(stage));
         }
+        ++ks;
         if (++stage == nstages) { stage = 0; phase ^= 1u; }
       };
       auto stage_a_lo = [&]() { return (((smem_base + stage * stage_bytes) & 0x3FFFFu) >> 4) | 0x10000u; };
@@ -414,10 +428,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       };
       for (long long tile = tile0; tile < p.num_tiles; tile += tile_step, ++it) {
         const TileCoord tc = decode_tile(p, tile, rank);
-        const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
+        const uint32_t as = p.acc_stages == 2 ? (it & 1u) : 0u, aphase = p.acc_stages == 2 ? ((it >> 1) & 1u) : (it & 1u);
         mbar_wait(tempty_bar(as), aphase ^ 1u);
         tc_fence_after();
-        tmem_d = tmem_base + as * (uint32_t)(MT * p.BN);
+        tmem_d = tmem_base + as * kparts * part_cols;
+        ks = 0;
         uint32_t accum = 0;
         for (int a = 0; a < p.kt; ++a) {
           int tv;
@@ -484,7 +499,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     uint32_t cbuf = 1;                         // bias / gamma / beta buffer in use (toggled whenever n0 changes)
     for (long long tile = tile0; tile < p.num_tiles; tile += tile_step, ++it) {
       const TileCoord tc = decode_tile(p, tile, rank);
-      const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
+      const uint32_t as = p.acc_stages == 2 ? (it & 1u) : 0u, aphase = p.acc_stages == 2 ? ((it >> 1) & 1u) : (it & 1u);
       if (tc.n0 != last_n0) {
         // all epilogue warps walk the same tile sequence, so this branch is uniform across them; a warp can only be one
         // barrier behind, which is why two buffers are enough
@@ -597,11 +612,24 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       };
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
-      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * p.MT + mt) * p.BN);
+      const uint32_t eparts = kSplit ? (uint32_t)p.kparts : 1u;
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * eparts * p.MT + mt) * p.BN);
       if constexpr (kSplit) {
+        // partial accumulators in use for this tile: min(kparts, K steps of the tile) (causally skipped taps shorten the loop)
+        uint32_t nparts = 1;
+        if (eparts > 1) {
+          uint32_t nk = 0;
+          for (int a = 0; a < p.kt; ++a) {
+            int tv_;
+            bool fc_;
+            if (tap_time(p, tc, a, tv_, fc_)) nk += (uint32_t)(p.kh * p.kw * p.num_kc);
+          }
+          nparts = nk < eparts ? nk : eparts;
+        }
+        const uint32_t part_stride = (uint32_t)(p.MT * p.BN);
         // ---- EXACT_TC epilogue: fp32 values straight from the accumulator (re-read per pass: the main loop is three
         // times as long as in bf16 mode, the epilogue has the time), two-pass LayerNorm statistics, full-precision
-        // SiLU, results written as hi | lo bf16 planes.
+        // SiLU, results written as hi | lo fp16 planes.
         const bf16* rl0 = r0 ? r0 + p.o_lo : nullptr;   // lo planes of the residual rows
         const bf16* rl1 = r1 ? r1 + p.o_lo : nullptr;
         const bf16* rl2 = r2 ? r2 + p.o_lo : nullptr;
@@ -609,8 +637,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             float a[8], b[8];
-            unpack8(*reinterpret_cast<const uint4*>(rh + jj + g * 8), a);
-            unpack8(*reinterpret_cast<const uint4*>(rl + jj + g * 8), b);
+            unpack8h(*reinterpret_cast<const uint4*>(rh + jj + g * 8), a);
+            unpack8h(*reinterpret_cast<const uint4*>(rl + jj + g * 8), b);
 #pragma unroll
             for (int e = 0; e < 8; ++e) f[g * 8 + e] = fmaf(sc, a[e] + b[e], f[g * 8 + e]);
           }
@@ -620,8 +648,19 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           uint32_t v[32];
           tmem_ld32(tbase + (uint32_t)jj, v);
           tmem_ld_wait();
+          if (nparts > 1) {   // fp32 (round-to-nearest) sum of the partial accumulators
+#pragma unroll 1
+            for (uint32_t pi = 1; pi < nparts; ++pi) {
+              uint32_t u[32];
+              tmem_ld32(tbase + pi * part_stride + (uint32_t)jj, u);
+              tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]) + bias_s[jj + e];
+              for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(u[e]));
+            }
+          }
+          // (the split weights carry a power-of-two scale: undo it on the accumulator, exactly, before the bias)
+#pragma unroll
+          for (int e = 0; e < 32; ++e) f[e] = fmaf(__uint_as_float(v[e]), p.acc_scale, bias_s[jj + e]);
           if (p.rb != 1.0f) {
 #pragma unroll
             for (int e = 0; e < 32; ++e) f[e] *= p.rb;
@@ -726,9 +765,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
               } else {
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
-                  const uint32_t h2 = pack_bf16x2(f[2 * e], f[2 * e + 1]);
+                  const uint32_t h2 = pack_f16x2(f[2 * e], f[2 * e + 1]);
                   hw[hc * 16 + e] = h2;
-                  lw[hc * 16 + e] = pack_bf16x2(f[2 * e] - bf16_lo(h2), f[2 * e + 1] - bf16_hi(h2));
+                  lw[hc * 16 + e] = pack_f16x2(f[2 * e] - f16_lo(h2), f[2 * e + 1] - f16_hi(h2));
                 }
               }
             }
@@ -909,9 +948,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   }
 }
 
-__global__ void fill_identity_kernel(bf16* e) {
+__global__ void fill_identity_kernel(bf16* e, int f16) {
   const int r = blockIdx.x, c = threadIdx.x;
-  e[r * 256 + c] = __float2bfloat16_rn(r == c ? 1.0f : 0.0f);
+  if (f16) reinterpret_cast<__half*>(e)[r * 256 + c] = __float2half_rn(r == c ? 1.0f : 0.0f);
+  else e[r * 256 + c] = __float2bfloat16_rn(r == c ? 1.0f : 0.0f);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1056,7 +1096,7 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   if (!enc) { g_tc_err = "cuTensorMapEncodeTiled unavailable"; return cudaErrorNotSupported; }
   const bool split = p.split != 0;
   const int cw = split ? 2 : 1;              // bf16 elements per logical channel (hi | lo planes)
-  const bool out_bf16 = tout != DT_F32;      // DT_BF16, or DT_SPLIT (two bf16 planes)
+  const bool out_bf16 = tout != DT_F32;      // DT_BF16, or DT_SPLIT (two 16-bit planes)
   if (split != (tout == DT_SPLIT) && tout != DT_F32) { g_tc_err = "split activations need a split (or fp32) output"; return cudaErrorInvalidValue; }
   TcParams t;
   memset(&t, 0, sizeof(t));
@@ -1164,8 +1204,14 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   t.stages = stages;
   // smem layout from the 1024-aligned base: [halo windows] [stages x (A | B)] [staging] [barriers | tmem slot | bias/gamma/beta | stats]
   t.stage_off = (uint32_t)(a_ring + stages * stage_bytes);
+  t.kparts = 1; t.acc_stages = 2;
+  if (split && p.kt * p.kh * p.kw * (p.Ci / 64) >= 16) {   // K >= 1024
+    int parts = 512 / (t.MT * t.BN);
+    if (parts > 8) parts = 8;
+    if (parts >= 2) { t.kparts = parts; t.acc_stages = (2 * parts * t.MT * t.BN <= 512) ? 2 : 1; }
+  }
   uint32_t cols = 32;
-  while (cols < (uint32_t)(2 * t.MT * t.BN)) cols <<= 1;
+  while (cols < (uint32_t)(t.acc_stages * t.kparts * t.MT * t.BN)) cols <<= 1;
   t.tmem_cols = cols;
   smem = fixed + staging + a_ring + (size_t)stages * stage_bytes + 8 * (2 * stages + 4 + 2 * t.a_stages);
   return 0;
@@ -1174,16 +1220,20 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
     // preference order; the later entries only matter for split operands (every operand tile doubled): give up the halo
     // windows, the second M tile, the store staging buffers, and finally (when no LayerNorm needs the whole row) the wide N tile
     const bool need_row = ln && ln->mode;
-    int rc = plan(true, true, true, 0);
-    if (rc == 1) rc = plan(false, true, true, 0);
-    if (rc == 1) rc = plan(false, false, true, 0);
-    if (rc == 1) rc = plan(false, false, false, 0);
+    // split + long K: narrow N tiles leave TMEM room for more partial accumulators (TcParams::kparts)
+    const int nk = p.kt * p.kh * p.kw * (p.Ci / 64);
+    const int bn_pref = (split && !need_row && w_batches <= 1) ? (nk >= 128 ? 64 : (nk >= 32 ? 128 : 0)) : 0;
+    int rc = plan(true, true, true, bn_pref);
+    if (rc == 1) rc = plan(false, true, true, bn_pref);
+    if (rc == 1) rc = plan(false, false, true, bn_pref);
+    if (rc == 1) rc = plan(false, false, false, bn_pref);
     if (rc == 1 && !need_row) rc = plan(false, false, true, 128);
     if (rc == 1 && !need_row) rc = plan(false, false, false, 128);
     if (rc == 1) g_tc_err = "not enough shared memory for 2 stages";
     if (rc != 0) return cudaErrorInvalidValue;
   }
   t.split = split ? 1 : 0; t.a_lo = p.Ci; t.b_lo = Kpad; t.o_lo = p.Co;
+  t.acc_scale = (split && p.acc_scale != 0.f) ? p.acc_scale : 1.0f;
   t.B = p.B; t.To = p.To; t.Ho = p.Ho; t.Wo = p.Wo; t.Co = p.Co; t.Ti = p.Ti;
   t.kt = p.kt; t.kh = p.kh; t.kw = p.kw; t.Ci = p.Ci; t.num_kc = p.Ci / 64;
   t.st = p.st; t.pt = p.pt; t.ph = p.ph; t.pw = p.pw; t.to_off = p.to_off; t.sp = p.sh;
@@ -1220,7 +1270,9 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
     const double out_bytes = (double)p.B * p.To * p.Ho * p.Wo * p.Co * 2.0 * cw;
     t.store_stream = (ev_env && out_bytes > 256e6) ? 1 : 0;
   }
-  t.res_mma = (p.res_mode == 1 && p.ra == 1.0f && p.rb == 1.0f && t.BN % 64 == 0 && p.Co % 64 == 0 && p.rsW % 8 == 0 && p.rsH % 8 == 0 &&
+  // (split mode: the weights carry a power-of-two scale that the epilogue removes from the whole accumulator, so the residual
+  // cannot ride the tensor pipe there -- it is added by the epilogue from the hi|lo planes in global memory)
+  t.res_mma = (!split && p.res_mode == 1 && p.ra == 1.0f && p.rb == 1.0f && t.BN % 64 == 0 && p.Co % 64 == 0 && p.rsW % 8 == 0 && p.rsH % 8 == 0 &&
                p.rsT % 8 == 0 && p.rsB % 8 == 0 && (((uintptr_t)p.res) & 15) == 0) ? 1 : 0;
 
   TcMaps maps;
@@ -1288,16 +1340,17 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
     if (t.ln_mode == 2 && !encode_out(&maps.o2, t.out2, p.To, p.osW, p.osH, p.osT, p.osB, qw, qh, qt)) return cudaErrorInvalidValue;
   }
   if (t.res_mma) {
-    static bf16* ident_dev[64] = {nullptr};   // 256 x 256 identity, built once per device on the launching stream
+    static bf16* ident_dev[2][64] = {{nullptr}};   // 256 x 256 identity (bf16 / fp16), built once per device on the launching stream
     int devid = 0;
     cudaGetDevice(&devid);
     if (devid < 0 || devid >= 64) { g_tc_err = "device index out of range"; return cudaErrorInvalidValue; }
-    if (!ident_dev[devid]) {
-      cudaError_t e = cudaMalloc(&ident_dev[devid], 256 * 256 * sizeof(bf16));
+    const int ik = split ? 1 : 0;
+    if (!ident_dev[ik][devid]) {
+      cudaError_t e = cudaMalloc(&ident_dev[ik][devid], 256 * 256 * sizeof(bf16));
       if (e != cudaSuccess) { g_tc_err = "cudaMalloc(identity)"; return e; }
-      fill_identity_kernel<<<256, 256, 0, s>>>(ident_dev[devid]);
+      fill_identity_kernel<<<256, 256, 0, s>>>(ident_dev[ik][devid], ik);
     }
-    bf16* ident = ident_dev[devid];
+    bf16* ident = ident_dev[ik][devid];
     if (!encode_out(&maps.r, p.res, p.resT, p.rsW, p.rsH, p.rsT, p.rsB, t.halo ? t.hP : t.BW, t.halo ? 16 + p.kh - 1 : t.BH, t.BT)) return cudaErrorInvalidValue;
     cuuint64_t dims[3] = {256, 256, 1};
     cuuint64_t strides[2] = {512, 256 * 512};

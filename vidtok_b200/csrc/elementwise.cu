@@ -99,31 +99,27 @@ template <typename T> struct RowAcc {
 };
 template <> struct RowAcc<split16> {
   static constexpr int W = 2;
-  static __device__ __forceinline__ float ld(const split16* row, int C, int c) {
-    return __bfloat162float(row[c].v) + __bfloat162float(row[C + c].v);
-  }
-  static __device__ __forceinline__ void st(split16* row, int C, int c, float v) {
-    const bf16 h = __float2bfloat16_rn(v);
-    row[c].v = h;
-    row[C + c].v = __float2bfloat16_rn(v - __bfloat162float(h));
-  }
+  static __device__ __forceinline__ float ld(const split16* row, int C, int c) { return split_load(&row[c].v, &row[C + c].v); }
+  static __device__ __forceinline__ void st(split16* row, int C, int c, float v) { split_store(&row[c].v, &row[C + c].v, v); }
 };
 __device__ __forceinline__ void split8(const float (&f)[8], uint4& hi, uint4& lo) {
-  __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&hi);
-  __nv_bfloat162* l2 = reinterpret_cast<__nv_bfloat162*>(&lo);
+  __half2* h2 = reinterpret_cast<__half2*>(&hi);
+  __half2* l2 = reinterpret_cast<__half2*>(&lo);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    h2[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-    l2[i] = __floats2bfloat162_rn(f[2 * i] - __low2float(h2[i]), f[2 * i + 1] - __high2float(h2[i]));
+    h2[i] = __floats2half2_rn(split_sat(f[2 * i]), split_sat(f[2 * i + 1]));
+    const float2 hf = __half22float2(h2[i]);
+    l2[i] = __floats2half2_rn(split_sat(f[2 * i] - hf.x), split_sat(f[2 * i + 1] - hf.y));
   }
 }
 __device__ __forceinline__ void join8(const uint4& hi, const uint4& lo, float (&f)[8]) {
-  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&hi);
-  const __nv_bfloat162* l2 = reinterpret_cast<const __nv_bfloat162*>(&lo);
+  const __half2* h2 = reinterpret_cast<const __half2*>(&hi);
+  const __half2* l2 = reinterpret_cast<const __half2*>(&lo);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    f[2 * i] = __low2float(h2[i]) + __low2float(l2[i]);
-    f[2 * i + 1] = __high2float(h2[i]) + __high2float(l2[i]);
+    const float2 a = __half22float2(h2[i]), b = __half22float2(l2[i]);
+    f[2 * i] = a.x + b.x;
+    f[2 * i + 1] = a.y + b.y;
   }
 }
 // LayerNorm(+SiLU) of split rows (EXACT_TC mode, C % 8 == 0): one warp per position, fp32 two-pass statistics,
@@ -507,18 +503,28 @@ __global__ void pack_w_kn_kernel(const float* __restrict__ w, float* __restrict_
   }
 }
 struct CollapseMap { int mt[3], mh[3], mw[3]; };
-// split != 0: rows are [hi(K) | lo(K)] (row length 2*K), lo = bf16(v - hi)
-__device__ __forceinline__ void put_w(bf16* out, long long row, int K, int k, float v, int split) {
-  const bf16 h = __float2bfloat16_rn(v);
-  if (split) {
-    out[row * 2 * K + k] = h;
-    out[row * 2 * K + K + k] = __float2bfloat16_rn(v - __bfloat162float(h));
-  } else {
-    out[row * K + k] = h;
+// wscale != 0: split rows [hi(K) | lo(K)] (row length 2*K) of fp16 planes of v * wscale (a power of two chosen by the caller
+// so that the lo plane stays in fp16's normal range; the conv epilogue undoes it on the accumulator); wscale == 0: bf16 rows
+__device__ __forceinline__ void put_w(bf16* out, long long row, int K, int k, float v, float wscale) {
+  if (wscale != 0.f) split_store(&out[row * 2 * K + k], &out[row * 2 * K + K + k], v * wscale);
+  else out[row * K + k] = __float2bfloat16_rn(v);
+}
+// max |w| of a tensor (one block; result in *out)
+__global__ void __launch_bounds__(1024) absmax_kernel(const float* __restrict__ w, long long n, float* __restrict__ out) {
+  float m = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(w[i]));
+  m = warp_max(m);
+  __shared__ float red[32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    t = warp_max(t);
+    if (threadIdx.x == 0) *out = t;
   }
 }
 __global__ void pack_w_collapsed_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Co, int Co_pad, int Ci,
-                                        int kt, int kh, int kw, CollapseMap cm, int kt2, int kh2, int kw2, int split) {
+                                        int kt, int kh, int kw, CollapseMap cm, int kt2, int kh2, int kw2, float wscale) {
   const int K2 = kt2 * kh2 * kw2 * Ci;
   const long long total = (long long)Co_pad * K2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -533,11 +539,11 @@ __global__ void pack_w_collapsed_kernel(const float* __restrict__ w, bf16* __res
           for (int c = 0; c < kw; ++c)
             if (cm.mt[a] == a2 && cm.mh[b] == b2 && cm.mw[c] == c2)
               v += w[((long long)co * Ci + ci) * (kt * kh * kw) + (a * kh + b) * kw + c];
-    put_w(out, co, K2, k, v, split);
+    put_w(out, co, K2, k, v, wscale);
   }
 }
 __global__ void pack_w_nk_bf16_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Co, int Co_pad, int Ci, int taps,
-                                      int Kpad, int split) {
+                                      int Kpad, float wscale) {
   const long long total = (long long)Co_pad * Kpad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(i % Kpad);
@@ -547,7 +553,7 @@ __global__ void pack_w_nk_bf16_kernel(const float* __restrict__ w, bf16* __restr
       const int tap = k / Ci, ci = k % Ci;
       v = w[((long long)co * Ci + ci) * taps + tap];
     }
-    put_w(out, co, Kpad, k, v, split);
+    put_w(out, co, Kpad, k, v, wscale);
   }
 }
 
@@ -943,16 +949,21 @@ cudaError_t launch_pack_w_kn(const float* w, float* out, int Co, int Ci, int tap
 }
 cudaError_t launch_pack_w_collapsed(const float* w, bf16* out, int Co, int Co_pad, int Ci, int kt, int kh, int kw,
                                     const int* mt, const int* mh, const int* mw, int kt2, int kh2, int kw2, cudaStream_t s,
-                                    bool split) {
+                                    float wscale) {
   CollapseMap cm;
   for (int i = 0; i < 3; ++i) { cm.mt[i] = i < kt ? mt[i] : -1; cm.mh[i] = i < kh ? mh[i] : -1; cm.mw[i] = i < kw ? mw[i] : -1; }
-  pack_w_collapsed_kernel<<<grid_for((long long)Co_pad * kt2 * kh2 * kw2 * Ci), 256, 0, s>>>(w, out, Co, Co_pad, Ci, kt, kh, kw, cm, kt2, kh2, kw2, split ? 1 : 0);
+  pack_w_collapsed_kernel<<<grid_for((long long)Co_pad * kt2 * kh2 * kw2 * Ci), 256, 0, s>>>(w, out, Co, Co_pad, Ci, kt, kh, kw, cm, kt2, kh2, kw2, wscale);
+  count_launch();
+  return cudaGetLastError();
+}
+cudaError_t launch_absmax(const float* w, long long n, float* out, cudaStream_t s) {
+  absmax_kernel<<<1, 1024, 0, s>>>(w, n, out);
   count_launch();
   return cudaGetLastError();
 }
 cudaError_t launch_pack_w_nk_bf16(const float* w, bf16* out, int Co, int Co_pad, int Ci, int taps, int Kpad, cudaStream_t s,
-                                  bool split) {
-  pack_w_nk_bf16_kernel<<<grid_for((long long)Co_pad * Kpad), 256, 0, s>>>(w, out, Co, Co_pad, Ci, taps, Kpad, split ? 1 : 0);
+                                  float wscale) {
+  pack_w_nk_bf16_kernel<<<grid_for((long long)Co_pad * Kpad), 256, 0, s>>>(w, out, Co, Co_pad, Ci, taps, Kpad, wscale);
   count_launch();
   return cudaGetLastError();
 }

@@ -7,8 +7,8 @@
 
 namespace vt {
 
-// DT_SPLIT: fp32-class activations stored as two bf16 planes side by side in the channel dimension,
-// [..., hi(C) | lo(C)] with hi = bf16(v), lo = bf16(v - hi) (the operand format of the bf16x3 tcgen05 mode).
+// DT_SPLIT: fp32-class activations stored as two fp16 planes side by side in the channel dimension,
+// [..., hi(C) | lo(C)] with hi = fp16(v), lo = fp16(v - hi) (common.cuh: split_store; the operand format of the EXACT_TC mode).
 // One logical element = 4 bytes; pointers to such tensors are bf16*, strides in ConvP count bf16 elements.
 enum DType { DT_F32 = 0, DT_BF16 = 1, DT_SPLIT = 2 };
 inline size_t dtype_size(DType t) { return t == DT_BF16 ? 2 : 4; }
@@ -43,14 +43,25 @@ cudaError_t launch_fsq_indices_to_codes(const int* indices, int d, const int* le
 // weight repacking: w [Co][Ci][taps] (reference OIDHW flattened) -> [K = tap*Ci + ci][Co] fp32
 cudaError_t launch_pack_w_kn(const float* w, float* out, int Co, int Ci, int taps, cudaStream_t s);
 // -> [Co][K = tap*Ci + ci] bf16 (K-major rows for the tcgen05 B operand)
-// split: rows are [hi(Kpad) | lo(Kpad)] (DT_SPLIT operand format)
+// wscale != 0: split rows [hi(Kpad) | lo(Kpad)] (fp16 planes, DT_SPLIT operand format) of w * wscale (see split_weight_scale)
 cudaError_t launch_pack_w_nk_bf16(const float* w, bf16* out, int Co, int Co_pad, int Ci, int taps, int Kpad, cudaStream_t s,
-                                  bool split = false);
+                                  float wscale = 0.f);
+cudaError_t launch_absmax(const float* w, long long n, float* out, cudaStream_t s);
+// Power-of-two scale for the split (fp16 hi|lo) copy of a weight tensor with the given max |w|: largest 2^s with
+// 2^s * maxabs * headroom < 4096 (headroom: phase-collapsed weights sum up to 4 taps), so that values at 1e-4 of the maximum
+// still have a normal fp16 lo plane.  The conv epilogue multiplies the accumulator by 1 / scale.
+inline float split_weight_scale(float maxabs, float headroom = 1.0f) {
+  if (!(maxabs > 0.f)) return 1.0f;
+  float sc = 1.0f;
+  while (sc * maxabs * headroom < 2048.0f && sc < 1.0e30f) sc *= 2.0f;
+  while (sc * maxabs * headroom >= 4096.0f && sc > 1.0e-30f) sc *= 0.5f;
+  return sc;
+}
 // phase-collapsed weights of "nearest-2x upsample then conv": original taps (a,b,c) of a kt x kh x kw kernel are
 // summed into tap (mt[a], mh[b], mw[c]) of a kt2 x kh2 x kw2 kernel; output [Co_pad][kt2*kh2*kw2*Ci] bf16
 cudaError_t launch_pack_w_collapsed(const float* w, bf16* out, int Co, int Co_pad, int Ci, int kt, int kh, int kw,
                                     const int* mt, const int* mh, const int* mw, int kt2, int kh2, int kw2, cudaStream_t s,
-                                    bool split = false);
+                                    float wscale = 0.f);
 // trilinear (align_corners=False) 2x upsampling along T of channels-last x [B,T,HWC] -> [B,2T,HWC]
 cudaError_t launch_time_interp2x(DType t, const void* x, void* y, int B, int T, long long hw, int C, cudaStream_t s);
 cudaError_t launch_upsample_nearest(DType t, const void* x, void* y, int B, int T, int H, int W, int C, int ut, int uh,

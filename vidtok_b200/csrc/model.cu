@@ -291,6 +291,7 @@ struct ConvOpt {
   long long res_bs = -1;          // residual batch stride override (views)
   float ra = 1.f, rb = 1.f;
   const float* ext_in = nullptr;  // external fp32 NCDHW input
+  bool ext_in_indices = false;    // ext_in is the int32 FSQ token tensor [B,T,H,W]: codes are formed in the conv's producer
   float* ext_out = nullptr;       // external fp32 NCDHW output
   long long in_bs = -1;           // input batch stride override (views into a larger tensor)
   const char* cache_key = nullptr;  // v1.1 causal cache identity (checkpoint prefix of the conv)
@@ -425,13 +426,18 @@ struct Exec {
     memset(&p, 0, sizeof(p));
     p.B = in.B; p.Ti = in.T; p.Hi = in.H; p.Wi = in.W; p.Ci = in.C;
     if (in.C != w.Ci) { rc = fail(VT_ERR_INVALID, "conv: Cin mismatch %d vs %d", in.C, w.Ci); return out; }
-    if (o.ext_in) {
+    if (o.ext_in && o.ext_in_indices) {
+      p.isC = 0; p.isT = (long long)in.H * in.W; p.isB = p.isT * in.T; p.isH = in.W; p.isW = 1;
+      p.fsq_d = m->desc.fsq_num_levels;
+      for (int i = 0; i < VT_MAX_FSQ && i < p.fsq_d; ++i) p.fsq_levels[i] = m->desc.fsq_levels[i];
+    } else if (o.ext_in) {
       p.isC = (long long)in.T * in.H * in.W; p.isB = p.isC * in.C; p.isT = (long long)in.H * in.W; p.isH = in.W; p.isW = 1;
     } else {
       // (stride overrides in ConvOpt count storage elements: bf16 values for split rows)
       p.isC = 1; p.isW = (long long)cw * in.C; p.isH = (long long)in.W * p.isW; p.isT = p.isH * in.H; p.isB = o.in_bs >= 0 ? o.in_bs : p.isT * in.T;
     }
     p.split = split ? 1 : 0;
+    p.acc_scale = split ? 1.0f / w.wscale3 : 1.0f;
     p.kt = w.kt; p.kh = w.kh; p.kw = w.kw;
     p.st = o.st; p.sh = o.sh; p.sw = o.sw;
     p.ut = o.ut; p.uh = o.uh; p.uw = o.uw;
@@ -528,7 +534,7 @@ struct Exec {
     o.fused_reg = reg_fuse;
     if (!dry) {
       const bf16* wst = split ? w.w_stem3 : w.w_stem;
-      const bool stem = tcm && !o.force_simt && o.ext_in && !o.ext_out && !o.out_view && wst && conv_stem_supported(p);
+      const bool stem = tcm && !o.force_simt && o.ext_in && !o.ext_in_indices && !o.ext_out && !o.out_view && wst && conv_stem_supported(p);
       if (tc) {
         void* optr = (reg_fuse && o.reg_only) ? nullptr : out.p;
         if (!cuda(launch_conv_tc(p, (const bf16*)in.p, wtc, w.Kpad, optr, tout, s, 1, 0, lf.mode ? &lf : nullptr, reg_fuse ? o.reg : nullptr),
@@ -1006,6 +1012,7 @@ static void run_encoder(Exec& ex, const float* x_ext, int B, int T, int H, int W
       p.isW = 1; p.isH = W; p.isT = (long long)H * W; p.isC = p.isT * T; p.isB = p.isC * p.Ci;
       p.To = T + t_rep; p.Ho = H; p.Wo = W; p.Co = e.conv_in.Co;
       p.split = ex.split ? 1 : 0;
+      p.acc_scale = ex.split ? 1.0f / e.conv_in.wscale3 : 1.0f;
       p.osC = 1; p.osW = (long long)p.Co * ex.cw; p.osH = (long long)W * p.osW; p.osT = p.osH * H; p.osB = p.osT * p.To;
       p.kt = p.kh = p.kw = 3; p.st = p.sh = p.sw = 1; p.ut = p.uh = p.uw = 1;
       p.pt = 2; p.ph = 1; p.pw = 1; p.t_rep = t_rep;
@@ -1058,7 +1065,7 @@ static void run_encoder(Exec& ex, const float* x_ext, int B, int T, int H, int W
 }
 
 // z_ext: fp32 [B,z,Tz,Hz,Wz]; x_out: fp32 [B,out_ch,Tout,H,W]
-static void run_decoder(Exec& ex, const float* z_ext, int B, int Tz, int Hz, int Wz, float* x_out) {
+static void run_decoder(Exec& ex, const float* z_ext, int B, int Tz, int Hz, int Wz, float* x_out, bool z_is_indices = false) {
   vt_model* m = ex.m;
   const vt_model_desc& d = m->desc;
   const StackW& g = m->dec;
@@ -1072,7 +1079,7 @@ static void run_decoder(Exec& ex, const float* z_ext, int B, int Tz, int Hz, int
     st.x = ex.conv(g.conv_in, zp, o);
     ex.free_act(zp);
   } else {
-    ConvOpt o; o.ext_in = z_ext;
+    ConvOpt o; o.ext_in = z_ext; o.ext_in_indices = z_is_indices;
     st.x = ex.conv(g.conv_in, zin, o);
   }
   std::vector<Stage> stages;
@@ -1310,6 +1317,21 @@ int32_t vt_model_finalize(vt_model* m, void* stream) {
   if (!m->packed_kn) VT_CUDA(cudaMalloc(&m->packed_kn, kn * sizeof(float)));
   if (!m->packed_nk && nk) VT_CUDA(cudaMalloc(&m->packed_nk, nk * sizeof(bf16)));
   if (!m->packed_nk3 && nk) VT_CUDA(cudaMalloc(&m->packed_nk3, 2 * nk * sizeof(bf16)));   // hi|lo copies (EXACT_TC)
+  // power-of-two scales of the split (fp16 hi|lo) weight copies: one max|w| per conv, read back once
+  {
+    float* d_max = nullptr;
+    VT_CUDA(cudaMalloc(&d_max, m->convs.size() * sizeof(float)));
+    for (size_t i = 0; i < m->convs.size(); ++i) {
+      const ConvW* c = m->convs[i];
+      VT_CUDA(launch_absmax(m->pool + m->params[c->pw].offset, (long long)c->Co * c->Ci * c->taps(), d_max + i, s));
+    }
+    std::vector<float> h_max(m->convs.size());
+    cudaError_t e = cudaMemcpyAsync(h_max.data(), d_max, h_max.size() * sizeof(float), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(d_max);
+    if (e != cudaSuccess) return fail(VT_ERR_CUDA, "weight scale readback: %s", cudaGetErrorString(e));
+    for (size_t i = 0; i < m->convs.size(); ++i) m->convs[i]->wscale3 = split_weight_scale(h_max[i], 4.0f);   // headroom: collapsed taps
+  }
   size_t okn = 0, onk = 0;
   for (ConvW* c : m->convs) {
     const int K = c->taps() * c->Ci;
@@ -1323,7 +1345,7 @@ int32_t vt_model_finalize(vt_model* m, void* stream) {
       c->w_nk3 = m->packed_nk3 + 2 * onk;
       onk += align_up((size_t)c->Co_pad * K, 512);
       VT_CUDA(launch_pack_w_nk_bf16(w, c->w_nk, c->Co, c->Co_pad, c->Ci, c->taps(), c->Kpad, s));
-      VT_CUDA(launch_pack_w_nk_bf16(w, c->w_nk3, c->Co, c->Co_pad, c->Ci, c->taps(), c->Kpad, s, true));
+      VT_CUDA(launch_pack_w_nk_bf16(w, c->w_nk3, c->Co, c->Co_pad, c->Ci, c->taps(), c->Kpad, s, c->wscale3));
     }
   }
   for (auto& lv : m->dec.levels) {
@@ -1337,10 +1359,10 @@ int32_t vt_model_finalize(vt_model* m, void* stream) {
           ConvW& ph = lv.up_ph[py * 2 + px];
           ph = ConvW();
           ph.Co = c.Co; ph.Ci = c.Ci; ph.kt = 1; ph.kh = 2; ph.kw = 2; ph.Co_pad = c.Co; ph.Kpad = 4 * c.Ci;
-          ph.bias = c.bias; ph.w_nk = m->packed_nk + onk; ph.w_nk3 = m->packed_nk3 + 2 * onk;
+          ph.bias = c.bias; ph.w_nk = m->packed_nk + onk; ph.w_nk3 = m->packed_nk3 + 2 * onk; ph.wscale3 = c.wscale3;
           onk += align_up((size_t)c.Co * 4 * c.Ci, 512);
           VT_CUDA(launch_pack_w_collapsed(w, ph.w_nk, c.Co, c.Co, c.Ci, 1, 3, 3, id1, py == 0 ? lo : hi, px == 0 ? lo : hi, 1, 2, 2, s));
-          VT_CUDA(launch_pack_w_collapsed(w, ph.w_nk3, c.Co, c.Co, c.Ci, 1, 3, 3, id1, py == 0 ? lo : hi, px == 0 ? lo : hi, 1, 2, 2, s, true));
+          VT_CUDA(launch_pack_w_collapsed(w, ph.w_nk3, c.Co, c.Co, c.Ci, 1, 3, 3, id1, py == 0 ? lo : hi, px == 0 ? lo : hi, 1, 2, 2, s, c.wscale3));
         }
     }
     if (lv.has_tup_phase) {
@@ -1350,11 +1372,11 @@ int32_t vt_model_finalize(vt_model* m, void* stream) {
         ConvW& ph = lv.tup_ph[pt];
         ph = ConvW();
         ph.Co = c.Co; ph.Ci = c.Ci; ph.kt = 2; ph.kh = 3; ph.kw = 3; ph.Co_pad = c.Co; ph.Kpad = 18 * c.Ci;
-        ph.bias = c.bias; ph.w_nk = m->packed_nk + onk; ph.w_nk3 = m->packed_nk3 + 2 * onk;
+        ph.bias = c.bias; ph.w_nk = m->packed_nk + onk; ph.w_nk3 = m->packed_nk3 + 2 * onk; ph.wscale3 = c.wscale3;
         onk += align_up((size_t)c.Co * 18 * c.Ci, 512);
         // even frames t'=2i read x'[2i-2..2i] = x[i-1],x[i-1],x[i]; odd frames read x[i-1],x[i],x[i]
         VT_CUDA(launch_pack_w_collapsed(w, ph.w_nk, c.Co, c.Co, c.Ci, 3, 3, 3, pt == 0 ? hi : lo, id3, id3, 2, 3, 3, s));
-        VT_CUDA(launch_pack_w_collapsed(w, ph.w_nk3, c.Co, c.Co, c.Ci, 3, 3, 3, pt == 0 ? hi : lo, id3, id3, 2, 3, 3, s, true));
+        VT_CUDA(launch_pack_w_collapsed(w, ph.w_nk3, c.Co, c.Co, c.Ci, 3, 3, 3, pt == 0 ? hi : lo, id3, id3, 2, 3, 3, s, c.wscale3));
       }
     }
   }
@@ -1365,7 +1387,7 @@ int32_t vt_model_finalize(vt_model* m, void* stream) {
       c.w_stem = m->packed_stem;
       c.w_stem3 = m->packed_stem + (size_t)c.Co * 128;
       VT_CUDA(launch_pack_w_nk_bf16(m->pool + m->params[c.pw].offset, c.w_stem, c.Co, c.Co, c.Ci, 27, 128, s));
-      VT_CUDA(launch_pack_w_nk_bf16(m->pool + m->params[c.pw].offset, c.w_stem3, c.Co, c.Co, c.Ci, 27, 128, s, true));
+      VT_CUDA(launch_pack_w_nk_bf16(m->pool + m->params[c.pw].offset, c.w_stem3, c.Co, c.Co, c.Ci, 27, 128, s, c.wscale3));
     }
   }
   {
@@ -1496,14 +1518,19 @@ int32_t vt_decode(vt_model* m, int32_t precision, const void* z, int32_t from_in
   vt_chunk_state one; one.m = m; one.persist = false; one.first = true; one.is_decoder = true;
   if (m->desc.version == 1) ex.ck = &one;
   const float* zf = (const float*)z;
+  bool idx_in_producer = false;
   if (from_indices) {
     if (m->desc.regularizer != VT_REG_FSQ) return fail(VT_ERR_INVALID, "decode_from_indices needs an FSQ model");
-    float* codes = (float*)ex.alloc((size_t)B * m->desc.z_channels * Tz * Hz * Wz * sizeof(float));
-    if (!ex.ok()) return ex.rc;
-    VT_CUDA(launch_fsq_indices_to_codes((const int*)z, m->desc.z_channels, m->desc.fsq_levels, (long long)Tz * Hz * Wz, B, codes, s));
-    zf = codes;
+    if (m->desc.version == 0) {
+      idx_in_producer = true;   // conv_in forms the codes from the tokens in its gather (no codes tensor)
+    } else {
+      float* codes = (float*)ex.alloc((size_t)B * m->desc.z_channels * Tz * Hz * Wz * sizeof(float));
+      if (!ex.ok()) return ex.rc;
+      VT_CUDA(launch_fsq_indices_to_codes((const int*)z, m->desc.z_channels, m->desc.fsq_levels, (long long)Tz * Hz * Wz, B, codes, s));
+      zf = codes;
+    }
   }
-  run_decoder(ex, zf, B, Tz, Hz, Wz, x_out);
+  run_decoder(ex, zf, B, Tz, Hz, Wz, x_out, idx_in_producer);
   return ex.rc;
 }
 
@@ -1849,6 +1876,20 @@ static inline DType act_type(int precision) {
   return precision == VT_PREC_FMA32 ? DT_F32 : (precision == VT_PREC_EXACT_TC ? DT_SPLIT : DT_BF16);
 }
 
+// power-of-two scale of the split copy of an operator's weight tensor (the model path does this once in vt_model_finalize)
+static int op_weight_scale(const float* w, long long n, float headroom, cudaStream_t s, float* scale) {
+  float* d_max = nullptr;
+  VT_CUDA(cudaMalloc(&d_max, sizeof(float)));
+  float h = 0.f;
+  cudaError_t e = launch_absmax(w, n, d_max, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&h, d_max, sizeof(float), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(d_max);
+  if (e != cudaSuccess) return fail(VT_ERR_CUDA, "weight scale: %s", cudaGetErrorString(e));
+  *scale = split_weight_scale(h, headroom);
+  return VT_OK;
+}
+
 // Shared body of vt_op_conv / vt_op_conv_ex: one convolution launch of the kernel the model path uses for that
 // precision, with temporary weight repacks.
 static int op_conv_impl(int precision, int force_simt, const vt_conv_desc* d, const vt_conv_ex* e, const void* x,
@@ -1917,7 +1958,13 @@ static int op_conv_impl(int precision, int force_simt, const vt_conv_desc* d, co
       return fail(VT_ERR_INVALID, "tcgen05 conv does not support this geometry: %s", d->Ci % 64 ? "Cin % 64 != 0" : conv_tc_last_error());
     const int Co_pad = (d->Co + 31) / 32 * 32;
     VT_CUDA(cudaMalloc(&wnk, (size_t)K * Co_pad * sizeof(bf16) * cw));
-    VT_CUDA(launch_pack_w_nk_bf16(w, wnk, d->Co, Co_pad, d->Ci, taps, K, s, ta == DT_SPLIT));
+    float wsc = 0.f;
+    if (ta == DT_SPLIT) {
+      int rc = op_weight_scale(w, (long long)d->Co * K, 1.0f, s, &wsc);
+      if (rc) { cudaFree(wnk); return rc; }
+      p.acc_scale = 1.0f / wsc;
+    }
+    VT_CUDA(launch_pack_w_nk_bf16(w, wnk, d->Co, Co_pad, d->Ci, taps, K, s, wsc));
     er = launch_conv_tc(p, (const bf16*)x, wnk, K, out, tout, s, 1, 0, lf.mode ? &lf : nullptr, reg);
   } else {
     VT_CUDA(cudaMalloc(&wkn, (size_t)K * d->Co * sizeof(float)));
@@ -1998,8 +2045,14 @@ int32_t vt_op_conv_stem(int32_t precision, const float* x, const float* w, const
   p.bias = bias;
   if (!conv_stem_supported(p)) return fail(VT_ERR_INVALID, "stem kernel does not take this geometry");
   bf16* wpk = nullptr;
+  float wsc = 0.f;
+  if (split) {
+    int rc = op_weight_scale(w, (long long)Co * Ci * 27, 1.0f, s, &wsc);
+    if (rc) return rc;
+    p.acc_scale = 1.0f / wsc;
+  }
   VT_CUDA(cudaMalloc(&wpk, (size_t)Co * 128 * 2 * sizeof(bf16)));
-  VT_CUDA(launch_pack_w_nk_bf16(w, wpk, Co, Co, Ci, 27, 128, s, split));
+  VT_CUDA(launch_pack_w_nk_bf16(w, wpk, Co, Co, Ci, 27, 128, s, wsc));
   cudaError_t er = launch_conv_stem(p, x, wpk, (bf16*)out, s);
   cudaError_t e2 = cudaStreamSynchronize(s);
   cudaFree(wpk);
@@ -2060,18 +2113,24 @@ int32_t vt_op_upsample_conv(int32_t precision, int32_t kind, const void* x, cons
   LevelW lv;
   const int id3[3] = {0, 1, 2}, id1[3] = {0, 0, 0};
   const int lo[3] = {0, 1, 1}, hi[3] = {0, 0, 1};
+  float wsc = 0.f;
+  if (split) {
+    int rcw = op_weight_scale(w, (long long)Co * Ci * (kind == 0 ? 9 : 27), 4.0f, s, &wsc);
+    if (rcw) { cudaFree(wp); return rcw; }
+  }
   for (int i = 0; i < nph; ++i) {
     ConvW& ph = kind == 0 ? lv.up_ph[i] : lv.tup_ph[i];
     ph = ConvW();
     ph.Co = Co; ph.Ci = Ci; ph.Co_pad = Co; ph.Kpad = taps2 * Ci; ph.bias = bias;
+    if (split) ph.wscale3 = wsc;
     bf16* dst = wp + per * i * (split ? 2 : 1);
     if (split) ph.w_nk3 = dst; else ph.w_nk = dst;
     if (kind == 0) {
       ph.kt = 1; ph.kh = 2; ph.kw = 2;
-      VT_CUDA(launch_pack_w_collapsed(w, dst, Co, Co, Ci, 1, 3, 3, id1, (i >> 1) == 0 ? lo : hi, (i & 1) == 0 ? lo : hi, 1, 2, 2, s, split));
+      VT_CUDA(launch_pack_w_collapsed(w, dst, Co, Co, Ci, 1, 3, 3, id1, (i >> 1) == 0 ? lo : hi, (i & 1) == 0 ? lo : hi, 1, 2, 2, s, wsc));
     } else {
       ph.kt = 2; ph.kh = 3; ph.kw = 3;
-      VT_CUDA(launch_pack_w_collapsed(w, dst, Co, Co, Ci, 3, 3, 3, i == 0 ? hi : lo, id3, id3, 2, 3, 3, s, split));
+      VT_CUDA(launch_pack_w_collapsed(w, dst, Co, Co, Ci, 3, 3, 3, i == 0 ? hi : lo, id3, id3, 2, 3, 3, s, wsc));
     }
   }
   lv.has_resample = kind == 0; lv.has_up_phase = kind == 0;

@@ -25,7 +25,8 @@ struct ConvW {
   int pw = -1, pb = -1;      // param indices (weight, bias)
   float* w_kn = nullptr;     // [K][Co] fp32
   bf16* w_nk = nullptr;      // [Co_pad][Kpad] bf16 (tcgen05 B operand), may be null
-  bf16* w_nk3 = nullptr;     // [Co_pad][hi(Kpad) | lo(Kpad)] bf16: split operand of the EXACT_TC (bf16x3) mode
+  bf16* w_nk3 = nullptr;     // [Co_pad][hi(Kpad) | lo(Kpad)] fp16 planes of w * wscale3: split operand of the EXACT_TC mode
+  float wscale3 = 1.f;       // power of two (kernels.h: split_weight_scale); the epilogue multiplies the accumulator by 1/wscale3
   int Kpad = 0;
   int Co_pad = 0;            // Cout rounded up to 32 (zero rows)
   bf16* w_stem = nullptr;    // [Co][128] bf16 (conv_stem.cu), only for the Cin<=4 stem

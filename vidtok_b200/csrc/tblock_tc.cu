@@ -469,6 +469,455 @@ __global__ void __launch_bounds__(kThreadsTb, 1) tblock_tc_kernel(const __grid_c
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Version 2: CTA pairs (cta_group::2), weights resident in shared memory.
+// The first version streams both convolutions' weight tiles through the operand ring for every frame (352 KB of L2 -> SM
+// traffic per 128-position frame against 3.6k cycles of tensor work) and serialises its TMA stores on one staging buffer:
+// measured 3.0-4.7 ms per block, no better than the two conv_tc launches it replaces.  Here
+//   * two CTAs of a cluster share every MMA (M = 256: each CTA's own 128-position strip; N = 128 split across the pair),
+//     so each CTA keeps only its 64-row half of W1 and W2: 2 convs x 3 taps x 2 chunks x 8 KB = 96 KB, loaded ONCE;
+//   * G2 runs in scatter form -- H[t] is multiplied into the accumulators of frames t, t+1 and t+2 (taps 2, 1, 0) as soon
+//     as it exists -- so ONE 32 KB H tile replaces the three-frame ring (TMEM: acc1 + 3 x acc2 = 512 columns);
+//   * the residual x[t] is added by the epilogue from global memory (no identity tiles in shared memory);
+//   * E2 double-buffers its store staging.
+// Per frame the operand ring now carries only the three n1 frames of G1 (96 KB), and the tensor pipe is the bound:
+//   MMA  : G1(t)  G2s(t-1)  G1(t+1)  G2s(t) ...      E1(t) normalises frame t while G2s(t-1) / G1(t+1) run.
+// Warp roles as above (0 producer, 1 MMA issuer -- leader CTA only --, 2 TMEM allocator, 3-6 E1, 7-10 E2).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kWTile = 64 * 128;        // one resident weight tile: 64 rows (this CTA's half of N) x 64 bf16
+constexpr int kASlots = 3;
+
+struct Tb2Params {
+  int B, T, H, W;
+  int BW, BH;
+  int tilesW, tilesH;
+  long long num_strips;      // strips of 128 positions; a pair takes strips 2p and 2p+1
+  const float* bias1;
+  const float* bias2;
+  const float* g2;
+  const float* b2;
+  int ln_out, ln_out_silu;
+  const float* g3;
+  const float* b3;
+  int store_stream;
+  const bf16* x;             // residual, read by the epilogue: dense [B,T,H,W,128]
+};
+struct Tb2Maps {
+  CUtensorMap n1, w1, w2, o, o2;
+};
+
+// cluster-scope arrive / wait for the barrier that publishes the H tile of BOTH CTAs to the leader's MMA issuer
+__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(rank) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 8000000000LL) __trap();
+  }
+}
+
+__global__ void __launch_bounds__(kThreadsTb, 1) tblock2_tc_kernel(const __grid_constant__ Tb2Maps maps, const Tb2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();                  // 0 = leader
+  // [resident W: 12 x 8 KB][H: kKc x 16 KB][A ring: kASlots x 16 KB][store staging: 4 warps x 2 x 4 KB][barriers][constants]
+  const uint32_t w_base = smem_base;
+  const uint32_t h_base = w_base + 12u * kWTile;
+  const uint32_t a_base = h_base + kKc * kTile;
+  const uint32_t stg_base = a_base + kASlots * kTile;
+  const uint32_t bar_base = stg_base + 4u * 2u * 4096u;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kASlots + s); };
+  const uint32_t bar2 = bar_base + 16u * kASlots;
+  const uint32_t w_full = bar2;
+  const uint32_t a1_full = bar2 + 8, a1_empty = bar2 + 16, h_full = bar2 + 24, h_empty = bar2 + 32;
+  auto a2_full = [&](int s) { return bar2 + 40u + 8u * s; };
+  auto a2_empty = [&](int s) { return bar2 + 64u + 8u * s; };
+  const uint32_t tmem_slot = bar2 + 88u;
+  const uint32_t const_base = bar2 + 128u;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+  float* cst = reinterpret_cast<float*>(smem_gen + (const_base - smem_base));   // bias1 | g2 | b2 | bias2 | g3 | b3
+
+  for (int i = threadIdx.x; i < kC; i += kThreadsTb) {
+    cst[i] = p.bias1 ? p.bias1[i] : 0.f;
+    cst[kC + i] = 0.5f * p.g2[i];          // SiLU in tanh form works on y/2
+    cst[2 * kC + i] = 0.5f * p.b2[i];
+    cst[3 * kC + i] = p.bias2 ? p.bias2[i] : 0.f;
+    const float sc = p.ln_out_silu ? 0.5f : 1.0f;
+    cst[4 * kC + i] = p.ln_out ? sc * p.g3[i] : 0.f;
+    cst[5 * kC + i] = p.ln_out ? sc * p.b3[i] : 0.f;
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&maps.n1); prefetch_tmap(&maps.w1); prefetch_tmap(&maps.w2); prefetch_tmap(&maps.o);
+    if (p.ln_out) prefetch_tmap(&maps.o2);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kASlots; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(w_full, 1);
+    mbar_init(a1_full, 1); mbar_init(a1_empty, 8);     // E1 warps of both CTAs arrive on the leader's barrier
+    mbar_init(h_full, 8); mbar_init(h_empty, 1);
+    for (int s = 0; s < 3; ++s) { mbar_init(a2_full(s), 1); mbar_init(a2_empty(s), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  constexpr uint32_t kTmemCols = 512;   // acc1 | acc2[3]
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const long long pair0 = blockIdx.x >> 1, pair_step = gridDim.x >> 1;
+  const long long num_pairs = (p.num_strips + 1) / 2;
+  // strip of THIS CTA inside pair tile `pt`; a missing second strip (odd strip count) is placed at batch index B: its TMA
+  // boxes are out of bounds (zero fill on loads, nothing stored) and its epilogue rows are marked invalid
+  auto decode = [&](long long pt, int& b, int& h0, int& w0, bool& live) {
+    const long long strip = 2 * pt + rank;
+    live = strip < p.num_strips;
+    const long long sidx = live ? strip : 0;
+    const int tw = (int)(sidx % p.tilesW);
+    long long m = sidx / p.tilesW;
+    const int th = (int)(m % p.tilesH);
+    b = live ? (int)(m / p.tilesH) : p.B;
+    h0 = th * p.BH;
+    w0 = tw * p.BW;
+  };
+  const int T = p.T;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs: own strip, own half of the weights) =====================
+    const bool el = elect_one();
+    if (el) {
+      if (rank == 0) mbar_expect_tx(w_full, 2u * 12u * kWTile);
+      for (int c = 0; c < 2; ++c)
+        for (int a = 0; a < 3; ++a)
+          for (int kc = 0; kc < kKc; ++kc)
+            tma_load_3d_2sm(w_base + (uint32_t)((c * 3 + a) * kKc + kc) * kWTile, c == 0 ? &maps.w1 : &maps.w2, w_full,
+                            a * kC + kc * 64, rank * 64, 0);
+    }
+    int slot = 0;
+    uint32_t phase = 0;
+    for (long long pt = pair0; pt < num_pairs; pt += pair_step) {
+      int b, h0, w0;
+      bool live;
+      decode(pt, b, h0, w0, live);
+      for (int t = 0; t < T; ++t) {
+        for (int a = 0; a < 3; ++a) {
+          const int tv = t - 2 + a;
+          if (tv < 0) continue;
+          for (int kc = 0; kc < kKc; ++kc) {
+            mbar_wait(empty_bar(slot), phase ^ 1u);
+            if (el) {
+              if (rank == 0) mbar_expect_tx(full_bar(slot), 2u * kTile);
+              tma_load_5d_2sm(a_base + slot * kTile, &maps.n1, full_bar(slot), kc * 64, w0, h0, tv, b);
+            }
+            if (++slot == kASlots) { slot = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA) =====================
+    if (rank == 0) {
+      const bool el = elect_one();
+      const uint32_t idesc = make_idesc(kC, 256);
+      const uint32_t hi_d = 64u | (1u << 14) | (2u << 29);
+      auto desc_lo = [&](uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | 0x10000u; };
+      auto mma4 = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t acc) {
+#pragma unroll
+        for (uint32_t j = 0; j < 8u; j += 2u) umma_f16_2sm_lohi(d, a_lo + j, hi_d, b_lo + j, hi_d, idesc, j == 0 ? acc : 1u);
+      };
+      auto wres = [&](int c, int a, int kc) { return desc_lo(w_base + (uint32_t)((c * 3 + a) * kKc + kc) * kWTile); };
+      int slot = 0;
+      uint32_t phase = 0;
+      long long f1 = 0, f2 = 0;    // global frame counters of G1 / G2s (barrier phases run across strips)
+      mbar_wait(w_full, 0);
+      tc_fence_after();
+      for (long long pt = pair0; pt < num_pairs; pt += pair_step) {
+        // G2s(u): H[u] (just normalised) into the accumulators of frames u (tap 2), u+1 (tap 1), u+2 (tap 0)
+        auto g2s = [&](int u) {
+          mbar_wait_cluster(h_full, (uint32_t)(f2 & 1));
+          tc_fence_after();
+          for (int j = 0; j < 3; ++j) {
+            if (u + j >= T) break;
+            const long long g = f2 + j;                       // global index of the target frame
+            const int as = (int)(g % 3);
+            const bool first = (j == 2) || (u == 0);          // first contribution to that frame's accumulator
+            if (first && g >= 3) {
+              mbar_wait(a2_empty(as), (uint32_t)(((g / 3) - 1) & 1));   // E2 has read the previous occupant (frame g-3)
+              tc_fence_after();
+            }
+            if (el) {
+              const uint32_t d = tmem_base + (uint32_t)kC + (uint32_t)as * kC;
+              for (int kc = 0; kc < kKc; ++kc) mma4(d, desc_lo(h_base + kc * kTile), wres(1, 2 - j, kc), (first && kc == 0) ? 0u : 1u);
+              if (j == 0) umma_commit_2sm(a2_full(as));       // frame u is complete
+            }
+          }
+          if (el) umma_commit_2sm(h_empty);
+          ++f2;
+        };
+        for (int t = 0; t < T; ++t) {
+          mbar_wait(a1_empty, (uint32_t)((f1 & 1) ^ 1));
+          tc_fence_after();
+          uint32_t accum = 0;
+          for (int a = 0; a < 3; ++a) {
+            if (t - 2 + a < 0) continue;
+            for (int kc = 0; kc < kKc; ++kc) {
+              mbar_wait(full_bar(slot), phase);
+              tc_fence_after();
+              if (el) {
+                mma4(tmem_base, desc_lo(a_base + slot * kTile), wres(0, a, kc), accum);
+                umma_commit_2sm(empty_bar(slot));
+              }
+              accum = 1;
+              if (++slot == kASlots) { slot = 0; phase ^= 1u; }
+            }
+          }
+          if (el) umma_commit_2sm(a1_full);
+          ++f1;
+          if (t >= 1) g2s(t - 1);
+        }
+        g2s(T - 1);
+      }
+    }
+  } else if (warp >= 3 && warp < 7) {
+    // ===================== E1: h = acc1 + b1 -> H = bf16(silu(LN2(h))) =====================
+    const int q = warp & 3;
+    const int rr = q * 32 + lane;
+    const int swz = lane & 7;
+    const float* bias1 = cst;
+    const float* gam = cst + kC;
+    const float* bet = cst + 2 * kC;
+    uint8_t* hrow = smem_gen + (h_base - smem_base) + (uint32_t)rr * 128u;
+    long long f = 0;
+    for (long long pt = pair0; pt < num_pairs; pt += pair_step) {
+      for (int t = 0; t < T; ++t, ++f) {
+        mbar_wait(a1_full, (uint32_t)(f & 1));
+        tc_fence_after();
+        const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint64_t lsum2 = 0ull, lsq2 = 0ull;
+        uint32_t keep[kC / 2];
+#pragma unroll
+        for (int c = 0; c < kC / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tb + (uint32_t)(c * 32), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const ulonglong2 bv = *reinterpret_cast<const ulonglong2*>(bias1 + c * 32 + g * 4);
+            const uint64_t a0 = add2(pk2(__uint_as_float(v[g * 4 + 0]), __uint_as_float(v[g * 4 + 1])), bv.x);
+            const uint64_t a1 = add2(pk2(__uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3])), bv.y);
+            lsum2 = add2(lsum2, add2(a0, a1));
+            lsq2 = fma2(a0, a0, lsq2);
+            lsq2 = fma2(a1, a1, lsq2);
+            float f0, f1, f2_, f3;
+            upk2(a0, f0, f1);
+            upk2(a1, f2_, f3);
+            keep[c * 16 + g * 2] = pack_bf16x2(f0, f1);
+            keep[c * 16 + g * 2 + 1] = pack_bf16x2(f2_, f3);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(a1_empty, 0);
+        float lsum, lsq;
+        {
+          float a, b;
+          upk2(lsum2, a, b); lsum = a + b;
+          upk2(lsq2, a, b); lsq = a + b;
+        }
+        const float mean = lsum * (1.0f / kC);
+        float var = fmaf(-mean, mean, lsq * (1.0f / kC));
+        var = var < 0.f ? 0.f : var;
+        const float rstd = rsqrtf(var + 1e-6f);
+        const float nmr = -mean * rstd;
+        const uint64_t rstd2 = pk2(rstd, rstd), nmr2 = pk2(nmr, nmr);
+        uint32_t o[kC / 2];
+#pragma unroll
+        for (int w2 = 0; w2 < kC / 4; ++w2) {   // 4 channels per step
+          const int ci = w2 * 4;
+          const ulonglong2 gv = *reinterpret_cast<const ulonglong2*>(gam + ci);
+          const ulonglong2 bv = *reinterpret_cast<const ulonglong2*>(bet + ci);
+          const uint32_t a2 = keep[ci / 2], b2 = keep[ci / 2 + 1];
+          uint64_t y0 = fma2(fma2(pk2(bf16_lo(a2), bf16_hi(a2)), rstd2, nmr2), gv.x, bv.x);
+          uint64_t y1 = fma2(fma2(pk2(bf16_lo(b2), bf16_hi(b2)), rstd2, nmr2), gv.y, bv.y);
+          float h0, h1, h2, h3;
+          upk2(y0, h0, h1);
+          upk2(y1, h2, h3);
+          y0 = fma2(y0, pk2(tanh_approx(h0), tanh_approx(h1)), y0);
+          y1 = fma2(y1, pk2(tanh_approx(h2), tanh_approx(h3)), y1);
+          float o0, o1, o2, o3;
+          upk2(y0, o0, o1);
+          upk2(y1, o2, o3);
+          o[ci / 2] = pack_bf16x2(o0, o1);
+          o[ci / 2 + 1] = pack_bf16x2(o2, o3);
+        }
+        // the single H tile: free once G2s(f-1) has consumed the previous frame
+        if (f >= 1) mbar_wait(h_empty, (uint32_t)((f - 1) & 1));
+#pragma unroll
+        for (int kc = 0; kc < kKc; ++kc)
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<uint4*>(hrow + kc * kTile + ((g ^ swz) << 4)) =
+                make_uint4(o[kc * 32 + g * 4], o[kc * 32 + g * 4 + 1], o[kc * 32 + g * 4 + 2], o[kc * 32 + g * 4 + 3]);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote_release(h_full, 0);
+      }
+    }
+  } else if (warp >= 7) {
+    // ===================== E2: out = acc2 + b2 + x (TMA store) [+ out2 = act(LN_next(out))] =====================
+    const int q = warp & 3;
+    const int rr = q * 32 + lane;
+    const int swz = lane & 7;
+    const float* bias2 = cst + 3 * kC;
+    const float* gam = cst + 4 * kC;
+    const float* bet = cst + 5 * kC;
+    const uint32_t wstg = stg_base + (uint32_t)(warp - 7) * 8192u;
+    uint8_t* wstg_gen = smem_gen + (stg_base - smem_base) + (uint32_t)(warp - 7) * 8192u;
+    const int row0 = q * 32;
+    const int qw0 = row0 % p.BW, qh0 = row0 / p.BW;
+    const int dw = rr % p.BW, dh = rr / p.BW;
+    uint32_t nstore = 0;
+    long long f = 0;
+    for (long long pt = pair0; pt < num_pairs; pt += pair_step) {
+      int b, h0, w0;
+      bool live;
+      decode(pt, b, h0, w0, live);
+      const bf16* xrow0 = p.x + ((((long long)(live ? b : 0) * T) * p.H + (h0 + dh)) * p.W + (w0 + dw)) * kC;
+      const long long xframe = (long long)p.H * p.W * kC;
+      for (int t = 0; t < T; ++t, ++f) {
+        const int as = (int)(f % 3);
+        auto put64 = [&](const uint32_t* pk, const CUtensorMap* m, int c0) {
+          const uint32_t bsel = nstore & 1u;
+          if (lane == 0) tma_store_wait_read1();   // the store before the previous one (same buffer) has been read
+          __syncwarp();
+          uint8_t* my = wstg_gen + bsel * 4096u + (uint32_t)lane * 128u;
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<uint4*>(my + ((g ^ swz) << 4)) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (p.store_stream) tma_store_5d_stream(m, wstg + bsel * 4096u, c0, w0 + qw0, h0 + qh0, t, b);
+            else tma_store_5d(m, wstg + bsel * 4096u, c0, w0 + qw0, h0 + qh0, t, b);
+            tma_store_commit();
+          }
+          ++nstore;
+        };
+        // residual row of this thread's position: all 16 loads are issued BEFORE the wait for the accumulator, so their
+        // latency hides behind the frame period (issued one by one between the TMEM loads they cost ~1 us each: 12 us per frame)
+        const bf16* xr = xrow0 + (long long)t * xframe;
+        uint4 xv[kC / 8];
+#pragma unroll
+        for (int k = 0; k < kC / 8; ++k) xv[k] = live ? __ldg(reinterpret_cast<const uint4*>(xr) + k) : make_uint4(0, 0, 0, 0);
+        mbar_wait(a2_full(as), (uint32_t)((f / 3) & 1));
+        tc_fence_after();
+        const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)kC + (uint32_t)as * kC;
+        uint64_t lsum2 = 0ull, lsq2 = 0ull;
+        uint32_t keep[kC / 2];
+#pragma unroll
+        for (int i = 0; i < kKc; ++i) {
+#pragma unroll
+          for (int hc = 0; hc < 2; ++hc) {
+            uint32_t v[32];
+            tmem_ld32(tb + (uint32_t)(i * 64 + hc * 32), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {   // 8 channels per step: one 16-byte residual load
+              float rv[8];
+              unpack8(xv[i * 8 + hc * 4 + g], rv);
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const ulonglong2 bv = *reinterpret_cast<const ulonglong2*>(bias2 + i * 64 + hc * 32 + g * 8 + h * 4);
+                uint64_t a0 = add2(pk2(__uint_as_float(v[g * 8 + h * 4 + 0]), __uint_as_float(v[g * 8 + h * 4 + 1])), bv.x);
+                uint64_t a1 = add2(pk2(__uint_as_float(v[g * 8 + h * 4 + 2]), __uint_as_float(v[g * 8 + h * 4 + 3])), bv.y);
+                a0 = add2(a0, pk2(rv[h * 4 + 0], rv[h * 4 + 1]));
+                a1 = add2(a1, pk2(rv[h * 4 + 2], rv[h * 4 + 3]));
+                if (p.ln_out) {
+                  lsum2 = add2(lsum2, add2(a0, a1));
+                  lsq2 = fma2(a0, a0, lsq2);
+                  lsq2 = fma2(a1, a1, lsq2);
+                }
+                float f0, f1, f2_, f3;
+                upk2(a0, f0, f1);
+                upk2(a1, f2_, f3);
+                keep[i * 32 + hc * 16 + g * 4 + h * 2] = pack_bf16x2(f0, f1);
+                keep[i * 32 + hc * 16 + g * 4 + h * 2 + 1] = pack_bf16x2(f2_, f3);
+              }
+            }
+          }
+          if (i == kKc - 1) {   // the accumulator has been read completely
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(a2_empty(as), 0);
+          }
+          put64(&keep[i * 32], &maps.o, i * 64);
+        }
+        if (p.ln_out) {
+          float lsum, lsq;
+          {
+            float a, b2_;
+            upk2(lsum2, a, b2_); lsum = a + b2_;
+            upk2(lsq2, a, b2_); lsq = a + b2_;
+          }
+          const float mean = lsum * (1.0f / kC);
+          float var = fmaf(-mean, mean, lsq * (1.0f / kC));
+          var = var < 0.f ? 0.f : var;
+          const float rstd = rsqrtf(var + 1e-6f);
+          const float nmr = -mean * rstd;
+          const uint64_t rstd2 = pk2(rstd, rstd), nmr2 = pk2(nmr, nmr);
+#pragma unroll
+          for (int i = 0; i < kKc; ++i) {
+            uint32_t o[32];
+#pragma unroll
+            for (int g = 0; g < 16; ++g) {
+              const ulonglong2 gv = *reinterpret_cast<const ulonglong2*>(gam + i * 64 + g * 4);
+              const ulonglong2 bv = *reinterpret_cast<const ulonglong2*>(bet + i * 64 + g * 4);
+              const uint32_t a2 = keep[i * 32 + 2 * g], b2 = keep[i * 32 + 2 * g + 1];
+              uint64_t y0 = fma2(fma2(pk2(bf16_lo(a2), bf16_hi(a2)), rstd2, nmr2), gv.x, bv.x);
+              uint64_t y1 = fma2(fma2(pk2(bf16_lo(b2), bf16_hi(b2)), rstd2, nmr2), gv.y, bv.y);
+              if (p.ln_out_silu) {
+                float h0_, h1, h2, h3;
+                upk2(y0, h0_, h1);
+                upk2(y1, h2, h3);
+                y0 = fma2(y0, pk2(tanh_approx(h0_), tanh_approx(h1)), y0);
+                y1 = fma2(y1, pk2(tanh_approx(h2), tanh_approx(h3)), y1);
+              }
+              float o0, o1, o2, o3;
+              upk2(y0, o0, o1);
+              upk2(y1, o2, o3);
+              o[2 * g] = pack_bf16x2(o0, o1);
+              o[2 * g + 1] = pack_bf16x2(o2, o3);
+            }
+            put64(o, &maps.o2, i * 64);
+          }
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
 __global__ void fill_identity256_kernel(bf16* e) {
   const int r = blockIdx.x, c = threadIdx.x;
   e[r * 256 + c] = __float2bfloat16_rn(r == c ? 1.0f : 0.0f);
@@ -492,6 +941,14 @@ EncodeTiledFn tb_get_encode() {
 
 thread_local std::string g_tb_err;
 
+// VT_TBLOCK: 0 = off (two conv_tc launches per block), 1 = version 1 (single CTA, streamed weights), 2 = version 2 (CTA
+// pairs, resident weights; default)
+int tblock_variant() {
+  static int env = -1;
+  if (env < 0) { const char* e = getenv("VT_TBLOCK"); env = e ? atoi(e) : 2; }
+  return env;
+}
+
 bool strip_box(int H, int W, int& BW, int& BH) {
   BW = 128;
   while (BW > 1 && (BW > W || W % BW != 0)) BW >>= 1;
@@ -500,15 +957,92 @@ bool strip_box(int H, int W, int& BW, int& BH) {
   return H % BH == 0 && BH <= 256;
 }
 
+cudaError_t launch_tblock2(const bf16* n1, const bf16* x, const bf16* w1, const float* bias1, const float* gamma2, const float* beta2,
+                           const bf16* w2, const float* bias2, bf16* out, bf16* out2, const float* gamma_out, const float* beta_out,
+                           bool out_silu, int B, int T, int H, int W, cudaStream_t s) {
+  EncodeTiledFn enc = tb_get_encode();
+  if (!enc) { g_tb_err = "cuTensorMapEncodeTiled unavailable"; return cudaErrorNotSupported; }
+  Tb2Params p;
+  memset(&p, 0, sizeof(p));
+  if (!strip_box(H, W, p.BW, p.BH)) { g_tb_err = "H x W not tileable"; return cudaErrorInvalidValue; }
+  p.B = B; p.T = T; p.H = H; p.W = W;
+  p.tilesW = W / p.BW; p.tilesH = H / p.BH;
+  p.num_strips = (long long)B * p.tilesH * p.tilesW;
+  p.bias1 = bias1; p.bias2 = bias2; p.g2 = gamma2; p.b2 = beta2;
+  p.ln_out = (out2 && gamma_out && beta_out) ? 1 : 0;
+  p.ln_out_silu = out_silu ? 1 : 0;
+  p.g3 = gamma_out; p.b3 = beta_out;
+  p.store_stream = ((double)B * T * H * W * kC * 2.0 > 256e6) ? 1 : 0;
+  p.x = x;
+  const size_t smem = 1024 + 12 * (size_t)kWTile + (size_t)kKc * kTile + (size_t)kASlots * kTile + 4 * 2 * 4096 + 16 * kASlots + 128 + 6 * kC * 4 + 256;
+  Tb2Maps maps;
+  auto enc_act = [&](CUtensorMap* m, const void* base, int bw, int bh) -> bool {
+    cuuint64_t dims[5] = {(cuuint64_t)kC, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)B};
+    cuuint64_t strides[4] = {(cuuint64_t)kC * 2, (cuuint64_t)W * kC * 2, (cuuint64_t)H * W * kC * 2, (cuuint64_t)T * H * W * kC * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { g_tb_err = "cuTensorMapEncodeTiled(activation) failed: " + std::to_string((int)r); return false; }
+    return true;
+  };
+  auto enc_w = [&](CUtensorMap* m, const void* base) -> bool {   // [128][3*128] bf16, box = 64 channels x 64 rows (one CTA's half of N)
+    cuuint64_t dims[3] = {(cuuint64_t)(3 * kC), (cuuint64_t)kC, 1};
+    cuuint64_t strides[2] = {(cuuint64_t)(3 * kC) * 2, (cuuint64_t)(3 * kC) * kC * 2};
+    cuuint32_t box[3] = {64, 64, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { g_tb_err = "cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r); return false; }
+    return true;
+  };
+  static bool attr_set[64] = {false};
+  static int sms[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) { g_tb_err = "device index out of range"; return cudaErrorInvalidValue; }
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(tblock2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e != cudaSuccess) { g_tb_err = "cudaFuncSetAttribute(smem)"; return e; }
+    attr_set[dev] = true;
+    cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (sms[dev] <= 0) sms[dev] = 148;
+  }
+  const int qw = p.BW < 32 ? p.BW : 32, qh = 32 / qw;
+  if (!enc_act(&maps.n1, n1, p.BW, p.BH) || !enc_act(&maps.o, out, qw, qh)) return cudaErrorInvalidValue;
+  maps.o2 = maps.o;
+  if (p.ln_out && !enc_act(&maps.o2, out2, qw, qh)) return cudaErrorInvalidValue;
+  if (!enc_w(&maps.w1, w1) || !enc_w(&maps.w2, w2)) return cudaErrorInvalidValue;
+  const long long num_pairs = (p.num_strips + 1) / 2, max_pairs = sms[dev] / 2;
+  const unsigned grid = 2u * (unsigned)(num_pairs < max_pairs ? num_pairs : max_pairs);
+  const double M = (double)B * T * H * W;
+  char det[96] = "";
+  if (prof_enabled()) snprintf(det, sizeof(det), "2x k311 %d->%d @%dx%dx%d strip%dx%d pair%s", kC, kC, T, H, W, p.BH, p.BW, p.ln_out ? " ln" : "");
+  ProfScope _ps("tblock_tc", 2.0 * 2.0 * M * 3 * kC * kC, 2.0 * M * kC * (3.0 + (p.ln_out ? 1.0 : 0.0)), s, det);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreadsTb);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tblock2_tc_kernel, maps, p);
+  count_launch();
+  return e != cudaSuccess ? e : cudaGetLastError();
+}
+
 }  // namespace
 
 const char* tblock_tc_last_error() { return g_tb_err.c_str(); }
 
 bool tblock_tc_supported(int B, int T, int H, int W, int C, bool planning) {
   g_tb_err.clear();
-  static int env = -1;   // VT_TBLOCK=0 switches the fused temporal block off (A/B measurements)
-  if (env < 0) { const char* e = getenv("VT_TBLOCK"); env = e ? atoi(e) : 1; }
-  if (!env) { g_tb_err = "disabled (VT_TBLOCK=0)"; return false; }
+  if (!tblock_variant()) { g_tb_err = "disabled (VT_TBLOCK=0)"; return false; }
   if (C != kC) { g_tb_err = "C != 128"; return false; }
   if (B <= 0 || T <= 0) { g_tb_err = "empty"; return false; }
   int BW, BH;
@@ -523,6 +1057,8 @@ cudaError_t launch_tblock_tc(const bf16* n1, const bf16* x, const bf16* w1, cons
                              const float* beta2, const bf16* w2, const float* bias2, bf16* out, bf16* out2,
                              const float* gamma_out, const float* beta_out, bool out_silu, int B, int T, int H, int W,
                              cudaStream_t s) {
+  if (tblock_variant() >= 2)
+    return launch_tblock2(n1, x, w1, bias1, gamma2, beta2, w2, bias2, out, out2, gamma_out, beta_out, out_silu, B, T, H, W, s);
   EncodeTiledFn enc = tb_get_encode();
   if (!enc) { g_tb_err = "cuTensorMapEncodeTiled unavailable"; return cudaErrorNotSupported; }
   TbParams p;

@@ -10,7 +10,7 @@ include/vidtok_b200.h.  There is no PyTorch/CPU fallback: a model that is not on
 
 Precision: the reference scripts run fp32 by default and bf16/fp16 under `--precision autocast`
 (scripts/inference_evaluate.py:77-79,137).  Mirroring that, `model.precision = None` (default) selects
-  * "exact"  -- fp32-class results on the tcgen05 tensor cores (bf16x3 split operands, fp32 LayerNorm/SiLU): the
+  * "exact"  -- fp32-class results on the tcgen05 tensor cores (fp16 hi|lo split operands x 3 MMAs, fp32 LayerNorm/SiLU): the
                 parity mode (1e-3 max-abs, FSQ codes equal), unless
   * "bf16"   -- torch.autocast is active (bf16 activations/weights on tcgen05, fp32 accumulate: the throughput mode;
                 outputs are returned in the autocast dtype like the reference's; an fp16 autocast region also
