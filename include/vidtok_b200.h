@@ -83,6 +83,9 @@ typedef struct vt_model_desc {
   int32_t fsq_num_levels;
   int32_t fsq_levels[VT_MAX_LEVELS];
   int32_t kl_sample;              /* DiagonalGaussianRegularizer(sample=...) regularizers.py:75 */
+  int32_t noncausal;              /* 1 = the non-causal family (vidtok/modules/model_3dnoncausal.py: Encoder3D / Decoder3D; v1.0
+                                     only): symmetric zero padding in time, plain nn.Conv3d/1d checkpoint keys, no front
+                                     padding of the clip, no dropped frames */
 } vt_model_desc;
 
 typedef struct vt_model vt_model;

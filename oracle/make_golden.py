@@ -33,8 +33,12 @@ GOLDEN_DIR = os.environ.get("VIDTOK_GOLDEN_OUT", os.path.join(ROOT, "tests", "go
 
 
 def model_yaml(version="v1_0", reg="kl", ch=16, ch_mult=(1, 2, 4, 4), z=4, norm="layernorm", interp=None,
-               levels=(8, 8, 8, 8, 8)):
+               levels=(8, 8, 8, 8, 8), causal=True):
     mod = "model_3dcausal" + ("_v1_1" if version == "v1_1" else "")
+    enc_cls, dec_cls = "EncoderCausal3DPadding", "DecoderCausal3DPadding"
+    if not causal:   # configs/vidtok_kl_noncausal_488_4chn.yaml:12,30
+        assert version == "v1_0"
+        mod, enc_cls, dec_cls = "model_3dnoncausal", "Encoder3D", "Decoder3D"
     eng = "autoencoder" + ("_v1_1" if version == "v1_1" else "")
     ep = dict(double_z=(reg == "kl"), z_channels=z, in_channels=3, out_ch=3, ch=ch, ch_mult=list(ch_mult),
               time_downsample_factor=4, num_res_blocks=2, dropout=0.0, use_checkpoint=False,
@@ -51,8 +55,8 @@ def model_yaml(version="v1_0", reg="kl", ch=16, ch_mult=(1, 2, 4, 4), z=4, norm=
         "target": f"vidtok.models.{eng}.AutoencodingEngine",
         "params": {
             "monitor": "val/rec_loss", "mode": "min", "ignore_keys": [],
-            "encoder_config": {"target": f"vidtok.modules.{mod}.EncoderCausal3DPadding", "params": ep},
-            "decoder_config": {"target": f"vidtok.modules.{mod}.DecoderCausal3DPadding",
+            "encoder_config": {"target": f"vidtok.modules.{mod}.{enc_cls}", "params": ep},
+            "decoder_config": {"target": f"vidtok.modules.{mod}.{dec_cls}",
                                "params": "${model.params.encoder_config.params}"},
             "regularizer_config": rc,
             "loss_config": {"target": "vidtok.modules.losses.GeneralLPIPSWithDiscriminator"},
@@ -62,6 +66,10 @@ def model_yaml(version="v1_0", reg="kl", ch=16, ch_mult=(1, 2, 4, 4), z=4, norm=
 
 # name -> (yaml kwargs, input shape (B,T,H,W), tiling (chunk or None), what to store)
 CASES = {
+    # non-causal family (model_3dnoncausal.py; 16-frame clips, configs/vidtok_kl_noncausal_488_4chn.yaml)
+    "tiny_kl_nc": (dict(causal=False), (1, 16, 32, 32), None, "full"),
+    "tiny_fsq_nc": (dict(causal=False, reg="fsq", z=5), (2, 16, 32, 32), None, "full"),
+    "mid_kl_nc": (dict(causal=False, ch=64), (1, 16, 64, 64), None, "full"),
     "tiny_kl_v10": (dict(), (1, 17, 32, 32), None, "full"),
     "tiny_kl_v10_t8": (dict(), (2, 8, 32, 32), None, "full"),
     "tiny_fsq_v10": (dict(reg="fsq", z=5), (2, 17, 32, 32), None, "full"),
@@ -118,7 +126,7 @@ def run_case(name: str):
 
     report = {"z": maxabs(z_ref, z_o), "dec": maxabs(dec_ref, dec_o)}
     assert dec_ref.shape == dec_o.shape, (dec_ref.shape, dec_o.shape)
-    if T % 4 == 1 or ykw.get('version') == 'v1_1':
+    if T % 4 == 1 or ykw.get('version') == 'v1_1' or not ykw.get('causal', True):
         assert dec_ref.shape == x.shape, (dec_ref.shape, x.shape)
     assert report["z"] <= 2e-5 and report["dec"] <= 2e-5, report
     if "indices" in log_ref:

@@ -49,6 +49,7 @@ class OracleCfg:
     regularizer: str = "kl"  # "kl" | "fsq"
     fsq_levels: Tuple[int, ...] = (8, 8, 8, 8, 8)
     kl_sample: bool = True
+    causal: bool = True  # False: vidtok.modules.model_3dnoncausal.Encoder3D / Decoder3D (v1.0 only)
 
     @property
     def nres(self) -> int:
@@ -81,7 +82,10 @@ def cfg_from_model_yaml(model_cfg: dict) -> OracleCfg:
         spatial_us=ep.get("spatial_us"), tempo_us=ep.get("tempo_us"),
         version="v1_1" if "v1_1" in tgt else "v1_0",
         interpolation_mode=ep.get("interpolation_mode", "nearest"),
+        causal="noncausal" not in model_cfg["params"]["encoder_config"]["target"],
     )
+    if not kw["causal"]:   # model_3dnoncausal.py:335,515: fixed schedules, no overrides
+        kw["spatial_ds"] = kw["tempo_ds"] = kw["spatial_us"] = kw["tempo_us"] = None
     if reg["target"].endswith("FSQRegularizer"):
         kw["regularizer"] = "fsq"
         kw["fsq_levels"] = tuple(reg["params"]["levels"])
@@ -304,6 +308,123 @@ def time_upsample(sd, key: str, x: Tensor, cfg: OracleCfg, st, num_temp_upsample
 
 
 # --------------------------------------------------------------------------------------------------
+# non-causal family (vidtok/modules/model_3dnoncausal.py): same stacks, symmetric zero padding in time, plain
+# nn.Conv3d / nn.Conv1d (checkpoint keys without the inner `.conv`), no front padding / frame dropping
+# --------------------------------------------------------------------------------------------------
+def nc_conv3d(sd, key: str, x: Tensor, stride=(1, 1, 1), padding=None) -> Tensor:
+    """nn.Conv3d(k, padding=(k-1)/2): model_3dnoncausal.py:20-23,271,276,348,430,522,600."""
+    w, b = sd[key + ".weight"], sd[key + ".bias"]
+    if padding is None:
+        padding = tuple((k - 1) // 2 for k in w.shape[2:])
+    return F.conv3d(x, w, b, stride=stride, padding=padding)
+
+
+def nc_conv1d(sd, key: str, x: Tensor) -> Tensor:
+    """nn.Conv1d(k=3, padding=1) on `(b h w) c t` (model_3dnoncausal.py:203,208; rearranges of model_3dcausal.py:20,22)."""
+    w, b = sd[key + ".weight"], sd[key + ".bias"]
+    B, C, T, H, W = x.shape
+    y = x.permute(0, 3, 4, 1, 2).reshape(B * H * W, C, T)
+    y = F.conv1d(y, w, b, padding=1)
+    return y.reshape(B, H, W, -1, T).permute(0, 3, 4, 1, 2)
+
+
+def nc_norm(sd, key: str, x: Tensor, cfg: OracleCfg, mode: str) -> Tensor:
+    """Normalize() as the non-causal call sites apply it.  layernorm: per position over C everywhere
+    (model_3dcausal.py:62-80).  groupnorm (no shipped config): statistics over whatever tensor the call site passes --
+    `frames`: `(b t) c h w` (ResnetBlock, via spatial_temporal_resblk), `seq`: `(b h w) c t` (ResnetBlock1D,
+    model_3dnoncausal.py:221-235), `volume`: the 5-D tensor (ResnetNoncausalBlock :284-300, AttnBlockWrapper :25-26)."""
+    B, C, T, H, W = x.shape
+    if cfg.norm_type == "layernorm":
+        y = F.layer_norm(x.permute(0, 2, 3, 4, 1), (C,), sd[key + ".norm.weight"], sd[key + ".norm.bias"], eps=1e-6)
+        return y.permute(0, 4, 1, 2, 3)
+    g, b = sd[key + ".weight"], sd[key + ".bias"]
+    if mode == "frames":
+        y = F.group_norm(x.permute(0, 2, 1, 3, 4).reshape(B * T, C, H, W), 32, g, b, eps=1e-6)
+        return y.reshape(B, T, C, H, W).permute(0, 2, 1, 3, 4)
+    if mode == "seq":
+        y = F.group_norm(x.permute(0, 3, 4, 1, 2).reshape(B * H * W, C, T), 32, g, b, eps=1e-6)
+        return y.reshape(B, H, W, C, T).permute(0, 3, 4, 1, 2)
+    return F.group_norm(x, 32, g, b, eps=1e-6)
+
+
+def nc_resblock(sd, key: str, x: Tensor, cfg: OracleCfg, kind: str) -> Tensor:
+    """ResnetBlock (2D, frames) / ResnetBlock1D (seq) / ResnetNoncausalBlock (volume): model_3dnoncausal.py:152-179,
+    221-248,284-311 -- norm, SiLU, conv, norm, SiLU, conv, + skip (1x1 nin_shortcut when channels change)."""
+    def conv(k, t):
+        if kind == "frames":
+            return conv2d_frames(t, sd[k + ".weight"], sd[k + ".bias"], padding=(sd[k + ".weight"].shape[-1] - 1) // 2)
+        if kind == "seq":
+            return nc_conv1d(sd, k, t)
+        return nc_conv3d(sd, k, t)
+    h = conv(key + ".conv1", silu(nc_norm(sd, key + ".norm1", x, cfg, kind)))
+    h = conv(key + ".conv2", silu(nc_norm(sd, key + ".norm2", h, cfg, kind)))
+    if key + ".nin_shortcut.weight" in sd:
+        x = conv(key + ".nin_shortcut", x)
+    return x + h
+
+
+def nc_attn_block(sd, key: str, x: Tensor, cfg: OracleCfg) -> Tensor:
+    """AttnBlockWrapper: model_3dnoncausal.py:17-34 (per-frame single-head SDPA, 1x1x1 nn.Conv3d projections)."""
+    B, C, T, H, W = x.shape
+    h = nc_norm(sd, key + ".norm", x, cfg, "volume")
+    q, k, v = (nc_conv3d(sd, f"{key}.{n}", h).permute(0, 2, 3, 4, 1).reshape(B, T, H * W, C) for n in ("q", "k", "v"))
+    o = F.scaled_dot_product_attention(q, k, v).reshape(B, T, H, W, C).permute(0, 4, 1, 2, 3)
+    return x + nc_conv3d(sd, key + ".proj_out", o)
+
+
+def nc_time_downsample(sd, key: str, x: Tensor) -> Tensor:
+    """TimeDownsampleRes2x: model_3dnoncausal.py:84-90 -- one zero frame appended, then
+    alpha*avgpool3d((3,1,1),s=(2,1,1)) + (1-alpha)*conv3d(k3, s=(2,1,1), padding=(0,1,1))."""
+    alpha = torch.sigmoid(sd[key + ".mix_factor"])
+    xp = F.pad(x, (0, 0, 0, 0, 0, 1))
+    return alpha * F.avg_pool3d(xp, (3, 1, 1), stride=(2, 1, 1)) + (1 - alpha) * nc_conv3d(sd, key + ".conv", xp, stride=(2, 1, 1), padding=(0, 1, 1))
+
+
+def nc_time_upsample(sd, key: str, x: Tensor) -> Tensor:
+    """TimeUpsampleRes2x: model_3dnoncausal.py:105-115 -- nearest 2x in T, alpha*x' + (1-alpha)*conv3d(k3, pad 1)(x')."""
+    alpha = torch.sigmoid(sd[key + ".mix_factor"])
+    x = F.interpolate(x.float(), scale_factor=[2.0, 1.0, 1.0], mode="nearest").to(x.dtype)
+    return alpha * x + (1 - alpha) * nc_conv3d(sd, key + ".conv", x)
+
+
+def nc_encoder_forward(sd, x: Tensor, cfg: OracleCfg) -> Tensor:
+    """Encoder3D.forward: model_3dnoncausal.py:446-482 (tempo_ds = [L-2, L-3], :335)."""
+    P = "encoder."
+    L = cfg.nres
+    h = nc_conv3d(sd, P + "conv_in", x)
+    for lvl in range(L):
+        for blk in range(cfg.num_res_blocks):
+            h = nc_resblock(sd, f"{P}down.{lvl}.block.{blk}", h, cfg, "frames")
+            h = nc_resblock(sd, f"{P}down_temporal.{lvl}.block.{blk}", h, cfg, "seq")
+        if lvl != L - 1:
+            h = downsample(sd, f"{P}down.{lvl}.downsample", h)
+            if lvl in (L - 2, L - 3):
+                h = nc_time_downsample(sd, f"{P}down_temporal.{lvl}.downsample", h)
+    h = nc_resblock(sd, P + "mid.block_1", h, cfg, "volume")
+    h = nc_attn_block(sd, P + "mid.attn_1", h, cfg)
+    h = nc_resblock(sd, P + "mid.block_2", h, cfg, "volume")
+    return nc_conv3d(sd, P + "conv_out", silu(nc_norm(sd, P + "norm_out", h, cfg, "volume")))
+
+
+def nc_decoder_forward(sd, z: Tensor, cfg: OracleCfg) -> Tensor:
+    """Decoder3D.forward: model_3dnoncausal.py:618-651 (tempo_us = [1, 2], :515)."""
+    P = "decoder."
+    h = nc_conv3d(sd, P + "conv_in", z)
+    h = nc_resblock(sd, P + "mid.block_1", h, cfg, "volume")
+    h = nc_attn_block(sd, P + "mid.attn_1", h, cfg)
+    h = nc_resblock(sd, P + "mid.block_2", h, cfg, "volume")
+    for lvl in reversed(range(cfg.nres)):
+        for blk in range(cfg.num_res_blocks + 1):
+            h = nc_resblock(sd, f"{P}up.{lvl}.block.{blk}", h, cfg, "frames")
+            h = nc_resblock(sd, f"{P}up_temporal.{lvl}.block.{blk}", h, cfg, "seq")
+        if lvl != 0:
+            h = upsample(sd, f"{P}up.{lvl}.upsample", h)
+            if lvl in (1, 2):
+                h = nc_time_upsample(sd, f"{P}up_temporal.{lvl}.upsample", h)
+    return nc_conv3d(sd, P + "conv_out", silu(nc_norm(sd, P + "norm_out", h, cfg, "volume")))
+
+
+# --------------------------------------------------------------------------------------------------
 # encoder / decoder stacks
 # --------------------------------------------------------------------------------------------------
 def encoder_forward(sd, x: Tensor, cfg: OracleCfg, st: Optional[ChunkState] = None) -> Tensor:
@@ -457,6 +578,10 @@ class OracleModel:
     def encode(self, x: Tensor, noise_fn=torch.randn, return_pre: bool = False):
         cfg = self.cfg
         x = x.to(self.dtype)
+        if not cfg.causal:
+            h = nc_encoder_forward(self.sd, x, cfg)
+            z, log = self._regularize(h, noise_fn)
+            return (z, log, h) if return_pre else (z, log)
         if cfg.version == "v1_0":
             h = encoder_forward(self.sd, x, cfg, None)
             z, log = self._regularize(h, noise_fn)
@@ -487,6 +612,8 @@ class OracleModel:
         if decode_from_indices:
             z = fsq_indices_to_codes(z, cfg.fsq_levels, self.dtype)
         z = z.to(self.dtype)
+        if not cfg.causal:
+            return nc_decoder_forward(self.sd, z, cfg)
         if cfg.version == "v1_0":
             return decoder_forward(self.sd, z, cfg, None)
         st = ChunkState(first=True)
@@ -557,11 +684,16 @@ def reference_param_shapes(cfg: OracleCfg) -> Dict[str, Tuple[int, ...]]:
         k = key + ".norm" if ln else key
         out[k + ".weight"], out[k + ".bias"] = (c,), (c,)
 
+    inner = ".conv" if cfg.causal else ""   # CausalConv3d / CausalConv1d wrap an nn.Conv; the non-causal family uses it directly
+
     def conv3d(key, co, ci, k=3):
-        out[key + ".conv.weight"], out[key + ".conv.bias"] = (co, ci, k, k, k), (co,)
+        out[key + inner + ".weight"], out[key + inner + ".bias"] = (co, ci, k, k, k), (co,)
 
     def conv1d(key, co, ci):
-        out[key + ".conv.weight"], out[key + ".conv.bias"] = (co, ci, 3), (co,)
+        out[key + inner + ".weight"], out[key + inner + ".bias"] = (co, ci, 3), (co,)
+
+    def tconv(key, c):   # Time{Down,Up}sampleRes[Causal]2x.conv
+        out[key + ".conv" + inner + ".weight"], out[key + ".conv" + inner + ".bias"] = (c, c, 3, 3, 3), (c,)
 
     def conv2d(key, co, ci, k):
         out[key + ".weight"], out[key + ".bias"] = (co, ci, k, k), (co,)
@@ -595,7 +727,7 @@ def reference_param_shapes(cfg: OracleCfg) -> Dict[str, Tuple[int, ...]]:
             conv2d(f"encoder.down.{l}.downsample.conv", block_in, block_in, 3)
             if l in cfg.enc_tempo_ds():
                 out[f"encoder.down_temporal.{l}.downsample.mix_factor"] = (1,)
-                conv3d(f"encoder.down_temporal.{l}.downsample.conv", block_in, block_in)
+                tconv(f"encoder.down_temporal.{l}.downsample", block_in)
     res3d("encoder.mid.block_1", block_in); attn("encoder.mid.attn_1", block_in); res3d("encoder.mid.block_2", block_in)
     norm("encoder.norm_out", block_in)
     conv3d("encoder.conv_out", (2 if cfg.double_z else 1) * cfg.z_channels, block_in)
@@ -613,7 +745,7 @@ def reference_param_shapes(cfg: OracleCfg) -> Dict[str, Tuple[int, ...]]:
             conv2d(f"decoder.up.{l}.upsample.conv", block_in, block_in, 3)
         if l in cfg.dec_tempo_us():
             out[f"decoder.up_temporal.{l}.upsample.mix_factor"] = (1,)
-            conv3d(f"decoder.up_temporal.{l}.upsample.conv", block_in, block_in)
+            tconv(f"decoder.up_temporal.{l}.upsample", block_in)
     norm("decoder.norm_out", block_in)
     conv3d("decoder.conv_out", cfg.out_ch, block_in)
     return out

@@ -35,7 +35,8 @@ def test_manifest_matches_reference_checkpoint_keys(case):
         assert tuple(sd[k].shape) == tuple(v), k
     want = "AutoencodingEngineV11" if "v1_1" in meta["model"]["target"] else "AutoencodingEngine"
     assert type(model).__name__ == want
-    assert model.is_causal and model.encoder.time_downsample_factor == 4
+    assert model.is_causal == ("noncausal" not in meta["model"]["params"]["encoder_config"]["target"])   # README.md:335
+    assert model.encoder.time_downsample_factor == 4
     if "v1_1" in meta["model"]["target"]:
         assert hasattr(model, "use_tiling") and model.t_chunk_dec == model.t_chunk_enc // 4 and model.use_overlap is False
 

@@ -23,7 +23,7 @@ class ModelDesc(C.Structure):
         ("n_spatial_us", C.c_int32), ("spatial_us", C.c_int32 * VT_MAX_LEVELS),
         ("n_tempo_us", C.c_int32), ("tempo_us", C.c_int32 * VT_MAX_LEVELS),
         ("interpolation_mode", C.c_int32), ("regularizer", C.c_int32), ("fsq_num_levels", C.c_int32),
-        ("fsq_levels", C.c_int32 * VT_MAX_LEVELS), ("kl_sample", C.c_int32),
+        ("fsq_levels", C.c_int32 * VT_MAX_LEVELS), ("kl_sample", C.c_int32), ("noncausal", C.c_int32),
     ]
 
 

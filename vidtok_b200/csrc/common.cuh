@@ -164,6 +164,7 @@ struct ConvP {
   long long rsB, rsT, rsH, rsW;       // residual element strides (channel stride 1)
   int resT;                           // residual frame count (mode 3 bounds)
   int res_t_mode;                     // mode 3 front pad: 0 zero (v1.0), 1 replicate frame 0, 2 res_cache (1 frame)
+  int res_pool_off;                   // mode 3 window: frames 2t-1+off .. 2t+1+off (0: causal, front pad; 1: non-causal, zero frame behind the end)
   const void* res_cache;              // [B,1,H,W,C]
   float ra, rb;
   // activations (input, cache, residual, bf16-class output) are hi|lo split fp16 planes (DT_SPLIT): every position holds

@@ -33,6 +33,7 @@ __device__ __forceinline__ const TIn* gather_ptr(const ConvP& p, const TIn* __re
   int ti = tv - p.t_rep;
   ti = ti < 0 ? 0 : ti;
   if (p.ut == 2) ti >>= 1;
+  if (ti >= p.Ti) return nullptr;   // zero padding behind the last frame (non-causal models: symmetric time padding)
   return x + (long long)b * p.isB + (long long)ti * p.isT + (long long)hi * p.isH + (long long)wi * p.isW;
 }
 
@@ -74,7 +75,7 @@ __device__ __forceinline__ void residual4(const ConvP& p, int b, int to, int ho,
     // AvgPool3d((3,1,1), stride (2,1,1)) over [front pad 1][R]  (model_3dcausal.py:242,250)
 #pragma unroll
     for (int d = -1; d <= 1; ++d) {
-      int tr = 2 * to + d;
+      int tr = 2 * to + d + p.res_pool_off;
       const TRes* q = nullptr;
       if (tr >= 0) {
         if (tr < p.resT) q = R + (long long)b * p.rsB + (long long)tr * p.rsT + (long long)ho * p.rsH + (long long)wo * p.rsW + n;

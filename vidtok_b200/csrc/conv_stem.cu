@@ -19,6 +19,7 @@ struct StemParams {
   int B, Ci, T, H, W;
   int To;          // output frames = t_rep + T
   int t_rep, t_mode;
+  int pt;          // front padding in time: 2 (causal) or 1 (non-causal: one zero frame on either side)
   const float* cache;   // t_mode 2: [B,Ci,2,H,W] fp32, the last two padded input frames of the previous chunk
   int Co;
   const float* bias;
@@ -159,8 +160,8 @@ __global__ void __launch_bounds__(256, kSplit ? 1 : 2) conv_stem_kernel(const St
         r /= PH;
         const int a = r % 3, ci = r / 3;
         const int hv = h0 + hh - 1, wv = w0 + ww - 1;
-        int tv = t + a - 2;  // virtual time axis: [t_rep copies of frame 0][T frames]
-        bool ok = hv >= 0 && hv < p.H && wv >= 0 && wv < p.W;
+        int tv = t + a - p.pt;  // virtual time axis: [t_rep copies of frame 0][T frames]
+        bool ok = hv >= 0 && hv < p.H && wv >= 0 && wv < p.W && tv < p.t_rep + p.T;
         if (tv < 0 && p.t_mode == 2) {
           if (ok) v = p.cache[((((long long)b * p.Ci + ci) * 2 + (2 + tv)) * p.H + hv) * p.W + wv];
           ok = false;
@@ -352,7 +353,8 @@ bool conv_stem_supported(const ConvP& p) {
   if (p.ut != 1 || p.uh != 1 || p.uw != 1 || p.to_off != 0 || p.res_mode != 0) return false;
   if (p.Ci * 27 > 128 || p.Co % 64 != 0 || p.Co > (p.split ? 128 : 256)) return false;
   if (p.t_mode == 2 && (!p.cache || p.cacheT != 2)) return false;
-  if (p.pt != 2 || p.ph != 1 || p.pw != 1) return false;
+  if ((p.pt != 2 && p.pt != 1) || p.ph != 1 || p.pw != 1) return false;
+  if (p.pt == 1 && (p.t_mode != 0 || p.t_rep != 0)) return false;   // symmetric padding: v1.0 non-causal only
   if (p.Ho != p.Hi || p.Wo != p.Wi || p.To != p.t_rep + p.Ti) return false;
   // external NCDHW fp32 input, dense channels-last bf16 output
   if (p.isW != 1 || p.isH != p.Wi || p.isT != (long long)p.Hi * p.Wi || p.isC != p.isT * p.Ti || p.isB != p.isC * p.Ci) return false;
@@ -365,6 +367,7 @@ bool conv_stem_supported(const ConvP& p) {
 cudaError_t launch_conv_stem(const ConvP& p, const float* x, const bf16* wpk, bf16* out, cudaStream_t s) {
   StemParams t;
   t.cache = (const float*)p.cache;
+  t.pt = p.pt;
   t.x = x; t.B = p.B; t.Ci = p.Ci; t.T = p.Ti; t.H = p.Hi; t.W = p.Wi; t.To = p.To; t.t_rep = p.t_rep; t.t_mode = p.t_mode;
   t.Co = p.Co; t.bias = p.bias; t.out = out;
   t.acc_scale = (p.split && p.acc_scale != 0.f) ? p.acc_scale : 1.0f;

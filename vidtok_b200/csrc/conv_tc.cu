@@ -63,7 +63,7 @@ struct TcParams {
   int res_mode;
   const bf16* res;
   long long rsB, rsT, rsH, rsW;
-  int resT, res_t_mode;
+  int resT, res_t_mode, res_pool_off;
   const bf16* res_cache;
   float ra, rb;
   void* out;
@@ -533,7 +533,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       } else if (valid && p.res_mode == 3) {
         // avg-pool of residual frames 2t-1, 2t, 2t+1 (front pad: zero / frame 0 / 1-frame cache)
         const long long sp = (long long)tc.b * p.rsB + (long long)h * p.rsH + (long long)w * p.rsW + tc.n0;
-        const int ta = 2 * t - 1, tb = 2 * t, tcn = 2 * t + 1;
+        const int ta = 2 * t - 1 + p.res_pool_off, tb = ta + 1, tcn = ta + 2;
         if (ta >= 0) r0 = p.res + sp + (long long)ta * p.rsT;
         else if (p.res_t_mode == 1) r0 = p.res + sp;
         else if (p.res_t_mode == 2) r0 = p.res_cache + (((long long)tc.b * p.Ho + h) * p.Wo + w) * (long long)p.Co * (kSplit ? 2 : 1) + tc.n0;
@@ -948,10 +948,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   }
 }
 
-__global__ void fill_identity_kernel(bf16* e, int f16) {
+// 256 x 256 diagonal matrix `value` * I (bf16, or fp16 for the split mode)
+__global__ void fill_identity_kernel(bf16* e, int f16, float value) {
   const int r = blockIdx.x, c = threadIdx.x;
-  if (f16) reinterpret_cast<__half*>(e)[r * 256 + c] = __float2half_rn(r == c ? 1.0f : 0.0f);
-  else e[r * 256 + c] = __float2bfloat16_rn(r == c ? 1.0f : 0.0f);
+  if (f16) reinterpret_cast<__half*>(e)[r * 256 + c] = __float2half_rn(r == c ? value : 0.0f);
+  else e[r * 256 + c] = __float2bfloat16_rn(r == c ? value : 0.0f);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1205,10 +1206,17 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   // smem layout from the 1024-aligned base: [halo windows] [stages x (A | B)] [staging] [barriers | tmem slot | bias/gamma/beta | stats]
   t.stage_off = (uint32_t)(a_ring + stages * stage_bytes);
   t.kparts = 1; t.acc_stages = 2;
-  if (split && p.kt * p.kh * p.kw * (p.Ci / 64) >= 16) {   // K >= 1024
-    int parts = 512 / (t.MT * t.BN);
-    if (parts > 8) parts = 8;
-    if (parts >= 2) { t.kparts = parts; t.acc_stages = (2 * parts * t.MT * t.BN <= 512) ? 2 : 1; }
+  {
+    const int nk_ = p.kt * p.kh * p.kw * (p.Ci / 64);
+    if (split && nk_ >= 64) {          // K >= 4096: as many partial accumulators as TMEM holds, no double buffering
+      int parts = 512 / (t.MT * t.BN);
+      if (parts > 8) parts = 8;
+      if (parts >= 2) { t.kparts = parts; t.acc_stages = (2 * parts * t.MT * t.BN <= 512) ? 2 : 1; }
+    } else if (split && nk_ >= 16) {   // 1024 <= K < 4096: only what fits beside the double-buffered accumulator
+      int parts = 256 / (t.MT * t.BN);
+      if (parts > 8) parts = 8;
+      if (parts >= 2) t.kparts = parts;
+    }
   }
   uint32_t cols = 32;
   while (cols < (uint32_t)(t.acc_stages * t.kparts * t.MT * t.BN)) cols <<= 1;
@@ -1239,7 +1247,7 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
   t.st = p.st; t.pt = p.pt; t.ph = p.ph; t.pw = p.pw; t.to_off = p.to_off; t.sp = p.sh;
   t.t_mode = p.t_mode; t.cacheT = p.cacheT;
   t.bias = p.bias; t.res_mode = p.res_mode; t.res = (const bf16*)p.res;
-  t.rsB = p.rsB; t.rsT = p.rsT; t.rsH = p.rsH; t.rsW = p.rsW; t.resT = p.resT; t.res_t_mode = p.res_t_mode;
+  t.rsB = p.rsB; t.rsT = p.rsT; t.rsH = p.rsH; t.rsW = p.rsW; t.resT = p.resT; t.res_t_mode = p.res_t_mode; t.res_pool_off = p.res_pool_off;
   t.res_cache = (const bf16*)p.res_cache; t.ra = p.ra; t.rb = p.rb;
   t.out = out; t.osB = p.osB; t.osT = p.osT; t.osH = p.osH; t.osW = p.osW; t.osC = p.osC;
   t.out_f32 = (tout == DT_F32) ? 1 : 0;
@@ -1270,9 +1278,16 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
     const double out_bytes = (double)p.B * p.To * p.Ho * p.Wo * p.Co * 2.0 * cw;
     t.store_stream = (ev_env && out_bytes > 256e6) ? 1 : 0;
   }
-  // (split mode: the weights carry a power-of-two scale that the epilogue removes from the whole accumulator, so the residual
-  // cannot ride the tensor pipe there -- it is added by the epilogue from the hi|lo planes in global memory)
-  t.res_mma = (!split && p.res_mode == 1 && p.ra == 1.0f && p.rb == 1.0f && t.BN % 64 == 0 && p.Co % 64 == 0 && p.rsW % 8 == 0 && p.rsH % 8 == 0 &&
+  // (split mode: the weights carry a power-of-two scale 2^s that the epilogue removes from the whole accumulator, so the
+  // residual is multiplied by 2^s * I -- exact in fp16 for s <= 15; larger scales fall back to the epilogue add)
+  int ident_s = 0;
+  bool ident_ok = true;
+  if (split) {
+    const float ws = 1.0f / t.acc_scale;
+    ident_s = ilogbf(ws);
+    ident_ok = ident_s >= 0 && ident_s <= 15 && ldexpf(1.0f, ident_s) == ws;
+  }
+  t.res_mma = (ident_ok && p.res_mode == 1 && p.ra == 1.0f && p.rb == 1.0f && t.BN % 64 == 0 && p.Co % 64 == 0 && p.rsW % 8 == 0 && p.rsH % 8 == 0 &&
                p.rsT % 8 == 0 && p.rsB % 8 == 0 && (((uintptr_t)p.res) & 15) == 0) ? 1 : 0;
 
   TcMaps maps;
@@ -1340,17 +1355,19 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
     if (t.ln_mode == 2 && !encode_out(&maps.o2, t.out2, p.To, p.osW, p.osH, p.osT, p.osB, qw, qh, qt)) return cudaErrorInvalidValue;
   }
   if (t.res_mma) {
-    static bf16* ident_dev[2][64] = {{nullptr}};   // 256 x 256 identity (bf16 / fp16), built once per device on the launching stream
+    // 256 x 256 identity: bf16 I, or the 16 fp16 matrices 2^s * I of the split mode; built once per device on the launching stream
+    static bf16* ident_dev[2][64] = {{nullptr}};
     int devid = 0;
     cudaGetDevice(&devid);
     if (devid < 0 || devid >= 64) { g_tc_err = "device index out of range"; return cudaErrorInvalidValue; }
     const int ik = split ? 1 : 0;
     if (!ident_dev[ik][devid]) {
-      cudaError_t e = cudaMalloc(&ident_dev[ik][devid], 256 * 256 * sizeof(bf16));
+      const int nmat = split ? 16 : 1;
+      cudaError_t e = cudaMalloc(&ident_dev[ik][devid], (size_t)nmat * 256 * 256 * sizeof(bf16));
       if (e != cudaSuccess) { g_tc_err = "cudaMalloc(identity)"; return e; }
-      fill_identity_kernel<<<256, 256, 0, s>>>(ident_dev[ik][devid], ik);
+      for (int i = 0; i < nmat; ++i) fill_identity_kernel<<<256, 256, 0, s>>>(ident_dev[ik][devid] + (size_t)i * 256 * 256, ik, ldexpf(1.0f, i));
     }
-    bf16* ident = ident_dev[ik][devid];
+    bf16* ident = ident_dev[ik][devid] + (size_t)(split ? ident_s : 0) * 256 * 256;
     if (!encode_out(&maps.r, p.res, p.resT, p.rsW, p.rsH, p.rsT, p.rsB, t.halo ? t.hP : t.BW, t.halo ? 16 + p.kh - 1 : t.BH, t.BT)) return cudaErrorInvalidValue;
     cuuint64_t dims[3] = {256, 256, 1};
     cuuint64_t strides[2] = {512, 256 * 512};

@@ -713,7 +713,7 @@ __global__ void __launch_bounds__(256) transpose_bf16_kernel(const bf16* __restr
 // (model_3dcausal.py:883-885).
 __global__ void __launch_bounds__(256) tap_planes_gather_kernel(const bf16* __restrict__ P, const float* __restrict__ bias,
                                                                 float* __restrict__ out, int B, int Ti, int H, int W, int NP,
-                                                                int Co, int to_off) {
+                                                                int Co, int to_off, int pt) {
   const int To = Ti - to_off;
   const long long total = (long long)B * To * H * W;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -725,8 +725,8 @@ __global__ void __launch_bounds__(256) tap_planes_gather_kernel(const bf16* __re
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      const int ti = to + to_off + a - 2;
-      if (ti < 0) continue;
+      const int ti = to + to_off + a - pt;   // pt = 2: causal front padding; 1: symmetric (non-causal)
+      if (ti < 0 || ti >= Ti) continue;
 #pragma unroll
       for (int bb = 0; bb < 3; ++bb) {
         const int hh = h + bb - 1;
@@ -987,13 +987,13 @@ cudaError_t launch_time_interp2x(DType t, const void* x, void* y, int B, int T, 
   return cudaGetLastError();
 }
 cudaError_t launch_tap_planes_gather(const bf16* P, const float* bias, float* out, int B, int Ti, int H, int W, int NP, int Co,
-                                     int to_off, cudaStream_t s) {
+                                     int to_off, cudaStream_t s, int pt) {
   const long long total = (long long)B * (Ti - to_off) * H * W;
   if (total <= 0) return cudaSuccess;
   ProfScope _ps("tap_planes_gather", 2.0 * 27 * Co * total, (double)B * Ti * H * W * NP * 2.0 + (double)total * Co * 4.0, s);
   long long g = (total + 255) / 256;
   if (g > 148LL * 32) g = 148LL * 32;
-  tap_planes_gather_kernel<<<(unsigned)g, 256, 0, s>>>(P, bias, out, B, Ti, H, W, NP, Co, to_off);
+  tap_planes_gather_kernel<<<(unsigned)g, 256, 0, s>>>(P, bias, out, B, Ti, H, W, NP, Co, to_off, pt);
   count_launch();
   return cudaGetLastError();
 }

@@ -115,7 +115,7 @@ cudaError_t launch_kl_clear(double* scratch, cudaStream_t s);
 cudaError_t launch_kl_finish(const double* scratch, int B, float* kl_loss, cudaStream_t s);
 // decoder head through per-tap partial outputs (see elementwise.cu)
 cudaError_t launch_tap_planes_gather(const bf16* P, const float* bias, float* out, int B, int Ti, int H, int W, int NP, int Co,
-                                     int to_off, cudaStream_t s);
+                                     int to_off, cudaStream_t s, int pt = 2);
 cudaError_t launch_pack_w_tap_planes(const float* w, bf16* out, int Co, int Ci, int NP, cudaStream_t s);
 // x [batch][rows][cols] -> y [batch][cols][rows] (bf16), rows and cols multiples of 32
 cudaError_t launch_transpose_bf16(const bf16* x, bf16* y, int batch, int rows, int cols, cudaStream_t s, bool split = false);

@@ -96,17 +96,20 @@ static int add_param(vt_model* m, const std::string& name, std::vector<int64_t> 
   return (int)m->params.size() - 1;
 }
 // CausalConv3d: "<key>.conv.{weight,bias}", weight [Co,Ci,kt,kh,kw]
+// (the non-causal family uses nn.Conv3d / nn.Conv1d directly: no inner ".conv", model_3dnoncausal.py:20-23,203,271,348)
 static void add_conv3d(vt_model* m, ConvW& c, const std::string& key, int Co, int Ci, int k) {
   c.Co = Co; c.Ci = Ci; c.kt = c.kh = c.kw = k;
-  c.pw = add_param(m, key + ".conv.weight", {Co, Ci, k, k, k});
-  c.pb = add_param(m, key + ".conv.bias", {Co});
+  const std::string in = m->desc.noncausal ? "" : ".conv";
+  c.pw = add_param(m, key + in + ".weight", {Co, Ci, k, k, k});
+  c.pb = add_param(m, key + in + ".bias", {Co});
   m->convs.push_back(&c);
 }
 // CausalConv1d: "<key>.conv.{weight,bias}", weight [Co,Ci,k]
 static void add_conv1d(vt_model* m, ConvW& c, const std::string& key, int Co, int Ci, int k) {
   c.Co = Co; c.Ci = Ci; c.kt = k; c.kh = c.kw = 1;
-  c.pw = add_param(m, key + ".conv.weight", {Co, Ci, k});
-  c.pb = add_param(m, key + ".conv.bias", {Co});
+  const std::string in = m->desc.noncausal ? "" : ".conv";
+  c.pw = add_param(m, key + in + ".weight", {Co, Ci, k});
+  c.pb = add_param(m, key + in + ".bias", {Co});
   m->convs.push_back(&c);
 }
 // nn.Conv2d: "<key>.{weight,bias}", weight [Co,Ci,k,k]
@@ -286,6 +289,8 @@ struct ConvOpt {
   int ph0 = -1, pw0 = -1, ph1 = -1, pw1 = -1;  // -1: (k-1)/2
   int ut = 1, uh = 1, uw = 1;
   int t_rep = 0, to_off = 0;
+  int pt_front = -1, pt_back = 0;  // time padding override (non-causal models); -1: causal front pad (k-1)+(1-st)
+  int res_pool_off = 0;            // res_mode 3 window offset (ConvP::res_pool_off)
   int res_mode = 0;
   const Act* res = nullptr;
   long long res_bs = -1;          // residual batch stride override (views)
@@ -442,13 +447,20 @@ struct Exec {
     p.st = o.st; p.sh = o.sh; p.sw = o.sw;
     p.ut = o.ut; p.uh = o.uh; p.uw = o.uw;
     p.t_rep = o.t_rep; p.to_off = o.to_off;
-    p.pt = (w.kt - 1) + (1 - o.st);                       // model_3dcausal.py:177
+    // time padding: causal front pad (model_3dcausal.py:177), or -- non-causal family -- symmetric zero padding for stride 1
+    // and one zero frame behind the end for the stride-2 time-downsample conv (model_3dnoncausal.py:80,86-87,101,203,271)
+    int ptf = o.pt_front, ptb = o.pt_back;
+    if (ptf < 0 && m->desc.noncausal && w.kt > 1) {
+      if (o.st == 1) ptf = ptb = (w.kt - 1) / 2;
+      else { ptf = 0; ptb = 1; }
+    }
+    p.pt = ptf >= 0 ? ptf : (w.kt - 1) + (1 - o.st);
     const int hp = (w.kh - 1) + (1 - o.sh), wp = (w.kw - 1) + (1 - o.sw);   // :178-179
     const int ph0 = o.ph0 >= 0 ? o.ph0 : hp / 2, ph1 = o.ph1 >= 0 ? o.ph1 : hp - hp / 2;
     const int pw0 = o.pw0 >= 0 ? o.pw0 : wp / 2, pw1 = o.pw1 >= 0 ? o.pw1 : wp - wp / 2;
     p.ph = ph0; p.pw = pw0;
     const int Tv = o.t_rep + o.ut * in.T;
-    p.To = (Tv + p.pt - w.kt) / o.st + 1 - o.to_off;
+    p.To = (Tv + p.pt + ptb - w.kt) / o.st + 1 - o.to_off;
     p.Ho = (o.uh * in.H + ph0 + ph1 - w.kh) / o.sh + 1;
     p.Wo = (o.uw * in.W + pw0 + pw1 - w.kw) / o.sw + 1;
     p.Co = w.Co;
@@ -495,6 +507,7 @@ struct Exec {
       if (r.C != w.Co) { rc = fail(VT_ERR_INVALID, "conv: residual channel mismatch"); return out; }
       if (o.res_mode == 3) {
         p.res_t_mode = 0;
+        p.res_pool_off = o.res_pool_off;
         if (v11) {
           p.res_t_mode = 1;   // replicate (model_3dcausal_v1_1.py:293-294)
           if (ck && ck->persist && o.cache_key) {
@@ -622,7 +635,7 @@ struct Exec {
   // `next`: the norm the FOLLOWING stage applies to this block's output (fused into conv2's epilogue when possible).
   // ResnetCausalBlock1D as ONE launch (tblock_tc.cu): BF16 mode, v1.0 zero padding, LayerNorm, 128 channels
   bool resblock1d_fused(const ResBlockW& r, Stream& st, const NormW* next, bool next_silu) {
-    if (prec != VT_PREC_BF16 || m->desc.version != 0 || m->desc.norm_type != VT_NORM_LAYERNORM) return false;
+    if (prec != VT_PREC_BF16 || m->desc.version != 0 || m->desc.noncausal || m->desc.norm_type != VT_NORM_LAYERNORM) return false;
     if (r.c1.Ci != 128 || r.c1.Co != 128 || r.c2.Co != 128 || !r.c1.w_nk || !r.c2.w_nk || r.c1.kt != 3 || r.c1.kh != 1) return false;
     if (!tblock_tc_supported(st.x.B, st.x.T, st.x.H, st.x.W, st.x.C, dry)) return false;
     Act n1 = take_norm(st, r.n1, true, true);
@@ -782,6 +795,7 @@ struct Exec {
     const std::string ck_ = lv.tkey + ".conv";
     ConvOpt o;
     o.st = 2; o.res_mode = 3; o.res = &st.x; o.ra = lv.alpha; o.rb = 1.f - lv.alpha; o.cache_key = ck_.c_str();
+    if (m->desc.noncausal) o.res_pool_off = 1;   // avg-pool window 2t .. 2t+2, zero frame behind the end (model_3dnoncausal.py:86-88)
     o.ln2 = next; o.ln2_silu = next_silu;
     Act out = conv(lv.tconv, st.x, o);
     set_stream(st, out, o);
@@ -849,6 +863,7 @@ struct Exec {
         for (int pt = 0; pt < 2 && ok(); ++pt) {
           ConvOpt op;
           op.ra = lv.alpha; op.rb = 1.f - lv.alpha; op.res_mode = 1; op.res = &x;
+          if (m->desc.noncausal) { op.pt_front = pt == 0 ? 1 : 0; op.pt_back = pt == 0 ? 0 : 1; }   // frames (i-1, i) / (i, i+1)
           const size_t off = (size_t)(pt * fr) * dtype_size(ta);
           op.out_view = dry ? out.p : (void*)((char*)out.p + off);
           op.ov_sW = (long long)lv.tconv.Co * cw; op.ov_sH = (long long)x.W * lv.tconv.Co * cw; op.ov_sT = 2 * fr * cw; op.ov_sB = 2 * fr * x.T * cw;
@@ -993,7 +1008,7 @@ static void run_encoder(Exec& ex, const float* x_ext, int B, int T, int H, int W
   const StackW& e = m->enc;
   const int tdf = d.time_downsample_factor;
   int t_rep = 0;
-  if (T % tdf != 0) t_rep = (d.version == 0) ? (tdf - 1) : (tdf - T % tdf);  // model_3dcausal.py:685-689 / _v1_1.py:755-760
+  if (T % tdf != 0 && !d.noncausal) t_rep = (d.version == 0) ? (tdf - 1) : (tdf - T % tdf);  // model_3dcausal.py:685-689 / _v1_1.py:755-760
   Act xin;
   xin.p = (void*)x_ext; xin.B = B; xin.T = T; xin.H = H; xin.W = W; xin.C = d.in_channels;
   Exec::Stream st;
@@ -1107,12 +1122,12 @@ static void run_decoder(Exec& ex, const float* z_ext, int B, int Tz, int Hz, int
     ex.free_act(n);
     if (ex.ok() && !ex.dry)
       ex.cuda(launch_tap_planes_gather((const bf16*)P.p, g.conv_out.bias, x_out, P.B, P.T, P.H, P.W, 128, g.conv_out.Co,
-                                       d.time_downsample_factor - 1, ex.s), "tap_planes_gather");
+                                       d.noncausal ? 0 : d.time_downsample_factor - 1, ex.s, d.noncausal ? 1 : 2), "tap_planes_gather");
     ex.free_act(P);
     return;
   }
   ConvOpt o; o.ext_out = x_out; o.cache_key = "decoder.conv_out";
-  if (d.version == 0) o.to_off = d.time_downsample_factor - 1;  // model_3dcausal.py:883-885
+  if (d.version == 0 && !d.noncausal) o.to_off = d.time_downsample_factor - 1;  // model_3dcausal.py:883-885
   ex.conv(g.conv_out, n, o);
   ex.free_act(n);
 }
@@ -1121,7 +1136,7 @@ static int latent_shape(const vt_model* m, int T, int H, int W, int* Tz, int* Hz
   const vt_model_desc& d = m->desc;
   const int tdf = d.time_downsample_factor;
   int t = T;
-  if (T % tdf != 0) t += (d.version == 0) ? (tdf - 1) : (tdf - T % tdf);
+  if (T % tdf != 0 && !d.noncausal) t += (d.version == 0) ? (tdf - 1) : (tdf - T % tdf);
   int h = H, w = W;
   for (int l = 0; l < d.num_levels; ++l) {
     if (contains(m->spatial_ds, l)) {
@@ -1142,7 +1157,7 @@ static void decoded_shape(const vt_model* m, int Tz, int Hz, int Wz, int* T, int
       if (contains(m->tempo_us, l)) t *= 2;
     }
   }
-  if (d.version == 0) t -= d.time_downsample_factor - 1;
+  if (d.version == 0 && !d.noncausal) t -= d.time_downsample_factor - 1;
   *T = t; *H = h; *W = w;
 }
 
@@ -1208,6 +1223,8 @@ int32_t vt_model_create(const vt_model_desc* desc, int32_t device, vt_model** ou
   if (d.num_levels < 2 || d.num_levels > VT_MAX_LEVELS) return fail(VT_ERR_INVALID, "num_levels out of range");
   if (d.ch <= 0 || d.ch % 4 != 0) return fail(VT_ERR_INVALID, "ch must be a positive multiple of 4");
   if (d.norm_type == VT_NORM_GROUPNORM && d.ch % 32 != 0) return fail(VT_ERR_INVALID, "groupnorm needs ch %% 32 == 0");
+  if (d.noncausal && d.version != 0) return fail(VT_ERR_INVALID, "the non-causal family exists in v1.0 only");
+  if (d.noncausal && d.norm_type == VT_NORM_GROUPNORM) return fail(VT_ERR_INVALID, "non-causal models with GroupNorm are not on the path (every shipped config uses layernorm)");
   if (d.regularizer == VT_REG_FSQ) {
     if (d.fsq_num_levels != d.z_channels) return fail(VT_ERR_INVALID, "FSQ with projections (dim != len(levels)) is not on the path");
     if (d.double_z) return fail(VT_ERR_INVALID, "FSQ needs double_z = false");
@@ -1375,8 +1392,10 @@ int32_t vt_model_finalize(vt_model* m, void* stream) {
         ph.bias = c.bias; ph.w_nk = m->packed_nk + onk; ph.w_nk3 = m->packed_nk3 + 2 * onk; ph.wscale3 = c.wscale3;
         onk += align_up((size_t)c.Co * 18 * c.Ci, 512);
         // even frames t'=2i read x'[2i-2..2i] = x[i-1],x[i-1],x[i]; odd frames read x[i-1],x[i],x[i]
-        VT_CUDA(launch_pack_w_collapsed(w, ph.w_nk, c.Co, c.Co, c.Ci, 3, 3, 3, pt == 0 ? hi : lo, id3, id3, 2, 3, 3, s));
-        VT_CUDA(launch_pack_w_collapsed(w, ph.w_nk3, c.Co, c.Co, c.Ci, 3, 3, 3, pt == 0 ? hi : lo, id3, id3, 2, 3, 3, s, c.wscale3));
+        // non-causal (pad 1 on both sides): even frames read x'[2i-1..2i+1] = x[i-1],x[i],x[i]; odd frames x[i],x[i],x[i+1]
+        const int* tmap = m->desc.noncausal ? (pt == 0 ? lo : hi) : (pt == 0 ? hi : lo);
+        VT_CUDA(launch_pack_w_collapsed(w, ph.w_nk, c.Co, c.Co, c.Ci, 3, 3, 3, tmap, id3, id3, 2, 3, 3, s));
+        VT_CUDA(launch_pack_w_collapsed(w, ph.w_nk3, c.Co, c.Co, c.Ci, 3, 3, 3, tmap, id3, id3, 2, 3, 3, s, c.wscale3));
       }
     }
   }

@@ -59,11 +59,16 @@ class TokenizerSpec:
     regularizer: str = "kl"
     fsq_levels: Tuple[int, ...] = ()
     kl_sample: bool = True
+    causal: bool = True   # False: the non-causal family (vidtok/modules/model_3dnoncausal.py)
 
     @staticmethod
-    def from_params(params: Dict[str, Any], version: int) -> "TokenizerSpec":
+    def from_params(params: Dict[str, Any], version: int, causal: bool = True) -> "TokenizerSpec":
         g = params.get
+        if not causal:   # model_3dnoncausal.py:335,515: fixed resampling schedules
+            params = {k: v for k, v in params.items() if k not in ("spatial_ds", "tempo_ds", "spatial_us", "tempo_us")}
+            g = params.get
         return TokenizerSpec(
+            causal=causal,
             version=version, ch=int(params["ch"]), ch_mult=tuple(int(c) for c in g("ch_mult", (1, 2, 4, 8))),
             num_res_blocks=int(params["num_res_blocks"]), in_channels=int(params["in_channels"]),
             out_ch=int(params["out_ch"]), z_channels=int(params["z_channels"]), double_z=bool(g("double_z", True)),
@@ -101,6 +106,7 @@ class TokenizerSpec:
         for i, l in enumerate(self.fsq_levels):
             d.fsq_levels[i] = int(l)
         d.kl_sample = int(self.kl_sample)
+        d.noncausal = int(not self.causal)
         return d
 
 
@@ -297,10 +303,11 @@ class _Stack(nn.Module):
     """Common part of the encoder / decoder mirrors: owns the parameters of one stack."""
 
     _prefix = ""
+    _causal = True
 
     def __init__(self, version: int, **params):
         super().__init__()
-        self.spec = TokenizerSpec.from_params(params, version)
+        self.spec = TokenizerSpec.from_params(params, version, causal=self._causal)
         self.norm_type = self.spec.norm_type
         self.ch = self.spec.ch
         self.num_resolutions = len(self.spec.ch_mult)
@@ -369,6 +376,53 @@ class DecoderCausal3DPadding(_Stack):
         return self.conv_out.conv.weight
 
     def forward(self, z: torch.Tensor) -> torch.Tensor:
+        return self._runtime().decode_raw(z, from_indices=False)
+
+
+class Encoder3D(_Stack):
+    """vidtok.modules.model_3dnoncausal.Encoder3D (model_3dnoncausal.py:314-482)."""
+
+    _prefix = "encoder."
+    _causal = False
+
+    def __init__(self, *args, **params):
+        assert not args, "keyword arguments only (as instantiate_from_config passes them)"
+        if params.get("norm_type", "groupnorm") != "layernorm":
+            raise NotImplementedError("non-causal models with GroupNorm are not on the path (every shipped config uses layernorm)")
+        super().__init__(0, **params)
+        self.is_causal = False
+        self.tempo_ds = [self.num_resolutions - 2, self.num_resolutions - 3]
+        if self.fix_encoder:
+            for p in self.parameters():
+                p.requires_grad = False
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        _, _, _, h = self._runtime().encode_raw(x, want_h=True, noise=None, need_reg=False)
+        return h
+
+
+class Decoder3D(_Stack):
+    """vidtok.modules.model_3dnoncausal.Decoder3D (model_3dnoncausal.py:485-651)."""
+
+    _prefix = "decoder."
+    _causal = False
+
+    def __init__(self, *args, **params):
+        assert not args
+        if params.get("norm_type", "groupnorm") != "layernorm":
+            raise NotImplementedError("non-causal models with GroupNorm are not on the path (every shipped config uses layernorm)")
+        if params.get("give_pre_end") or params.get("tanh_out"):
+            raise NotImplementedError("give_pre_end / tanh_out are not used by any shipped config")
+        super().__init__(0, **params)
+        self.tempo_us = [1, 2]
+        if self.fix_decoder:
+            for p in self.parameters():
+                p.requires_grad = False
+
+    def get_last_layer(self, **kwargs):
+        return self.conv_out.weight
+
+    def forward(self, z: torch.Tensor, **kwargs) -> torch.Tensor:
         return self._runtime().decode_raw(z, from_indices=False)
 
 
@@ -598,7 +652,9 @@ class _EngineBase(nn.Module):
         self.lr_g_factor = lr_g_factor
         self.is_causal = self.encoder.is_causal
 
-        spec = TokenizerSpec.from_params(dict(encoder_config.get("params", {})), self._version)
+        spec = TokenizerSpec.from_params(dict(encoder_config.get("params", {})), self._version, causal=self.encoder.spec.causal)
+        if self.encoder.spec.causal != self.decoder.spec.causal:
+            raise ValueError("encoder and decoder must both be causal or both be non-causal")
         if isinstance(self.regularization, FSQRegularizer):
             spec.regularizer, spec.fsq_levels = "fsq", tuple(self.regularization.levels)
         elif isinstance(self.regularization, DiagonalGaussianRegularizer):
