@@ -443,6 +443,46 @@ def test_fused_temporal_resblock(geom, with_ln):
         check(ncdhw(o2.float().cpu()), out2, N.PREC_BF16, "tblock out2", slack=2.5)
 
 
+def test_fused_temporal_resblock_many_frames_per_cta_pair():
+    """Same block at a size where every CTA pair walks ~7 strips x 20 frames (barrier phases wrap many times, the H tile and
+    the three accumulators are recycled hundreds of times, the peer CTA publishes its half through the forwarder warp).
+    The reference is plain PyTorch fp32 on the GPU (TF32 off) with h rounded to bf16 where the kernel rounds it."""
+    from gpu_util import _p, stream
+    import torch.nn.functional as F
+    B, T, H, W, C_ = 4, 20, 128, 256, 128
+    g = torch.Generator(device="cuda").manual_seed(11)
+    n1 = torch.randn((B, T, H, W, C_), device="cuda", generator=g).to(torch.bfloat16)
+    x = torch.randn((B, T, H, W, C_), device="cuda", generator=g).to(torch.bfloat16)
+    w1 = (torch.randn((C_, C_, 3), device="cuda", generator=g) / math.sqrt(3 * C_)).to(torch.bfloat16).float()
+    w2 = (torch.randn((C_, C_, 3), device="cuda", generator=g) / math.sqrt(3 * C_)).to(torch.bfloat16).float()
+    b1, b2, g2, be2, g3, be3 = [torch.randn(C_, device="cuda", generator=g) * 0.3 for _ in range(6)]
+    g2, g3 = 1.0 + g2, 1.0 + g3
+    o, o2 = torch.empty_like(x), torch.empty_like(x)
+    N.check(N.lib().vt_op_tblock(_p(n1), _p(x), _p(w1), _p(b1), _p(g2), _p(be2), _p(w2), _p(b2), _p(g3), _p(be3), 1,
+                                 _p(o), _p(o2), B, T, H, W, C_, stream()))
+    torch.cuda.synchronize()
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        worst = 0.0
+        for bi in range(B):   # per clip to bound the fp32 temporaries
+            sl = slice(bi, bi + 1)
+            def tc1(a, w, b):   # [1,T,H,W,C]: causal conv over T (two zero frames in front), C -> C
+                a = F.pad(a, (0, 0, 0, 0, 0, 0, 2, 0)).permute(0, 2, 3, 4, 1).reshape(-1, C_, T + 2)
+                return F.conv1d(a, w, b).reshape(1, H, W, C_, T).permute(0, 4, 1, 2, 3)
+            h = tc1(n1[sl].float(), w1, b1)
+            hn = F.silu(F.layer_norm(h, (C_,), g2, be2, 1e-6)).to(torch.bfloat16).float()
+            ref = x[sl].float() + tc1(hn, w2, b2)
+            ref2 = F.silu(F.layer_norm(ref, (C_,), g3, be3, 1e-6))
+            r1 = ((o[sl].float() - ref).abs() / (2.0 * (2.0 ** -7 * ref.abs() + 2e-2))).max().item()
+            r2 = ((o2[sl].float() - ref2).abs() / (2.5 * (2.0 ** -7 * ref2.abs() + 2e-2))).max().item()
+            worst = max(worst, r1, r2)
+            assert r1 <= 1.0 and r2 <= 1.0, (bi, r1, r2)
+        print(f"tblock stress: worst error / bound = {worst:.3f}")
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # regularizers as the epilogue of the bottleneck convolution (encoder conv_out)
 # ---------------------------------------------------------------------------------------------------------------

@@ -63,6 +63,14 @@ __device__ __forceinline__ float silu_f(float x) {
 }
 // accurate variant for the EXACT mode (expf, not the fast intrinsic)
 __device__ __forceinline__ float silu_exact(float x) { return x * (1.0f / (1.0f + expf(-x))); }
+// SiLU of the EXACT_TC epilogues: ex2.approx (2 ulp) and rcp.approx (1 ulp) instead of expf() and an IEEE division -- 5
+// instructions instead of ~25 per element, relative error < 1e-6 for |x| < 16 (the epilogue was bound by this arithmetic)
+__device__ __forceinline__ float silu_tc(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
+}
 
 // ---- DT_SPLIT planes: v = hi + lo with hi = fp16(v), lo = fp16(v - hi): 11 + 11 mantissa bits, so a product of two split
 // numbers that drops lo*lo is good to ~2^-21 (fp32-class).  (bf16 planes would give 8 + 8 bits: products good to 2^-17 only,

@@ -644,10 +644,16 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           }
         };
         // v = rb * (acc + bias) + ra * R for the 32 channels [jj, jj + 32) of this thread's row
-        auto chunk = [&](int jj, float (&f)[32]) {
+        // `finished` (later passes of a LayerNorm epilogue): the row was parked in the accumulator by the first pass
+        auto chunk = [&](int jj, float (&f)[32], bool finished, bool park) {
           uint32_t v[32];
           tmem_ld32(tbase + (uint32_t)jj, v);
           tmem_ld_wait();
+          if (finished) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
+            return;
+          }
           if (nparts > 1) {   // fp32 (round-to-nearest) sum of the partial accumulators
 #pragma unroll 1
             for (uint32_t pi = 1; pi < nparts; ++pi) {
@@ -678,6 +684,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
 #pragma unroll
             for (int e = 0; e < 32; ++e) f[e] = fmaf(s3, acc3[e], f[e]);
           }
+          if (park) {   // partial sums, bias and residual (global loads) are paid once per row, not once per pass
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(f[e]);
+            tmem_st32(tbase + (uint32_t)jj, v);
+            tmem_st_wait();
+          }
         };
         // sum over this thread's channels of g(v); completed across the two groups when they share a row (MT == 1)
         float mean = 0.f, rstd = 0.f;
@@ -692,7 +704,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
 #pragma unroll 1
             for (int hc = 0; hc * 32 < ncol; ++hc) {
               float f[32];
-              chunk(sl * 64 + hc * 32, f);
+              chunk(sl * 64 + hc * 32, f, false, true);
 #pragma unroll
               for (int e = 0; e < 32; ++e) part += f[e];
             }
@@ -712,7 +724,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
 #pragma unroll 1
             for (int hc = 0; hc * 32 < ncol; ++hc) {
               float f[32];
-              chunk(sl * 64 + hc * 32, f);
+              chunk(sl * 64 + hc * 32, f, true, false);
 #pragma unroll
               for (int e = 0; e < 32; ++e) { const float d = f[e] - mean; part = fmaf(d, d, part); }
             }
@@ -738,12 +750,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
               if (hc * 32 >= ncol) break;
               const int jj = j + hc * 32;
               float f[32];
-              chunk(jj, f);
+              chunk(jj, f, p.ln_mode != 0, false);
               if (normalized) {
 #pragma unroll
                 for (int e = 0; e < 32; ++e) {
                   float y = (f[e] - mean) * rstd * gamma_s[jj + e] + beta_s[jj + e];
-                  if (p.ln_silu) y = silu_exact(y);
+                  if (p.ln_silu) y = silu_tc(y);
                   f[e] = y;
                 }
               }
@@ -1387,8 +1399,8 @@ cudaError_t launch_conv_tc(const ConvP& p, const bf16* x, const bf16* w_nk, int 
     grid = 2u * (unsigned)(t.num_tiles < pairs ? t.num_tiles : pairs);
   }
   const double Mrows = (double)p.B * p.To * p.Ho * p.Wo;
-  char det[96] = "";
-  if (prof_enabled()) snprintf(det, sizeof(det), "k%d%d%d s%d%d %d->%d @%dx%dx%d tile%dx%dx%d bn%d mt%d%s", p.kt, p.kh, p.kw, p.st, p.sh, p.Ci, p.Co, p.To, p.Ho, p.Wo, t.tileBT, t.tileBH, t.BW, t.BN, t.MT, t.pair ? (t.halo ? " pair halo" : " pair") : (t.halo ? " halo" : ""));
+  char det[128] = "";
+  if (prof_enabled()) snprintf(det, sizeof(det), "k%d%d%d s%d%d %d->%d @%dx%dx%d tile%dx%dx%d bn%d mt%d%s ln%d r%d%s p%d", p.kt, p.kh, p.kw, p.st, p.sh, p.Ci, p.Co, p.To, p.Ho, p.Wo, t.tileBT, t.tileBH, t.BW, t.BN, t.MT, t.pair ? (t.halo ? " pair halo" : " pair") : (t.halo ? " halo" : ""), t.ln_mode, p.res_mode, t.res_mma ? "m" : "", split ? t.kparts : 1);
   ProfScope _ps(split ? "conv_tc3" : "conv_tc", 2.0 * Mrows * p.kt * p.kh * p.kw * p.Ci * p.Co,
                 2.0 * cw * ((double)p.B * p.Ti * p.Hi * p.Wi * p.Ci) + Mrows * p.Co * (tout == DT_F32 ? 4.0 : 2.0 * cw), s, det);
   if (t.pair) {

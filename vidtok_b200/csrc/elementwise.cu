@@ -122,8 +122,9 @@ __device__ __forceinline__ void join8(const uint4& hi, const uint4& lo, float (&
     f[2 * i + 1] = a.y + b.y;
   }
 }
-// LayerNorm(+SiLU) of split rows (EXACT_TC mode, C % 8 == 0): one warp per position, fp32 two-pass statistics,
-// full-precision SiLU; the row (<= 2 KB) is re-read from L1 for the second and third pass.
+// LayerNorm(+SiLU) of split rows (EXACT_TC mode, C % 8 == 0): one warp per position, fp32 two-pass statistics.  Rows of up
+// to 512 channels (every LayerNorm of the model zoo) stay in registers: one read of x, one write of y; longer rows re-read
+// x from L1 for the second and third pass.
 template <bool SILU>
 __global__ void __launch_bounds__(256) layernorm_split_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, bf16* __restrict__ y,
@@ -133,6 +134,50 @@ __global__ void __launch_bounds__(256) layernorm_split_kernel(const bf16* __rest
   if (row >= rows) return;
   const bf16* xr = x + row * 2 * C;
   bf16* yr = y + row * 2 * C;
+  if (C <= 512) {
+    float f[2][8];
+    const int c0 = lane * 8, c1 = lane * 8 + 256;
+    const bool h0 = c0 < C, h1 = c1 < C;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[0][i] = f[1][i] = 0.f;
+    if (h0) join8(__ldg(reinterpret_cast<const uint4*>(xr + c0)), __ldg(reinterpret_cast<const uint4*>(xr + C + c0)), f[0]);
+    if (h1) join8(__ldg(reinterpret_cast<const uint4*>(xr + c1)), __ldg(reinterpret_cast<const uint4*>(xr + C + c1)), f[1]);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += f[0][i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += f[1][i];
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+    if (h0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float d = f[0][i] - mean; q = fmaf(d, d, q); }
+    }
+    if (h1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float d = f[1][i] - mean; q = fmaf(d, d, q); }
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + 1e-6f);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int c = k ? c1 : c0;
+      if (!(k ? h1 : h0)) continue;
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float t = (f[k][i] - mean) * rstd * gg[i] + bb[i];
+        f[k][i] = SILU ? silu_tc(t) : t;
+      }
+      uint4 hi, lo;
+      split8(f[k], hi, lo);
+      *reinterpret_cast<uint4*>(yr + c) = hi;
+      *reinterpret_cast<uint4*>(yr + C + c) = lo;
+    }
+    return;
+  }
   float s = 0.f;
   for (int c = lane * 8; c < C; c += 256) {
     float f[8];
@@ -155,7 +200,7 @@ __global__ void __launch_bounds__(256) layernorm_split_kernel(const bf16* __rest
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float t = (f[i] - mean) * rstd * gamma[c + i] + beta[c + i];
-      f[i] = SILU ? silu_exact(t) : t;
+      f[i] = SILU ? silu_tc(t) : t;
     }
     uint4 hi, lo;
     split8(f, hi, lo);

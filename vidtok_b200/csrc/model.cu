@@ -263,6 +263,34 @@ struct CacheBuf {
 
 }  // namespace vt
 
+namespace vt {
+// Finished cache buffers are parked for the next video of the same geometry.  The pool is bounded: a process that tiles videos
+// of many different resolutions would otherwise keep every size it has ever seen (memory torch's allocator cannot see).
+static size_t cache_pool_cap() {
+  static size_t cap = 0;
+  if (!cap) { const char* e = getenv("VT_CACHE_POOL_MB"); cap = (size_t)(e ? atoll(e) : 8192) << 20; if (!cap) cap = 1; }
+  return cap;
+}
+static void pool_put(vt_model* m, size_t bytes, void* ptr) {
+  m->cache_pool.insert({bytes, ptr});
+  m->cache_pool_bytes += bytes;
+  while (m->cache_pool_bytes > cache_pool_cap() && !m->cache_pool.empty()) {   // evict the largest buffers first
+    auto it = std::prev(m->cache_pool.end());
+    cudaFree(it->second);
+    m->cache_pool_bytes -= it->first;
+    m->cache_pool.erase(it);
+  }
+}
+static void* pool_take(vt_model* m, size_t bytes) {
+  auto it = m->cache_pool.find(bytes);
+  if (it == m->cache_pool.end()) return nullptr;
+  void* ptr = it->second;
+  m->cache_pool_bytes -= it->first;
+  m->cache_pool.erase(it);
+  return ptr;
+}
+}  // namespace vt
+
 struct vt_chunk_state {
   vt_model* m = nullptr;
   int prec = 0;
@@ -276,7 +304,7 @@ struct vt_chunk_state {
     for (auto& kv : caches)
       for (int i = 0; i < 2; ++i)
         if (kv.second.buf[i]) {
-          if (m && persist) m->cache_pool.insert({kv.second.bytes, kv.second.buf[i]});
+          if (m && persist) vt::pool_put(m, kv.second.bytes, kv.second.buf[i]);
           else cudaFree(kv.second.buf[i]);
         }
   }
@@ -407,15 +435,9 @@ struct Exec {
     if (c.bytes != bytes) {
       if (dry) { c.bytes = bytes; c.T = T; return &c; }
       for (int i = 0; i < 2; ++i) {
-        if (c.buf[i]) m->cache_pool.insert({c.bytes, c.buf[i]});
-        c.buf[i] = nullptr;
-        auto it = m->cache_pool.find(bytes);
-        if (it != m->cache_pool.end()) {
-          c.buf[i] = it->second;
-          m->cache_pool.erase(it);
-        } else if (!cuda(cudaMalloc(&c.buf[i], bytes), "cudaMalloc(causal cache)")) {
-          return nullptr;
-        }
+        if (c.buf[i]) pool_put(m, c.bytes, c.buf[i]);
+        c.buf[i] = pool_take(m, bytes);
+        if (!c.buf[i] && !cuda(cudaMalloc(&c.buf[i], bytes), "cudaMalloc(causal cache)")) return nullptr;
       }
       c.bytes = bytes; c.T = T; c.valid = false; c.cur = 0;
     }

@@ -112,6 +112,7 @@ struct vt_model {
   // device buffers of finished chunk states, reused by the next video (cudaMalloc/cudaFree per cache per video would
   // dominate the tiled path: ~100 caches per direction)
   std::multimap<size_t, void*> cache_pool;
+  size_t cache_pool_bytes = 0;         // bytes parked in cache_pool; capped (VT_CACHE_POOL_MB, default 8192): see pool_put()
   // whole-video tiling (vt_encode_video / vt_decode_video): the library's own copy stream and the events that order chunk
   // staging (stream `copy`) against chunk compute (the caller's stream)
   cudaStream_t copy_stream = nullptr;

@@ -482,10 +482,14 @@ __global__ void __launch_bounds__(kThreadsTb, 1) tblock_tc_kernel(const __grid_c
 //   * E2 double-buffers its store staging.
 // Per frame the operand ring now carries only the three n1 frames of G1 (96 KB), and the tensor pipe is the bound:
 //   MMA  : G1(t)  G2s(t-1)  G1(t+1)  G2s(t) ...      E1(t) normalises frame t while G2s(t-1) / G1(t+1) run.
-// Warp roles as above (0 producer, 1 MMA issuer -- leader CTA only --, 2 TMEM allocator, 3-6 E1, 7-10 E2).
+// Warp roles: 0 producer, 1 G1 issuer (leader) / H forwarder (peer), 2 TMEM allocator + G2s issuer (leader), 3-10 E1, 11-18 E2.  Each epilogue group has
+// EIGHT warps -- lane quarter x 64-channel half -- because a group of four (one warp per scheduler) was the measured bound:
+// ncu showed ~65% of the frame period spent issuing the LayerNorm/SiLU arithmetic of one 128-channel row per thread.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kWTile = 64 * 128;        // one resident weight tile: 64 rows (this CTA's half of N) x 64 bf16
 constexpr int kASlots = 3;
+constexpr int kEpi2 = 8;                     // warps per epilogue group (E1, E2): 4 lane quarters x 2 channel halves
+constexpr int kThreadsTb2 = (3 + 2 * kEpi2) * 32;
 
 struct Tb2Params {
   int B, T, H, W;
@@ -524,18 +528,18 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
   }
 }
 
-__global__ void __launch_bounds__(kThreadsTb, 1) tblock2_tc_kernel(const __grid_constant__ Tb2Maps maps, const Tb2Params p) {
+__global__ void __launch_bounds__(kThreadsTb2, 1) tblock2_tc_kernel(const __grid_constant__ Tb2Maps maps, const Tb2Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();                  // 0 = leader
-  // [resident W: 12 x 8 KB][H: kKc x 16 KB][A ring: kASlots x 16 KB][store staging: 4 warps x 2 x 4 KB][barriers][constants]
+  // [resident W: 12 x 8 KB][H: kKc x 16 KB][A ring: kASlots x 16 KB][store staging: 8 warps x 4 KB][barriers][constants][LN partial sums]
   const uint32_t w_base = smem_base;
   const uint32_t h_base = w_base + 12u * kWTile;
   const uint32_t a_base = h_base + kKc * kTile;
   const uint32_t stg_base = a_base + kASlots * kTile;
-  const uint32_t bar_base = stg_base + 4u * 2u * 4096u;
+  const uint32_t bar_base = stg_base + (uint32_t)kEpi2 * 4096u;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kASlots + s); };
   const uint32_t bar2 = bar_base + 16u * kASlots;
@@ -544,11 +548,13 @@ __global__ void __launch_bounds__(kThreadsTb, 1) tblock2_tc_kernel(const __grid_
   auto a2_full = [&](int s) { return bar2 + 40u + 8u * s; };
   auto a2_empty = [&](int s) { return bar2 + 64u + 8u * s; };
   const uint32_t tmem_slot = bar2 + 88u;
+  const uint32_t h_local = bar2 + 96u;
   const uint32_t const_base = bar2 + 128u;
+  const uint32_t stat_base = const_base + 6u * kC * 4u;     // LayerNorm partial sums: [E1|E2][parity][half][128] float2
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
   float* cst = reinterpret_cast<float*>(smem_gen + (const_base - smem_base));   // bias1 | g2 | b2 | bias2 | g3 | b3
 
-  for (int i = threadIdx.x; i < kC; i += kThreadsTb) {
+  for (int i = threadIdx.x; i < kC; i += kThreadsTb2) {
     cst[i] = p.bias1 ? p.bias1[i] : 0.f;
     cst[kC + i] = 0.5f * p.g2[i];          // SiLU in tanh form works on y/2
     cst[2 * kC + i] = 0.5f * p.b2[i];
@@ -564,9 +570,9 @@ __global__ void __launch_bounds__(kThreadsTb, 1) tblock2_tc_kernel(const __grid_
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kASlots; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(w_full, 1);
-    mbar_init(a1_full, 1); mbar_init(a1_empty, 8);     // E1 warps of both CTAs arrive on the leader's barrier
-    mbar_init(h_full, 8); mbar_init(h_empty, 1);
-    for (int s = 0; s < 3; ++s) { mbar_init(a2_full(s), 1); mbar_init(a2_empty(s), 8); }
+    mbar_init(a1_full, 1); mbar_init(a1_empty, 2 * kEpi2);     // E1 warps of both CTAs arrive on the leader's barrier
+    mbar_init(h_full, kEpi2 + 1); mbar_init(h_local, kEpi2); mbar_init(h_empty, 1);
+    for (int s = 0; s < 3; ++s) { mbar_init(a2_full(s), 1); mbar_init(a2_empty(s), 2 * kEpi2); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   constexpr uint32_t kTmemCols = 512;   // acc1 | acc2[3]
@@ -628,8 +634,11 @@ __global__ void __launch_bounds__(kThreadsTb, 1) tblock2_tc_kernel(const __grid_
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA) =====================
+  } else if (warp == 1 || warp == 2) {
+    // ===================== MMA issuers (leader CTA): warp 1 = G1, warp 2 = G2s =====================
+    // Two issuing warps so that neither convolution's waits (operand ring for G1, the normalised H tile for G2s) sit in front
+    // of the other one's MMAs; the tensor pipe executes whatever has been issued, in order.
+    // In the peer CTA warp 1 forwards "my half of H is written" to the leader (see E1).
     if (rank == 0) {
       const bool el = elect_one();
       const uint32_t idesc = make_idesc(kC, 256);
@@ -640,77 +649,92 @@ __global__ void __launch_bounds__(kThreadsTb, 1) tblock2_tc_kernel(const __grid_
         for (uint32_t j = 0; j < 8u; j += 2u) umma_f16_2sm_lohi(d, a_lo + j, hi_d, b_lo + j, hi_d, idesc, j == 0 ? acc : 1u);
       };
       auto wres = [&](int c, int a, int kc) { return desc_lo(w_base + (uint32_t)((c * 3 + a) * kKc + kc) * kWTile); };
-      int slot = 0;
-      uint32_t phase = 0;
-      long long f1 = 0, f2 = 0;    // global frame counters of G1 / G2s (barrier phases run across strips)
       mbar_wait(w_full, 0);
       tc_fence_after();
-      for (long long pt = pair0; pt < num_pairs; pt += pair_step) {
-        // G2s(u): H[u] (just normalised) into the accumulators of frames u (tap 2), u+1 (tap 1), u+2 (tap 0)
-        auto g2s = [&](int u) {
-          mbar_wait_cluster(h_full, (uint32_t)(f2 & 1));
-          tc_fence_after();
-          for (int j = 0; j < 3; ++j) {
-            if (u + j >= T) break;
-            const long long g = f2 + j;                       // global index of the target frame
-            const int as = (int)(g % 3);
-            const bool first = (j == 2) || (u == 0);          // first contribution to that frame's accumulator
-            if (first && g >= 3) {
-              mbar_wait(a2_empty(as), (uint32_t)(((g / 3) - 1) & 1));   // E2 has read the previous occupant (frame g-3)
-              tc_fence_after();
-            }
-            if (el) {
-              const uint32_t d = tmem_base + (uint32_t)kC + (uint32_t)as * kC;
-              for (int kc = 0; kc < kKc; ++kc) mma4(d, desc_lo(h_base + kc * kTile), wres(1, 2 - j, kc), (first && kc == 0) ? 0u : 1u);
-              if (j == 0) umma_commit_2sm(a2_full(as));       // frame u is complete
-            }
-          }
-          if (el) umma_commit_2sm(h_empty);
-          ++f2;
-        };
-        for (int t = 0; t < T; ++t) {
-          mbar_wait(a1_empty, (uint32_t)((f1 & 1) ^ 1));
-          tc_fence_after();
-          uint32_t accum = 0;
-          for (int a = 0; a < 3; ++a) {
-            if (t - 2 + a < 0) continue;
-            for (int kc = 0; kc < kKc; ++kc) {
-              mbar_wait(full_bar(slot), phase);
-              tc_fence_after();
-              if (el) {
-                mma4(tmem_base, desc_lo(a_base + slot * kTile), wres(0, a, kc), accum);
-                umma_commit_2sm(empty_bar(slot));
+      if (warp == 1) {
+        int slot = 0;
+        uint32_t phase = 0;
+        long long f1 = 0;            // global frame counter (barrier phases run across strips)
+        for (long long pt = pair0; pt < num_pairs; pt += pair_step) {
+          for (int t = 0; t < T; ++t, ++f1) {
+            mbar_wait(a1_empty, (uint32_t)((f1 & 1) ^ 1));
+            tc_fence_after();
+            uint32_t accum = 0;
+            for (int a = 0; a < 3; ++a) {
+              if (t - 2 + a < 0) continue;
+              for (int kc = 0; kc < kKc; ++kc) {
+                mbar_wait(full_bar(slot), phase);
+                tc_fence_after();
+                if (el) {
+                  mma4(tmem_base, desc_lo(a_base + slot * kTile), wres(0, a, kc), accum);
+                  umma_commit_2sm(empty_bar(slot));
+                }
+                accum = 1;
+                if (++slot == kASlots) { slot = 0; phase ^= 1u; }
               }
-              accum = 1;
-              if (++slot == kASlots) { slot = 0; phase ^= 1u; }
             }
+            if (el) umma_commit_2sm(a1_full);
           }
-          if (el) umma_commit_2sm(a1_full);
-          ++f1;
-          if (t >= 1) g2s(t - 1);
         }
-        g2s(T - 1);
+      } else {
+        long long f2 = 0;
+        for (long long pt = pair0; pt < num_pairs; pt += pair_step) {
+          // G2s(u): H[u] (just normalised) into the accumulators of frames u (tap 2), u+1 (tap 1), u+2 (tap 0)
+          for (int u = 0; u < T; ++u, ++f2) {
+            mbar_wait_cluster(h_full, (uint32_t)(f2 & 1));
+            tc_fence_after();
+            for (int j = 0; j < 3; ++j) {
+              if (u + j >= T) break;
+              const long long g = f2 + j;                       // global index of the target frame
+              const int as = (int)(g % 3);
+              const bool first = (j == 2) || (u == 0);          // first contribution to that frame's accumulator
+              if (first && g >= 3) {
+                mbar_wait(a2_empty(as), (uint32_t)(((g / 3) - 1) & 1));   // E2 has read the previous occupant (frame g-3)
+                tc_fence_after();
+              }
+              if (el) {
+                const uint32_t d = tmem_base + (uint32_t)kC + (uint32_t)as * kC;
+                for (int kc = 0; kc < kKc; ++kc) mma4(d, desc_lo(h_base + kc * kTile), wres(1, 2 - j, kc), (first && kc == 0) ? 0u : 1u);
+                if (j == 0) umma_commit_2sm(a2_full(as));       // frame u is complete
+              }
+            }
+            if (el) umma_commit_2sm(h_empty);
+          }
+        }
       }
+    } else if (warp == 1) {
+      // peer CTA: its E1 warps arrive on the local h_local; ONE thread then publishes with cluster-scope release on the
+      // leader's h_full (eight release.cluster arrives straight from the E1 warps cost ~17% of the frame period each)
+      long long f = 0;
+      for (long long pt = pair0; pt < num_pairs; pt += pair_step)
+        for (int t = 0; t < T; ++t, ++f) {
+          mbar_wait(h_local, (uint32_t)(f & 1));
+          if (lane == 0) mbar_arrive_remote_release(h_full, 0);
+          __syncwarp();
+        }
     }
-  } else if (warp >= 3 && warp < 7) {
+  } else if (warp >= 3 && warp < 3 + kEpi2) {
     // ===================== E1: h = acc1 + b1 -> H = bf16(silu(LN2(h))) =====================
+    // 8 warps: warp & 3 picks the TMEM lane quarter (32 positions), hf the 64-channel half (= one K tile of H)
     const int q = warp & 3;
+    const int hf = (warp - 3) >> 2;
     const int rr = q * 32 + lane;
     const int swz = lane & 7;
-    const float* bias1 = cst;
-    const float* gam = cst + kC;
-    const float* bet = cst + 2 * kC;
-    uint8_t* hrow = smem_gen + (h_base - smem_base) + (uint32_t)rr * 128u;
+    const float* bias1 = cst + hf * 64;
+    const float* gam = cst + kC + hf * 64;
+    const float* bet = cst + 2 * kC + hf * 64;
+    uint8_t* hrow = smem_gen + (h_base - smem_base) + (uint32_t)hf * kTile + (uint32_t)rr * 128u;
+    float2* st1 = reinterpret_cast<float2*>(smem_gen + (stat_base - smem_base));     // [parity][half][row]
     long long f = 0;
     for (long long pt = pair0; pt < num_pairs; pt += pair_step) {
       for (int t = 0; t < T; ++t, ++f) {
         mbar_wait(a1_full, (uint32_t)(f & 1));
         tc_fence_after();
-        const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * 64);
         uint64_t lsum2 = 0ull, lsq2 = 0ull;
-        uint32_t keep[kC / 2];
+        uint32_t keep[32];
 #pragma unroll
-        for (int c = 0; c < kC / 32; ++c) {
+        for (int c = 0; c < 2; ++c) {
           uint32_t v[32];
           tmem_ld32(tb + (uint32_t)(c * 32), v);
           tmem_ld_wait();
@@ -738,15 +762,23 @@ __global__ void __launch_bounds__(kThreadsTb, 1) tblock2_tc_kernel(const __grid_
           upk2(lsum2, a, b); lsum = a + b;
           upk2(lsq2, a, b); lsq = a + b;
         }
+        // the other half of the row is held by the warp 4 above / below: exchange partial sums through shared memory
+        st1[((int)(f & 1) * 2 + hf) * 128 + rr] = make_float2(lsum, lsq);
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");    // the two warps of this lane quarter only
+        {
+          const float2 o2 = st1[((int)(f & 1) * 2 + (hf ^ 1)) * 128 + rr];
+          lsum += o2.x;
+          lsq += o2.y;
+        }
         const float mean = lsum * (1.0f / kC);
         float var = fmaf(-mean, mean, lsq * (1.0f / kC));
         var = var < 0.f ? 0.f : var;
         const float rstd = rsqrtf(var + 1e-6f);
         const float nmr = -mean * rstd;
         const uint64_t rstd2 = pk2(rstd, rstd), nmr2 = pk2(nmr, nmr);
-        uint32_t o[kC / 2];
+        uint32_t o[32];
 #pragma unroll
-        for (int w2 = 0; w2 < kC / 4; ++w2) {   // 4 channels per step
+        for (int w2 = 0; w2 < 16; ++w2) {   // 4 channels per step
           const int ci = w2 * 4;
           const ulonglong2 gv = *reinterpret_cast<const ulonglong2*>(gam + ci);
           const ulonglong2 bv = *reinterpret_cast<const ulonglong2*>(bet + ci);
@@ -767,111 +799,116 @@ __global__ void __launch_bounds__(kThreadsTb, 1) tblock2_tc_kernel(const __grid_
         // the single H tile: free once G2s(f-1) has consumed the previous frame
         if (f >= 1) mbar_wait(h_empty, (uint32_t)((f - 1) & 1));
 #pragma unroll
-        for (int kc = 0; kc < kKc; ++kc)
-#pragma unroll
-          for (int g = 0; g < 8; ++g)
-            *reinterpret_cast<uint4*>(hrow + kc * kTile + ((g ^ swz) << 4)) =
-                make_uint4(o[kc * 32 + g * 4], o[kc * 32 + g * 4 + 1], o[kc * 32 + g * 4 + 2], o[kc * 32 + g * 4 + 3]);
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<uint4*>(hrow + ((g ^ swz) << 4)) = make_uint4(o[g * 4], o[g * 4 + 1], o[g * 4 + 2], o[g * 4 + 3]);
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive_remote_release(h_full, 0);
+        if (lane == 0) mbar_arrive(rank == 0 ? h_full : h_local);
       }
     }
-  } else if (warp >= 7) {
+  } else if (warp >= 3 + kEpi2) {
     // ===================== E2: out = acc2 + b2 + x (TMA store) [+ out2 = act(LN_next(out))] =====================
     const int q = warp & 3;
+    const int hf = (warp - 3 - kEpi2) >> 2;
     const int rr = q * 32 + lane;
     const int swz = lane & 7;
-    const float* bias2 = cst + 3 * kC;
-    const float* gam = cst + 4 * kC;
-    const float* bet = cst + 5 * kC;
-    const uint32_t wstg = stg_base + (uint32_t)(warp - 7) * 8192u;
-    uint8_t* wstg_gen = smem_gen + (stg_base - smem_base) + (uint32_t)(warp - 7) * 8192u;
+    const float* bias2 = cst + 3 * kC + hf * 64;
+    const float* gam = cst + 4 * kC + hf * 64;
+    const float* bet = cst + 5 * kC + hf * 64;
+    const uint32_t wstg = stg_base + (uint32_t)(warp - 3 - kEpi2) * 4096u;
+    uint8_t* wstg_gen = smem_gen + (wstg - smem_base);
+    float2* st2 = reinterpret_cast<float2*>(smem_gen + (stat_base - smem_base)) + 2 * 2 * 128;
     const int row0 = q * 32;
     const int qw0 = row0 % p.BW, qh0 = row0 / p.BW;
     const int dw = rr % p.BW, dh = rr / p.BW;
-    uint32_t nstore = 0;
     long long f = 0;
     for (long long pt = pair0; pt < num_pairs; pt += pair_step) {
       int b, h0, w0;
       bool live;
       decode(pt, b, h0, w0, live);
-      const bf16* xrow0 = p.x + ((((long long)(live ? b : 0) * T) * p.H + (h0 + dh)) * p.W + (w0 + dw)) * kC;
+      const bf16* xrow0 = p.x + ((((long long)(live ? b : 0) * T) * p.H + (h0 + dh)) * p.W + (w0 + dw)) * kC + hf * 64;
       const long long xframe = (long long)p.H * p.W * kC;
+      uint4 xv[8];
       for (int t = 0; t < T; ++t, ++f) {
         const int as = (int)(f % 3);
-        auto put64 = [&](const uint32_t* pk, const CUtensorMap* m, int c0) {
-          const uint32_t bsel = nstore & 1u;
-          if (lane == 0) tma_store_wait_read1();   // the store before the previous one (same buffer) has been read
+        auto put64 = [&](const uint32_t* pk, const CUtensorMap* m) {
+          if (lane == 0) tma_store_wait_read();    // this warp's previous store has read the staging buffer
           __syncwarp();
-          uint8_t* my = wstg_gen + bsel * 4096u + (uint32_t)lane * 128u;
+          uint8_t* my = wstg_gen + (uint32_t)lane * 128u;
 #pragma unroll
           for (int g = 0; g < 8; ++g)
             *reinterpret_cast<uint4*>(my + ((g ^ swz) << 4)) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
           fence_async_smem();
           __syncwarp();
           if (lane == 0) {
-            if (p.store_stream) tma_store_5d_stream(m, wstg + bsel * 4096u, c0, w0 + qw0, h0 + qh0, t, b);
-            else tma_store_5d(m, wstg + bsel * 4096u, c0, w0 + qw0, h0 + qh0, t, b);
+            if (p.store_stream) tma_store_5d_stream(m, wstg, hf * 64, w0 + qw0, h0 + qh0, t, b);
+            else tma_store_5d(m, wstg, hf * 64, w0 + qw0, h0 + qh0, t, b);
             tma_store_commit();
           }
-          ++nstore;
         };
-        // residual row of this thread's position: all 16 loads are issued BEFORE the wait for the accumulator, so their
-        // latency hides behind the frame period (issued one by one between the TMEM loads they cost ~1 us each: 12 us per frame)
-        const bf16* xr = xrow0 + (long long)t * xframe;
-        uint4 xv[kC / 8];
+        // residual (this thread's position, its 64 channels).  E2 is the slowest stage, so a load issued at the top of the
+        // frame is waited for in full (~2k cycles at 3 TB/s of DRAM traffic): the rows of frame t+1 are requested as soon as
+        // the registers of frame t are free (below), and only the first frame of a strip is loaded here
+        if (t == 0) {
 #pragma unroll
-        for (int k = 0; k < kC / 8; ++k) xv[k] = live ? __ldg(reinterpret_cast<const uint4*>(xr) + k) : make_uint4(0, 0, 0, 0);
+          for (int k = 0; k < 8; ++k) xv[k] = live ? __ldg(reinterpret_cast<const uint4*>(xrow0) + k) : make_uint4(0, 0, 0, 0);
+        }
         mbar_wait(a2_full(as), (uint32_t)((f / 3) & 1));
         tc_fence_after();
-        const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)kC + (uint32_t)as * kC;
+        const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)kC + (uint32_t)as * kC + (uint32_t)(hf * 64);
         uint64_t lsum2 = 0ull, lsq2 = 0ull;
-        uint32_t keep[kC / 2];
+        uint32_t keep[32];
 #pragma unroll
-        for (int i = 0; i < kKc; ++i) {
+        for (int hc = 0; hc < 2; ++hc) {
+          uint32_t v[32];
+          tmem_ld32(tb + (uint32_t)(hc * 32), v);
+          tmem_ld_wait();
 #pragma unroll
-          for (int hc = 0; hc < 2; ++hc) {
-            uint32_t v[32];
-            tmem_ld32(tb + (uint32_t)(i * 64 + hc * 32), v);
-            tmem_ld_wait();
+          for (int g = 0; g < 4; ++g) {   // 8 channels per step: one 16-byte residual load
+            float rv[8];
+            unpack8(xv[hc * 4 + g], rv);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {   // 8 channels per step: one 16-byte residual load
-              float rv[8];
-              unpack8(xv[i * 8 + hc * 4 + g], rv);
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const ulonglong2 bv = *reinterpret_cast<const ulonglong2*>(bias2 + i * 64 + hc * 32 + g * 8 + h * 4);
-                uint64_t a0 = add2(pk2(__uint_as_float(v[g * 8 + h * 4 + 0]), __uint_as_float(v[g * 8 + h * 4 + 1])), bv.x);
-                uint64_t a1 = add2(pk2(__uint_as_float(v[g * 8 + h * 4 + 2]), __uint_as_float(v[g * 8 + h * 4 + 3])), bv.y);
-                a0 = add2(a0, pk2(rv[h * 4 + 0], rv[h * 4 + 1]));
-                a1 = add2(a1, pk2(rv[h * 4 + 2], rv[h * 4 + 3]));
-                if (p.ln_out) {
-                  lsum2 = add2(lsum2, add2(a0, a1));
-                  lsq2 = fma2(a0, a0, lsq2);
-                  lsq2 = fma2(a1, a1, lsq2);
-                }
-                float f0, f1, f2_, f3;
-                upk2(a0, f0, f1);
-                upk2(a1, f2_, f3);
-                keep[i * 32 + hc * 16 + g * 4 + h * 2] = pack_bf16x2(f0, f1);
-                keep[i * 32 + hc * 16 + g * 4 + h * 2 + 1] = pack_bf16x2(f2_, f3);
+            for (int h = 0; h < 2; ++h) {
+              const ulonglong2 bv = *reinterpret_cast<const ulonglong2*>(bias2 + hc * 32 + g * 8 + h * 4);
+              uint64_t a0 = add2(pk2(__uint_as_float(v[g * 8 + h * 4 + 0]), __uint_as_float(v[g * 8 + h * 4 + 1])), bv.x);
+              uint64_t a1 = add2(pk2(__uint_as_float(v[g * 8 + h * 4 + 2]), __uint_as_float(v[g * 8 + h * 4 + 3])), bv.y);
+              a0 = add2(a0, pk2(rv[h * 4 + 0], rv[h * 4 + 1]));
+              a1 = add2(a1, pk2(rv[h * 4 + 2], rv[h * 4 + 3]));
+              if (p.ln_out) {
+                lsum2 = add2(lsum2, add2(a0, a1));
+                lsq2 = fma2(a0, a0, lsq2);
+                lsq2 = fma2(a1, a1, lsq2);
               }
+              float f0, f1, f2_, f3;
+              upk2(a0, f0, f1);
+              upk2(a1, f2_, f3);
+              keep[hc * 16 + g * 4 + h * 2] = pack_bf16x2(f0, f1);
+              keep[hc * 16 + g * 4 + h * 2 + 1] = pack_bf16x2(f2_, f3);
             }
           }
-          if (i == kKc - 1) {   // the accumulator has been read completely
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_remote(a2_empty(as), 0);
-          }
-          put64(&keep[i * 32], &maps.o, i * 64);
         }
+        tc_fence_before();     // the accumulator slice has been read completely
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(a2_empty(as), 0);
+        float lsum = 0.f, lsq = 0.f;
+        if (p.ln_out) {   // partial sums out first: the partner's arrive at the barrier below hides behind the store of `out`
+          float a, b2_;
+          upk2(lsum2, a, b2_); lsum = a + b2_;
+          upk2(lsq2, a, b2_); lsq = a + b2_;
+          st2[((int)(f & 1) * 2 + hf) * 128 + rr] = make_float2(lsum, lsq);
+        }
+        if (t + 1 < T) {
+          const bf16* xr = xrow0 + (long long)(t + 1) * xframe;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) xv[k] = live ? __ldg(reinterpret_cast<const uint4*>(xr) + k) : make_uint4(0, 0, 0, 0);
+        }
+        put64(keep, &maps.o);
         if (p.ln_out) {
-          float lsum, lsq;
+          asm volatile("bar.sync %0, 64;" ::"r"(5 + q) : "memory");
           {
-            float a, b2_;
-            upk2(lsum2, a, b2_); lsum = a + b2_;
-            upk2(lsq2, a, b2_); lsq = a + b2_;
+            const float2 o2 = st2[((int)(f & 1) * 2 + (hf ^ 1)) * 128 + rr];
+            lsum += o2.x;
+            lsq += o2.y;
           }
           const float mean = lsum * (1.0f / kC);
           float var = fmaf(-mean, mean, lsq * (1.0f / kC));
@@ -879,31 +916,28 @@ __global__ void __launch_bounds__(kThreadsTb, 1) tblock2_tc_kernel(const __grid_
           const float rstd = rsqrtf(var + 1e-6f);
           const float nmr = -mean * rstd;
           const uint64_t rstd2 = pk2(rstd, rstd), nmr2 = pk2(nmr, nmr);
+          uint32_t o[32];
 #pragma unroll
-          for (int i = 0; i < kKc; ++i) {
-            uint32_t o[32];
-#pragma unroll
-            for (int g = 0; g < 16; ++g) {
-              const ulonglong2 gv = *reinterpret_cast<const ulonglong2*>(gam + i * 64 + g * 4);
-              const ulonglong2 bv = *reinterpret_cast<const ulonglong2*>(bet + i * 64 + g * 4);
-              const uint32_t a2 = keep[i * 32 + 2 * g], b2 = keep[i * 32 + 2 * g + 1];
-              uint64_t y0 = fma2(fma2(pk2(bf16_lo(a2), bf16_hi(a2)), rstd2, nmr2), gv.x, bv.x);
-              uint64_t y1 = fma2(fma2(pk2(bf16_lo(b2), bf16_hi(b2)), rstd2, nmr2), gv.y, bv.y);
-              if (p.ln_out_silu) {
-                float h0_, h1, h2, h3;
-                upk2(y0, h0_, h1);
-                upk2(y1, h2, h3);
-                y0 = fma2(y0, pk2(tanh_approx(h0_), tanh_approx(h1)), y0);
-                y1 = fma2(y1, pk2(tanh_approx(h2), tanh_approx(h3)), y1);
-              }
-              float o0, o1, o2, o3;
-              upk2(y0, o0, o1);
-              upk2(y1, o2, o3);
-              o[2 * g] = pack_bf16x2(o0, o1);
-              o[2 * g + 1] = pack_bf16x2(o2, o3);
+          for (int g = 0; g < 16; ++g) {
+            const ulonglong2 gv = *reinterpret_cast<const ulonglong2*>(gam + g * 4);
+            const ulonglong2 bv = *reinterpret_cast<const ulonglong2*>(bet + g * 4);
+            const uint32_t a2 = keep[2 * g], b2 = keep[2 * g + 1];
+            uint64_t y0 = fma2(fma2(pk2(bf16_lo(a2), bf16_hi(a2)), rstd2, nmr2), gv.x, bv.x);
+            uint64_t y1 = fma2(fma2(pk2(bf16_lo(b2), bf16_hi(b2)), rstd2, nmr2), gv.y, bv.y);
+            if (p.ln_out_silu) {
+              float h0_, h1, h2, h3;
+              upk2(y0, h0_, h1);
+              upk2(y1, h2, h3);
+              y0 = fma2(y0, pk2(tanh_approx(h0_), tanh_approx(h1)), y0);
+              y1 = fma2(y1, pk2(tanh_approx(h2), tanh_approx(h3)), y1);
             }
-            put64(o, &maps.o2, i * 64);
+            float o0, o1, o2, o3;
+            upk2(y0, o0, o1);
+            upk2(y1, o2, o3);
+            o[2 * g] = pack_bf16x2(o0, o1);
+            o[2 * g + 1] = pack_bf16x2(o2, o3);
           }
+          put64(o, &maps.o2);
         }
       }
     }
@@ -974,7 +1008,8 @@ cudaError_t launch_tblock2(const bf16* n1, const bf16* x, const bf16* w1, const 
   p.g3 = gamma_out; p.b3 = beta_out;
   p.store_stream = ((double)B * T * H * W * kC * 2.0 > 256e6) ? 1 : 0;
   p.x = x;
-  const size_t smem = 1024 + 12 * (size_t)kWTile + (size_t)kKc * kTile + (size_t)kASlots * kTile + 4 * 2 * 4096 + 16 * kASlots + 128 + 6 * kC * 4 + 256;
+  const size_t smem = 1024 + 12 * (size_t)kWTile + (size_t)kKc * kTile + (size_t)kASlots * kTile + (size_t)kEpi2 * 4096 + 16 * kASlots + 128 + 6 * kC * 4 +
+                      2 * 2 * 2 * 128 * 8 + 256;
   Tb2Maps maps;
   auto enc_act = [&](CUtensorMap* m, const void* base, int bw, int bh) -> bool {
     cuuint64_t dims[5] = {(cuuint64_t)kC, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)B};
@@ -1023,7 +1058,7 @@ cudaError_t launch_tblock2(const bf16* n1, const bf16* x, const bf16* w1, const 
   ProfScope _ps("tblock_tc", 2.0 * 2.0 * M * 3 * kC * kC, 2.0 * M * kC * (3.0 + (p.ln_out ? 1.0 : 0.0)), s, det);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kThreadsTb);
+  cfg.blockDim = dim3(kThreadsTb2);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
