@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -388,11 +389,30 @@ def run_b200_arm(args, c):
             traffic = None
     roof = None
     if rank == 0:
+        # PROF_STEPS steps back to back under the profiler, long enough to be at the sustained (power-capped) clock and for
+        # nvidia-smi to sample it: the per-kernel sum, the event-timed wall time of the same steps and the clock during them,
+        # so that "step time - kernel sum" can be split into bubbles and clock
+        PROF_STEPS = max(5, int(math.ceil(2500.0 / (ms / args.steps))))   # >= 2.5 s: nvidia-smi's first second yields no samples
+        PROF_STEPS = max(5, min(PROF_STEPS, 8000 // max(launches // max(args.steps, 1), 1)))   # bound the events the profiler holds
+        samp2 = ClockSampler(local)
+        samp2.start()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         lib.vt_profile_start()
-        step_resident()
+        p0.record()
+        for _ in range(PROF_STEPS):
+            step_resident()
+        p1.record()
+        torch.cuda.synchronize(dev)
         buf = __import__("ctypes").create_string_buffer(1 << 16)
         n = lib.vt_profile_stop(buf, len(buf))
+        clocks_prof = samp2.stop()
+        prof_wall_ms = p0.elapsed_time(p1) / PROF_STEPS
         prof = json.loads(buf.value.decode()) if n > 0 else {}
+        for v in prof.values():   # per step
+            v["ms"] /= PROF_STEPS
+            v["flops"] /= PROF_STEPS
+            v["bytes"] /= PROF_STEPS
+            v["launches"] = int(round(v["launches"] / PROF_STEPS))
         tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
         dom = max(prof.items(), key=lambda kv: kv[1]["ms"])[0] if prof else None
         if dom is not None:
@@ -409,6 +429,10 @@ def run_b200_arm(args, c):
                     "whole_path": {"achieved": c["flops"] * B * args.steps / (ms / 1e3) / 1e12, "unit": "TFLOP/s per GPU (algorithmic)",
                                    "frac": c["flops"] * B * args.steps / (ms / 1e3) / 1e12 / peaks["tflops"]},
                     "sum_kernel_ms": tot_ms,
+                    "profiled": {"steps": PROF_STEPS, "wall_ms_per_step": prof_wall_ms, "sum_kernel_ms_per_step": tot_ms,
+                                 "sm_mhz": clocks_prof.get("sm_mhz"),
+                                 "note": "the same steps timed as a whole (CUDA events) and per launch (the library's profiler brackets every "
+                                         "launch with events, which serialises launches and adds ~2 event records per kernel)"},
                     "kernels_ms": {k: round(v["ms"], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}}
 
     # ---- CPU baseline + parity on one sample (rank 0, N == 1 only): PSNR for KL, code mismatches for FSQ
