@@ -271,3 +271,34 @@ def test_video_calls_with_host_staging_equal_device_path(case):
             torch.cuda.synchronize()
             st.close()
             assert torch.equal(torch.cat(zs, dim=2), z_dev)
+
+
+@pytest.mark.gpu
+def test_two_models_on_two_devices_in_one_process():
+    """Kernel attributes (227 KB dynamic shared memory) and the SM count are per device: a second model on another GPU of the
+    same process must launch every tcgen05 kernel there (a process-wide `static bool` guarded the opt-in)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two visible GPUs")
+    d, meta = load_golden("tiny_kl_v10")
+    sd, x = synth_weights(meta, d), synth_inputs(meta, d)
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        from vidtok_b200.compat_util import instantiate_from_config
+        model = instantiate_from_config(resolved_model_cfg(meta))
+        model.load_state_dict(sd, strict=False)
+        model = model.to(dev).eval()
+        for mode in ("exact", "bf16"):
+            model.precision = mode
+            with torch.no_grad(), torch.cuda.device(dev):
+                torch.manual_seed(meta["noise_seed"])
+                z, dec, _ = model(x.to(dev))
+            torch.cuda.synchronize(dev)
+            assert z.device == torch.device(dev)
+            outs.append((dev, mode, z.cpu(), dec.cpu()))
+    ref = torch.from_numpy(d["z"])
+    for dev, mode, z, dec in outs:
+        tol = TOL if mode == "exact" else 0.25
+        assert float((z - ref).abs().max()) <= tol, (dev, mode)
+    # same bits on both devices
+    assert torch.equal(outs[0][2], outs[2][2]) and torch.equal(outs[0][3], outs[2][3])
+    assert torch.equal(outs[1][2], outs[3][2]) and torch.equal(outs[1][3], outs[3][3])
