@@ -488,6 +488,7 @@ def run_b200_arm(args, c):
             "roofline": roof,
             "cpu_baseline": cpu,
             "psnr": parity,
+            "parity": parity,   # same record under the name VERDICT r1 asked for (PSNR delta; FSQ code mismatches for fsq488)
         }
         print(json.dumps(line), flush=True)
     if torch.distributed.is_initialized():
