@@ -33,7 +33,7 @@ GOLDEN_DIR = os.environ.get("VIDTOK_GOLDEN_OUT", os.path.join(ROOT, "tests", "go
 
 
 def model_yaml(version="v1_0", reg="kl", ch=16, ch_mult=(1, 2, 4, 4), z=4, norm="layernorm", interp=None,
-               levels=(8, 8, 8, 8, 8), causal=True):
+               levels=(8, 8, 8, 8, 8), causal=True, extra=None):
     mod = "model_3dcausal" + ("_v1_1" if version == "v1_1" else "")
     enc_cls, dec_cls = "EncoderCausal3DPadding", "DecoderCausal3DPadding"
     if not causal:   # configs/vidtok_kl_noncausal_488_4chn.yaml:12,30
@@ -45,6 +45,8 @@ def model_yaml(version="v1_0", reg="kl", ch=16, ch_mult=(1, 2, 4, 4), z=4, norm=
               init_pad_mode="replicate", norm_type=norm, fix_encoder=False, fix_decoder=False)
     if interp is not None:
         ep["interpolation_mode"] = interp
+    if extra:   # spatial_ds / spatial_us / tempo_ds / tempo_us / time_downsample_factor of the 444 / 288 / 888 configurations
+        ep.update(extra)
     if reg == "kl":
         rc = {"target": "vidtok.modules.regularizers.DiagonalGaussianRegularizer"}
     else:
@@ -70,6 +72,12 @@ CASES = {
     "tiny_kl_nc": (dict(causal=False), (1, 16, 32, 32), None, "full"),
     "tiny_fsq_nc": (dict(causal=False, reg="fsq", z=5), (2, 16, 32, 32), None, "full"),
     "mid_kl_nc": (dict(causal=False, ch=64), (1, 16, 64, 64), None, "full"),
+    # other compression ratios of the zoo: 4x4x4 (configs/vidtok_kl_causal_444_4chn.yaml:20-21), 2x8x8 (vidtok_kl_causal_288_8chn.yaml:20-22),
+    # 8x8x8 v1.1 (vidtok_v1_1/vidtok_fsq_causal_888_32768_v1_1.yaml:21-23)
+    "tiny_kl_444_v10": (dict(extra=dict(spatial_ds=[1, 2], spatial_us=[1, 2])), (1, 17, 32, 32), None, "full"),
+    "tiny_kl_288_v10": (dict(z=8, extra=dict(tempo_ds=[1], tempo_us=[2], time_downsample_factor=2)), (1, 17, 32, 32), None, "full"),
+    "tiny_fsq_888_v11": (dict(version="v1_1", reg="fsq", z=5, interp="trilinear",
+                              extra=dict(tempo_ds=[0, 1, 2], tempo_us=[1, 2, 3], time_downsample_factor=8)), (1, 17, 32, 32), None, "full"),
     "tiny_kl_v10": (dict(), (1, 17, 32, 32), None, "full"),
     "tiny_kl_v10_t8": (dict(), (2, 8, 32, 32), None, "full"),
     "tiny_fsq_v10": (dict(reg="fsq", z=5), (2, 17, 32, 32), None, "full"),

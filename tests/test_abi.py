@@ -36,9 +36,10 @@ def test_manifest_matches_reference_checkpoint_keys(case):
     want = "AutoencodingEngineV11" if "v1_1" in meta["model"]["target"] else "AutoencodingEngine"
     assert type(model).__name__ == want
     assert model.is_causal == ("noncausal" not in meta["model"]["params"]["encoder_config"]["target"])   # README.md:335
-    assert model.encoder.time_downsample_factor == 4
+    tdf = meta["model"]["params"]["encoder_config"]["params"]["time_downsample_factor"]
+    assert model.encoder.time_downsample_factor == tdf
     if "v1_1" in meta["model"]["target"]:
-        assert hasattr(model, "use_tiling") and model.t_chunk_dec == model.t_chunk_enc // 4 and model.use_overlap is False
+        assert hasattr(model, "use_tiling") and model.t_chunk_dec == model.t_chunk_enc // tdf and model.use_overlap is False
 
 
 def test_engine_surface_and_state_dict_roundtrip():
